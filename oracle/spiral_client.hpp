@@ -1,0 +1,354 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see spiral_oracle.hpp).
+//
+// Harness-only restatement of the Spiral CLIENT (keygen / query generation / response
+// decoding) so that the tests can build valid queries and decrypt server output the same way
+// the reference's own tests do (lib/spiral-rs/src/server.rs:787-1047).  The client is OUT OF
+// SCOPE as product; nothing here is ever shipped or benchmarked.
+//
+// Randomness: the reference draws from ChaCha20Rng::from_entropy() (client.rs:547,626), so no
+// reference stream exists to match; we use a seeded xoshiro256** so tests are reproducible.
+#pragma once
+#include "spiral_oracle.hpp"
+
+namespace orc {
+
+struct Rng {                       // xoshiro256**, seeded through splitmix64
+  u64 s[4];
+  explicit Rng(u64 seed) {
+    for (int i = 0; i < 4; i++) {
+      seed += 0x9E3779B97F4A7C15ULL;
+      u64 z = seed;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      s[i] = z ^ (z >> 31);
+    }
+  }
+  static u64 rotl(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+  u64 next() {
+    u64 result = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t; s[3] = rotl(s[3], 45);
+    return result;
+  }
+};
+
+// discrete_gaussian.rs:64-139
+struct DiscreteGaussian {
+  std::vector<u64> cdf_table;
+  i64 max_val;
+  explicit DiscreteGaussian(double noise_width) {
+    max_val = (i64)std::ceil(noise_width * 4.0);
+    std::vector<double> table;
+    double total = 0.0;
+    for (i64 i = -max_val; i <= max_val; i++) {
+      double pv = std::exp(-M_PI * (double)(i * i) / (noise_width * noise_width));
+      table.push_back(pv);
+      total += pv;
+    }
+    double cum = 0.0;
+    for (double pv : table) {
+      cum += pv / total;
+      double scaled = std::round(cum * 18446744073709551615.0);
+      cdf_table.push_back(scaled >= 18446744073709551615.0 ? ~(u64)0 : (u64)scaled);
+    }
+  }
+  u64 sample(u64 modulus, Rng& rng) const {
+    u64 sampled = rng.next();
+    size_t len = (size_t)(2 * max_val + 1);
+    u64 to_output = 0;
+    for (size_t i = len; i-- > 0;) {
+      i64 out_val = (i64)i - max_val;
+      if (out_val < 0) out_val += (i64)modulus;
+      if (!(sampled > cdf_table[i])) to_output = (u64)out_val;
+    }
+    return to_output;
+  }
+};
+
+inline PolyMatrix random_raw(const Params& p, size_t rows, size_t cols, Rng& rng) {   // poly.rs:105-117
+  PolyMatrix m = raw_zero(p, rows, cols);
+  for (auto& x : m.data) x = rng.next() % p.modulus;
+  return m;
+}
+inline PolyMatrix noise_raw(const Params& p, size_t rows, size_t cols, const DiscreteGaussian& dg, Rng& rng) {
+  PolyMatrix m = raw_zero(p, rows, cols);
+  for (auto& x : m.data) x = dg.sample(p.modulus, rng);
+  return m;
+}
+inline PolyMatrix neg_raw(const Params& p, const PolyMatrix& a) {
+  PolyMatrix r = raw_zero(p, a.rows, a.cols);
+  invert(p, r, a);
+  return r;
+}
+inline PolyMatrix single_poly(const Params& p, u64 val) {
+  PolyMatrix r = raw_zero(p, 1, 1);
+  r.data[0] = val;
+  return r;
+}
+// client.rs:332-338
+inline PolyMatrix matrix_with_identity(const Params& p, const PolyMatrix& m) {
+  PolyMatrix r = raw_zero(p, m.rows, m.rows + 1);
+  r.copy_into(m, 0, 0);
+  for (size_t i = 0; i < m.rows; i++) r.poly(i, 1 + i)[0] = 1;
+  return r;
+}
+
+struct Client {
+  const Params& p;
+  PolyMatrix sk_gsw, sk_reg, sk_gsw_full, sk_reg_full;
+  DiscreteGaussian dg;
+  Rng rng, rng_pub;
+  Client(const Params& params, u64 seed)
+      : p(params), sk_gsw(raw_zero(params, params.n, 1)), sk_reg(raw_zero(params, 1, 1)),
+        dg(params.noise_width), rng(seed), rng_pub(seed ^ 0xA5A5A5A55A5A5A5AULL) {
+    sk_gsw_full = matrix_with_identity(p, sk_gsw);
+    sk_reg_full = matrix_with_identity(p, sk_reg);
+  }
+  // client.rs:130-144 (HAMMING_WEIGHT = 256, :13)
+  void gen_ternary_mat(PolyMatrix& mat) {
+    const size_t hamming = 256;
+    for (size_t r = 0; r < mat.rows; r++)
+      for (size_t c = 0; c < mat.cols; c++) {
+        u64* pol = mat.poly(r, c);
+        for (size_t i = 0; i < p.poly_len; i++) pol[i] = 0;
+        for (size_t i = 0; i < hamming; i++) pol[i] = 1;
+        for (size_t i = hamming; i < 2 * hamming; i++) pol[i] = p.modulus - 1;
+        for (size_t i = p.poly_len; i-- > 1;) std::swap(pol[i], pol[rng.next() % (i + 1)]);
+      }
+  }
+  // client.rs:419-449
+  PolyMatrix get_regev_sample() {
+    PolyMatrix a = random_raw(p, 1, 1, rng_pub);
+    PolyMatrix e = noise_raw(p, 1, 1, dg, rng);
+    PolyMatrix b_p = mul(p, to_ntt_alloc(p, sk_reg), to_ntt_alloc(p, a));
+    PolyMatrix b = add_alloc(p, to_ntt_alloc(p, e), b_p);
+    PolyMatrix out = ntt_zero(p, 2, 1);
+    out.copy_into(to_ntt_alloc(p, neg_raw(p, a)), 0, 0);
+    out.copy_into(b, 1, 0);
+    return out;
+  }
+  PolyMatrix get_fresh_reg_public_key(size_t m) {
+    PolyMatrix out = ntt_zero(p, 2, m);
+    for (size_t i = 0; i < m; i++) out.copy_into(get_regev_sample(), 0, i);
+    return out;
+  }
+  // client.rs:401-417
+  PolyMatrix get_fresh_gsw_public_key(size_t m) {
+    PolyMatrix a = random_raw(p, 1, m, rng_pub);
+    PolyMatrix e = noise_raw(p, p.n, m, dg, rng);
+    PolyMatrix a_inv = neg_raw(p, a);
+    PolyMatrix b_p = mul(p, to_ntt_alloc(p, sk_gsw), to_ntt_alloc(p, a));
+    PolyMatrix b = add_alloc(p, to_ntt_alloc(p, e), b_p);
+    return stack(p, a_inv, from_ntt_alloc(p, b));
+  }
+  // client.rs:451-472
+  PolyMatrix encrypt_matrix_gsw(const PolyMatrix& ag) {
+    PolyMatrix pk = get_fresh_gsw_public_key(ag.cols);
+    return add_alloc(p, to_ntt_alloc(p, pk), ag.pad_top(p, 1));
+  }
+  PolyMatrix encrypt_matrix_reg(const PolyMatrix& a) {
+    PolyMatrix pk = get_fresh_reg_public_key(a.cols);
+    return add_alloc(p, pk, a.pad_top(p, 1));
+  }
+  PolyMatrix decrypt_matrix_reg(const PolyMatrix& a) { return mul(p, to_ntt_alloc(p, sk_reg_full), a); }   // :474-476
+  // client.rs:482-502
+  std::vector<PolyMatrix> generate_expansion_params(size_t num_exp, size_t m_exp) {
+    PolyMatrix g_exp_ntt = to_ntt_alloc(p, build_gadget(p, 1, m_exp));
+    std::vector<PolyMatrix> res;
+    for (size_t i = 0; i < num_exp; i++) {
+      size_t t = (p.poly_len / ((size_t)1 << i)) + 1;
+      PolyMatrix tau = raw_zero(p, 1, 1);
+      automorph(p, tau, sk_reg, t);
+      PolyMatrix prod = mul(p, to_ntt_alloc(p, tau), g_exp_ntt);
+      res.push_back(encrypt_matrix_reg(prod));
+    }
+    return res;
+  }
+  // client.rs:533-616
+  PublicParameters generate_keys() {
+    gen_ternary_mat(sk_gsw);
+    gen_ternary_mat(sk_reg);
+    sk_gsw_full = matrix_with_identity(p, sk_gsw);
+    sk_reg_full = matrix_with_identity(p, sk_reg);
+    PolyMatrix sk_reg_ntt = to_ntt_alloc(p, sk_reg), sk_gsw_ntt = to_ntt_alloc(p, sk_gsw);
+    PublicParameters pp;
+    PolyMatrix gadget_conv_ntt = to_ntt_alloc(p, build_gadget(p, 1, p.t_conv));
+    size_t num_packing = p.version == 0 ? p.n : 1;
+    for (size_t i = 0; i < num_packing; i++) {
+      PolyMatrix scaled = ntt_zero(p, 1, p.t_conv);
+      scalar_multiply(p, scaled, sk_reg_ntt, gadget_conv_ntt);
+      PolyMatrix ag = ntt_zero(p, p.n, p.t_conv);
+      ag.copy_into(scaled, i, 0);
+      pp.v_packing.push_back(encrypt_matrix_gsw(ag));
+    }
+    if (p.version > 0) {
+      PolyMatrix scaled = mul(p, sk_gsw_ntt, gadget_conv_ntt);
+      pp.v_packing.push_back(encrypt_matrix_gsw(shift_rows_by_one(p, scaled)));
+    }
+    if (p.expand_queries) {
+      pp.v_expansion_left = generate_expansion_params(p.g(), p.t_exp_left);
+      if (p.version == 0 || p.t_exp_right != p.t_exp_left) {
+        pp.v_expansion_right = generate_expansion_params(p.stop_round() + 1, p.t_exp_right);
+        pp.has_right = true;
+      }
+      PolyMatrix g_conv = build_gadget(p, 2, 2 * p.t_conv);
+      PolyMatrix sk_sq = mul(p, sk_reg_ntt, sk_reg_ntt);
+      PolyMatrix conv = ntt_zero(p, 2, 2 * p.t_conv);
+      for (size_t i = 0; i < 2 * p.t_conv; i++) {
+        PolyMatrix sigma;
+        if (i % 2 == 0) sigma = mul(p, sk_sq, to_ntt_alloc(p, single_poly(p, g_conv.poly(0, i)[0])));
+        else sigma = mul(p, sk_reg_ntt, to_ntt_alloc(p, single_poly(p, g_conv.poly(1, i)[0])));
+        conv.copy_into(encrypt_matrix_reg(sigma), 0, i);
+      }
+      pp.v_conversion.push_back(conv);
+    }
+    return pp;
+  }
+  // client.rs:618-721
+  Query generate_query(size_t idx_target) {
+    size_t further_dims = p.db_dim_2;
+    size_t idx_dim0 = idx_target / ((size_t)1 << further_dims);
+    size_t idx_further = idx_target % ((size_t)1 << further_dims);
+    u64 scale_k = p.modulus / p.pt_modulus;
+    size_t bits_per = get_bits_per(p, p.t_gsw);
+    Query q;
+    if (p.expand_queries) {
+      PolyMatrix sigma = raw_zero(p, 1, 1);
+      u64 inv_first = 0, inv_rest = 0;
+      invert_uint_mod((u64)1 << p.g(), p.modulus, inv_first);
+      invert_uint_mod((u64)1 << (p.stop_round() + 1), p.modulus, inv_rest);
+      if (p.db_dim_2 == 0) {
+        for (size_t i = 0; i < ((size_t)1 << p.db_dim_1); i++) if (i == idx_dim0) sigma.data[i] = scale_k;
+        for (size_t i = 0; i < p.poly_len; i++) sigma.data[i] = multiply_uint_mod(sigma.data[i], inv_first, p.modulus);
+      } else {
+        for (size_t i = 0; i < ((size_t)1 << p.db_dim_1); i++) if (i == idx_dim0) sigma.data[2 * i] = scale_k;
+        for (size_t i = 0; i < further_dims; i++) {
+          u64 mask = (u64)1 << i;
+          bool bit = ((u64)idx_further & mask) == mask;
+          for (size_t j = 0; j < p.t_gsw; j++) {
+            size_t idx = i * p.t_gsw + j;
+            sigma.data[2 * idx + 1] = bit ? ((u64)1 << (bits_per * j)) : 0;
+          }
+        }
+        for (size_t i = 0; i < p.poly_len / 2; i++) {
+          sigma.data[2 * i] = multiply_uint_mod(sigma.data[2 * i], inv_first, p.modulus);
+          sigma.data[2 * i + 1] = multiply_uint_mod(sigma.data[2 * i + 1], inv_rest, p.modulus);
+        }
+      }
+      q.ct = from_ntt_alloc(p, encrypt_matrix_reg(to_ntt_alloc(p, sigma)));
+    } else {
+      size_t num_expanded = (size_t)1 << p.db_dim_1;
+      std::vector<PolyMatrix> reg_cts;
+      for (size_t i = 0; i < num_expanded; i++) {
+        u64 value = (i == idx_dim0) ? scale_k : 0;
+        reg_cts.push_back(encrypt_matrix_reg(to_ntt_alloc(p, single_poly(p, value))));
+      }
+      q.v_buf.assign(num_expanded * 2 * p.poly_len, 0);
+      reorient_reg_ciphertexts(p, q.v_buf.data(), reg_cts);
+      for (size_t i = 0; i < further_dims; i++) {
+        u64 bit = ((u64)idx_further >> i) & 1;
+        PolyMatrix ct_gsw = ntt_zero(p, 2, 2 * p.t_gsw);
+        for (size_t j = 0; j < p.t_gsw; j++) {
+          u64 value = ((u64)1 << (bits_per * j)) * bit;
+          PolyMatrix sigma_ntt = to_ntt_alloc(p, single_poly(p, value));
+          PolyMatrix prod = mul(p, to_ntt_alloc(p, sk_reg), sigma_ntt);
+          ct_gsw.copy_into(encrypt_matrix_reg(prod), 0, 2 * j);
+          ct_gsw.copy_into(encrypt_matrix_reg(sigma_ntt), 0, 2 * j + 1);
+        }
+        q.v_ct.push_back(from_ntt_alloc(p, ct_gsw));
+      }
+    }
+    return q;
+  }
+  // client.rs:732-810.  Returns the decoded (instances*n) x n plaintext matrix (mod p), i.e.
+  // `result` before `to_vec` (:809).
+  PolyMatrix decode_response_poly(const uint8_t* data) {
+    u64 pm = p.pt_modulus;
+    u64 q1 = 4 * p.pt_modulus;
+    size_t q1_bits = log2_ceil(q1);
+    u64 q2 = Q2_VALUES[p.q2_bits];
+    size_t q2_bits = p.q2_bits;
+    Params q2p = params_init(p.poly_len, {q2}, p.noise_width, p.n, p.pt_modulus, p.q2_bits, p.t_conv, p.t_exp_left,
+                             p.t_exp_right, p.t_gsw, p.expand_queries, p.db_dim_1, p.db_dim_2, p.instances,
+                             p.db_item_size, p.version);
+    PolyMatrix sk_q2 = raw_zero(q2p, p.n, 1);
+    for (size_t i = 0; i < p.poly_len * p.n; i++) sk_q2.data[i] = recenter(sk_gsw.data[i], p.modulus, q2);
+    PolyMatrix sk_q2_ntt = to_ntt_alloc(q2p, sk_q2);
+    PolyMatrix result = raw_zero(p, p.instances * p.n, p.n);
+    size_t bit_offs = 0;
+    size_t N = p.poly_len;
+    for (size_t inst = 0; inst < p.instances; inst++) {
+      PolyMatrix first_row = raw_zero(q2p, 1, p.n);
+      PolyMatrix rest_rows = raw_zero(p, p.n, p.n);
+      for (size_t i = 0; i < p.n * N; i++) { first_row.data[i] = read_arbitrary_bits(data, bit_offs, q2_bits); bit_offs += q2_bits; }
+      for (size_t i = 0; i < p.n * p.n * N; i++) { rest_rows.data[i] = read_arbitrary_bits(data, bit_offs, q1_bits); bit_offs += q1_bits; }
+      PolyMatrix first_ntt = to_ntt_alloc(q2p, first_row);
+      PolyMatrix sk_prod = from_ntt_alloc(q2p, mul(q2p, sk_q2_ntt, first_ntt));
+      i64 q1_i = (i64)q1, q2_i = (i64)q2;
+      i128 p_i = (i128)pm;
+      for (size_t i = 0; i < p.n * p.n * N; i++) {
+        i64 val_first = (i64)sk_prod.data[i];
+        if (val_first >= q2_i / 2) val_first -= q2_i;
+        i64 val_rest = (i64)rest_rows.data[i];
+        if (val_rest >= q1_i / 2) val_rest -= q1_i;
+        i64 denom = (i64)(q2 * (q1 / pm));
+        i64 r = val_first * q1_i + val_rest * q2_i;
+        i64 sign = r >= 0 ? 1 : -1;
+        i128 res = ((i128)(r + sign * (denom / 2))) / (i128)denom;
+        res = (res + ((i128)denom / p_i) * p_i + 2 * p_i) % p_i;
+        result.data[inst * p.n * p.n * N + i] = (u64)res;
+      }
+    }
+    return result;
+  }
+};
+
+// poly.rs:213-235 (PolyMatrixRaw::to_vec)
+inline std::vector<uint8_t> raw_to_vec(const Params& p, const PolyMatrix& m, size_t modulus_bits, size_t num_coeffs) {
+  size_t sz_bits = m.rows * m.cols * num_coeffs * modulus_bits;
+  size_t sz_bytes = (sz_bits + 7) / 8 + 32;
+  size_t rounded = ((sz_bytes + 15) / 16) * 16;
+  std::vector<uint8_t> data(rounded, 0);
+  size_t bit_offs = 0;
+  for (size_t r = 0; r < m.rows; r++)
+    for (size_t c = 0; c < m.cols; c++) {
+      for (size_t z = 0; z < num_coeffs; z++) {
+        write_arbitrary_bits(data.data(), m.poly(r, c)[z], bit_offs, modulus_bits);
+        bit_offs += modulus_bits;
+      }
+      bit_offs = (bit_offs / 8) * 8;
+    }
+  return data;
+}
+
+// server.rs:223-275 with a seeded counter PRNG instead of the reference's unseeded SmallRng.
+// Plaintext coefficient (instance,trial,item i, z) = splitmix64(seed, index) % p — the same
+// generator the GPU-side DB loader uses, so full-size DBs never have to be built on the CPU.
+inline u64 splitmix64_at(u64 seed, u64 index) {
+  u64 z = seed + (index + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+inline u64 db_plain_coeff(const Params& p, u64 seed, size_t slice, size_t item, size_t z) {
+  u64 index = ((u64)slice * p.num_items() + item) * p.poly_len + z;
+  return splitmix64_at(seed, index) % p.pt_modulus;
+}
+inline void generate_db(const Params& p, u64 seed, u64* db /* [slices][z][ii][j] */) {
+  size_t trials = p.n * p.n, dim0 = (size_t)1 << p.db_dim_1, num_per = (size_t)1 << p.db_dim_2;
+  size_t num_items = dim0 * num_per, N = p.poly_len;
+  for (size_t slice = 0; slice < p.instances * trials; slice++) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < num_items; i++) {
+      size_t ii = i % num_per, j = i / num_per;
+      PolyMatrix item = raw_zero(p, 1, 1);
+      for (size_t z = 0; z < N; z++)
+        item.data[z] = recenter_mod(db_plain_coeff(p, seed, slice, i, z), p.pt_modulus, p.modulus);
+      PolyMatrix nt = to_ntt_alloc(p, item);
+      for (size_t z = 0; z < N; z++)
+        db[((slice * N + z) * num_per + ii) * dim0 + j] = nt.data[z] | (nt.data[N + z] << 32);
+    }
+  }
+}
+
+}  // namespace orc

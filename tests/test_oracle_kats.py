@@ -1,0 +1,204 @@
+"""Pin the CPU oracle against every known-answer test the reference holds for this path
+(SURVEY.md §8c).  Each test cites the reference test it restates."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from oracle_lib import LIB
+
+Q0, Q1 = 268369921, 249561089
+Q = Q0 * Q1
+
+
+@pytest.fixture(scope="module")
+def P():
+    # util.rs:63-82 get_test_params (n2 nu 9/6 ... t_exp 8/56)
+    return O.Params(n=2, nu_1=9, nu_2=6, p=256, q2_bits=20, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=56,
+                    instances=1, db_item_size=2048, version=0)
+
+
+def test_build_ntt_tables_correct(P):
+    # ntt.rs:379-398
+    assert P.ntt_table(0, 2)[0] == 134184961
+    assert P.ntt_table(0, 2)[1] == 96647580
+    x = 0
+    for m in range(2):
+        for w in range(4):
+            t = P.ntt_table(m, w)
+            assert t.size == 2048
+            x ^= int(np.bitwise_xor.reduce(t))
+    assert x == 519370102
+
+
+def test_minimal_primitive_roots():
+    # SURVEY A.1 (number_theory.rs:41-55)
+    assert LIB.orc_min_primitive_root(4096, Q0) == 66687
+    assert LIB.orc_min_primitive_root(4096, Q1) == 158221
+
+
+def test_ntt_forward_correct(P):
+    # ntt.rs:400-409
+    v = np.zeros(2 * 2048, dtype=np.uint64)
+    v[0] = 100
+    v[2048] = 100
+    out = P.ntt_forward(v)
+    assert out[50] == 100 and out[2048 + 50] == 100
+    assert np.all(out == 100)
+
+
+def test_ntt_inverse_correct(P):
+    # ntt.rs:411-423
+    v = np.full(2 * 2048, 100, dtype=np.uint64)
+    out = P.ntt_inverse(v)
+    assert out[0] == 100 and out[2048] == 100
+    assert out[50] == 0 and out[2048 + 50] == 0
+
+
+def test_ntt_roundtrip(P):
+    # ntt.rs:425-443
+    rng = np.random.default_rng(1)
+    v = np.concatenate([rng.integers(0, Q0, 2048, dtype=np.uint64), rng.integers(0, Q1, 2048, dtype=np.uint64)])
+    assert np.array_equal(P.ntt_inverse(P.ntt_forward(v)), v)
+
+
+def test_ntt_matches_definition(P):
+    # out[k] = sum_i a_i psi^{(2 bitrev(k)+1) i}, checked directly for a few k
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, Q0, 2048, dtype=np.uint64)
+    v = np.concatenate([a, a % np.uint64(Q1)])
+    out = P.ntt_forward(v)
+    for q, psi, off in ((Q0, 66687, 0), (Q1, 158221, 2048)):
+        for k in (0, 1, 5, 1000, 2047):
+            br = int(format(k, "011b")[::-1], 2)
+            e = 2 * br + 1
+            w = pow(psi, e, q)
+            acc, pw = 0, 1
+            for i in range(2048):
+                acc = (acc + int(v[off + i]) * pw) % q
+                pw = pw * w % q
+            assert out[off + k] == acc
+
+
+def test_calc_index_correct():
+    # ntt.rs:445-449
+    def ci(i, l):
+        a = np.array(i, dtype=np.uint64)
+        b = np.array(l, dtype=np.uint64)
+        return LIB.orc_calc_index(O._p64(a), O._p64(b), len(i))
+    assert ci([2, 3, 4], [10, 10, 100]) == 2304
+    assert ci([2, 3, 4], [3, 5, 7]) == 95
+
+
+def test_get_barrett_crs_correct(P):
+    # arith.rs:476-490
+    out = np.zeros(2, dtype=np.uint64)
+    for m, exp in ((Q0, (16144578669088582089, 68736257792)), (Q1, (10966983149909726427, 73916747789)),
+                   (Q, (7906011006380390721, 275))):
+        LIB.orc_barrett_crs(O.C.c_uint64(m), O._p64(out))
+        assert (int(out[0]), int(out[1])) == exp
+    assert (P.cr0_0, P.cr1_0) == (16144578669088582089, 68736257792)
+    assert (P.cr0_mod, P.cr1_mod) == (7906011006380390721, 275)
+    assert P.modulus == 66974689739603969  # arith.rs:494
+
+
+def test_barrett_reduction_u128_raw_correct():
+    # arith.rs:492-508 fixed vectors + REAL randomised checks (the reference's `combine` is vacuous)
+    f = lambda v: LIB.orc_barrett_reduction_u128_raw(Q, 7906011006380390721, 275, v & (2**64 - 1), v >> 64)
+    assert f(Q) == 0
+    assert f(Q + 1) == 1
+    assert f(Q * 7 + 5) == 5
+    rng = np.random.default_rng(3)
+    for _ in range(20000):
+        # the range crt_compose_2 produces: x*A + y*B with x,y < 2^28, A,B < q  (< 2^85)
+        v = int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**23)) + int(rng.integers(0, 2**62))
+        assert f(v) == v % Q
+
+
+def test_barrett_raw_u64_correct():
+    # arith.rs:510-520, plus per-modulus constants
+    rng = np.random.default_rng(4)
+    for _ in range(20000):
+        v = int(rng.integers(0, 2**64, dtype=np.uint64))
+        assert LIB.orc_barrett_raw_u64(v, 275, Q) == v % Q
+        assert LIB.orc_barrett_raw_u64(v, 68736257792, Q0) == v % Q0
+        assert LIB.orc_barrett_raw_u64(v, 73916747789, Q1) == v % Q1
+
+
+def test_div2_uint_mod_correct():
+    # arith.rs:456-459
+    assert LIB.orc_div2_uint_mod(3, 7) == 5
+
+
+def test_multiply_negacyclic(P):
+    # poly.rs:731-743: (100 X) * (7 X) = 700 X^2
+    a = np.zeros(2048, dtype=np.uint64)
+    b = np.zeros(2048, dtype=np.uint64)
+    a[1] = 100
+    b[1] = 7
+    prod = P.from_ntt(P.multiply(P.to_ntt(a), P.to_ntt(b), 1, 1, 1))
+    exp = np.zeros(2048, dtype=np.uint64)
+    exp[2] = 700
+    assert np.array_equal(prod, exp)
+    # wrap-around sign: X^2047 * X = -1
+    a[:] = 0
+    b[:] = 0
+    a[2047] = 1
+    b[1] = 1
+    prod = P.from_ntt(P.multiply(P.to_ntt(a), P.to_ntt(b), 1, 1, 1))
+    assert prod[0] == Q - 1 and np.all(prod[1:] == 0)
+
+
+def test_gadget_invert_is_correct(P):
+    # gadget.rs:78-95
+    mat = np.zeros(2 * 2048, dtype=np.uint64)
+    mat[37] = 3
+    mat[2048 + 37] = 6
+    log_q = P.modulus_log2
+    assert log_q == 56
+    r = P.gadget_invert(mat, 2, 1, 2 * log_q).reshape(2 * log_q, 2048)
+    assert (r[0, 37], r[2, 37], r[4, 37]) == (1, 1, 0)
+    assert (r[1, 37], r[3, 37], r[5, 37], r[7, 37]) == (0, 1, 1, 0)
+
+
+def test_bits_per(P):
+    # SURVEY A.7 (gadget.rs:3-9)
+    for t, b in ((8, 8), (7, 9), (4, 15), (3, 19), (5, 12), (10, 6), (56, 1)):
+        assert P.bits_per(t) == b
+
+
+def test_bit_io_roundtrip():
+    # util.rs:410-428
+    data = np.zeros(64, dtype=np.uint8)
+    LIB.orc_write_bits(O._p8(data), O.C.c_uint64(33), 0, 20)
+    LIB.orc_write_bits(O._p8(data), O.C.c_uint64(0xABCDE), 20, 20)
+    LIB.orc_write_bits(O._p8(data), O.C.c_uint64(0x1FFFFF), 50, 21)   # straddles a 64-bit word
+    assert LIB.orc_read_bits(O._p8(data), 0, 20) == 33
+    assert LIB.orc_read_bits(O._p8(data), 20, 20) == 0xABCDE
+    assert LIB.orc_read_bits(O._p8(data), 50, 21) == 0x1FFFFF
+
+
+def test_params_derived_quantities():
+    # util.rs:361-398 (params_from_json == Params::init) — derived fields for the e2e parameter files
+    e0 = O.Params.named("E0")
+    assert (e0.g, e0.stop_round) == (10, 6)          # t_gsw*nu_2 + dim0 = 40+512 -> 10 ; ceil(log2 40) = 6
+    assert e0.query_bytes == 32 + 2048 * 8
+    e1 = O.Params.named("E1")
+    assert (e1.g, e1.stop_round) == (10, 6)          # 35+512 ; ceil(log2 35)
+    # setup_bytes (params.rs:146-167): v1 with t_exp_left == t_exp_right drops the right matrices
+    assert e1.setup_bytes == 32 + (2 * 2 * 3 + 10 * 5 + 0 + 2 * 3) * 2048 * 8
+    assert e0.setup_bytes == 32 + (4 * 4 * 4 + 10 * 8 + 7 * 56 + 2 * 4) * 2048 * 8
+
+
+def test_rescale_matches_rounding():
+    # arith.rs:429-444: round-half-away-from-zero of centered(a)*out/in, lifted to [0,out)
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    for out_mod in (1024, 786433, 3604481):
+        for _ in range(2000):
+            a = int(rng.integers(0, Q))
+            c = a - Q if a >= Q // 2 else a
+            # the reference adds sign*(in/2) with in/2 floored, then truncates toward zero
+            sign = 1 if c >= 0 else -1
+            num = c * out_mod + sign * (Q // 2)
+            r = abs(num) // Q * (1 if num >= 0 else -1)
+            assert LIB.orc_rescale(a, Q, out_mod) == r % out_mod

@@ -1,0 +1,80 @@
+"""Semantic (decrypt-and-compare) tests of the CPU oracle, mirroring the reference's own stage
+and full-protocol tests (lib/spiral-rs/src/server.rs:787-1047)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+def _full_protocol(name, idx, seed=7, **over):
+    P = O.Params.named(name, **over)
+    cl = O.Client(P, seed)
+    pp = cl.generate_keys()
+    q = cl.generate_query(idx)
+    db = P.generate_db(0xB1755)
+    resp, d = P.process_query(pp, q, db, dump=True)
+    assert resp.size == P.response_bytes()
+    dec = cl.decode_response(resp)
+    assert np.array_equal(dec, P.db_plain_item(0xB1755, idx))
+    return P, cl, pp, q, db, resp, d
+
+
+@pytest.mark.parametrize("name,idx", [("T", 77), ("T1", 200), ("T0", 131)])
+def test_full_protocol_is_correct(name, idx):
+    # server.rs:995-1048 full_protocol_is_correct (+ version-1 packing, lib/server pack.rs:45-98)
+    _full_protocol(name, idx)
+
+
+def test_full_protocol_direct_upload():
+    # util.rs:139-153 no-expansion mode (direct_upload): query = v_buf + v_ct
+    _full_protocol("T", 19, expand_queries=False)
+
+
+def test_multiply_reg_by_database_is_correct():
+    # server.rs:870-925: one-hot Regev selector over dim0, decrypt row target%num_per
+    P = O.Params.named("T")
+    cl = O.Client(P, 11)
+    cl.generate_keys()
+    db = P.generate_db(5)
+    target = 0x2B % (P.dim0 * P.num_per) + 100
+    t0, t1 = target // P.num_per, target % P.num_per
+    scale_k = P.modulus // P.p
+    cts = []
+    for i in range(P.dim0):
+        sigma = np.zeros(P.N, dtype=np.uint64)
+        sigma[0] = scale_k if i == t0 else 0
+        cts.append(cl.encrypt_reg(sigma).reshape(2, 2, P.N))
+    cts = np.stack(cts)  # [j][r][n][z]
+    v = (cts[:, :, 0, :] | (cts[:, :, 1, :] << np.uint64(32))).transpose(2, 0, 1).copy()  # [z][j][r]
+    out = P.multiply_reg_by_database(db[: P.dim0 * P.num_per * P.N], v.reshape(-1))
+    dec = cl.decrypt_reg(out.reshape(P.num_per, 4 * P.N)[t1])
+    resc = np.array([O.LIB.orc_rescale(int(x), P.modulus, P.p) for x in dec], dtype=np.uint64)
+    plain = P.db_plain_item(5, target).reshape(P.n * P.n, P.N)[0]
+    assert np.array_equal(resc, plain)
+
+
+def test_fold_matches_process_query_dump():
+    # the fold stage inside process_query equals the stand-alone fold on the same inputs
+    P, cl, pp, q, db, resp, d = _full_protocol("T", 5)
+    inter = P.from_ntt(d["first_mult"])          # num_per x (2x1) raw
+    folded = P.fold_ciphertexts(inter, d["v_folding"], d["v_folding_neg"])
+    assert np.array_equal(folded[: 2 * P.N], d["folded"][: 2 * P.N])
+    assert np.array_equal(P.get_v_folding_neg(d["v_folding"]), d["v_folding_neg"])
+    # sparse-server zero shortcut (lib/server fold.rs:37-43) is inert on a dense DB
+    folded_s = P.fold_ciphertexts(inter, d["v_folding"], d["v_folding_neg"], sparse=True)
+    assert np.array_equal(folded_s, folded)
+
+
+def test_dpir_matvec_matches_numpy():
+    # kernels.rs:14-113 vs a plain numpy evaluation of SURVEY A.12; rows not a multiple of 8
+    rng = np.random.default_rng(9)
+    rows, cols = 43, 37
+    a = rng.integers(0, 2**30, rows * cols, dtype=np.uint32)
+    b = rng.integers(0, 2**32, 3 * cols, dtype=np.uint32)
+    out = O.dpir_matvec_packed(a, b, rows, cols)
+    A = a.reshape(rows, cols).astype(np.uint64)
+    B = b.astype(np.uint64).reshape(cols, 3)
+    exp = np.zeros(rows, dtype=np.uint64)
+    for m in range(3):
+        exp += (((A >> np.uint64(10 * m)) & np.uint64(1023)) * B[:, m][None, :]).sum(axis=1)
+    assert np.array_equal(out, (exp & np.uint64(0xFFFFFFFF)).astype(np.uint32))
