@@ -1,0 +1,154 @@
+/* b200pir — C ABI of the B200-native server-side PIR query path.
+ *
+ * This is the drop-in boundary: every entry point replaces one Rust function of blyssprivacy/sdk
+ * (reference @ fdb7206); the Rust host code keeps its own signature and forwards here through a thin
+ * `extern "C"` shim.  The reference has no FFI of its own, so the ABI flattens
+ * the reference's argument types to plain pointers + sizes:
+ *
+ *   PolyMatrixRaw   rows x cols polys, each 2048 u64 coefficients            (lib/spiral-rs/src/poly.rs:59-64)
+ *   PolyMatrixNTT   rows x cols polys, each [crt(2)][2048] u64 residues     (poly.rs:66-71, :263-265)
+ *   db: &[u64]      [instance][trial][z][ii][j] words = q0-residue | q1-residue << 32   (server.rs:263-269)
+ *   v_firstdim      [z][j][r] words, same packing                            (util.rs:343-350)
+ *
+ * All buffers are HOST memory owned by the caller unless the name says `_dev`.  Outputs are caller
+ * allocated.  Nothing unwinds across the boundary: every function returns 0 on success or a negative
+ * code (B200PIR_E_*), and b200pir_last_error() returns the message for the calling thread.
+ * Concurrent calls on one context are serialised internally (one CUDA stream per context); use one
+ * context per host thread / GPU for concurrency.
+ */
+#ifndef B200PIR_H
+#define B200PIR_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PIR_E_BADARG (-1)
+#define B200PIR_E_SHAPE (-2)
+#define B200PIR_E_CUDA (-3)
+#define B200PIR_E_UNSUPPORTED (-4)
+
+typedef struct b200pir_ctx b200pir_ctx;  /* params + tables + workspace on one GPU */
+typedef struct b200pir_db b200pir_db;    /* HBM-resident database                   */
+typedef struct b200pir_pp b200pir_pp;    /* HBM-resident PublicParameters of a client */
+typedef struct b200pir_dpir b200pir_dpir; /* HBM-resident DoublePIR packed matrix    */
+
+/* The scalar fields of spiral_rs::params::Params that params_from_json_obj reads
+ * (lib/spiral-rs/src/util.rs:224-263); poly_len = 2048 and the two CRT moduli are fixed there (:246-247). */
+typedef struct {
+  uint64_t n, nu_1, nu_2, p, q2_bits, t_gsw, t_conv, t_exp_left, t_exp_right, instances, db_item_size, version;
+  int32_t expand_queries; /* 0 = direct_upload */
+} b200pir_params;
+
+const char* b200pir_last_error(void);
+int b200pir_device_count(void);
+
+/* Params::init (params.rs:224-296): builds NTT tables, Barrett constants, v_neg1 on `device`. */
+int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** out);
+void b200pir_ctx_destroy(b200pir_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this context. */
+int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
+int b200pir_ctx_synchronize(b200pir_ctx* ctx);
+/* knobs: "mul_variant" (kernel tiling), "batch" (queries per database pass: 1, 2 or 4), "profile" (0/1);
+ * unknown keys -> B200PIR_E_BADARG */
+int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);
+/* params.setup_bytes / query_bytes / response length (params.rs:146-182, server.rs:476-481) */
+int b200pir_ctx_sizes(b200pir_ctx* ctx, uint64_t* setup_bytes, uint64_t* query_bytes, uint64_t* response_bytes);
+
+/* ---- database: replaces the `db: &[u64]` argument of process_query (server.rs:650-655) ---------- */
+/* Allocates slices*dim0*num_per*2048 words in HBM (zero = every item empty).
+ * Multi-GPU row sharding: with shard_count = G (a power of two dividing num_per) this GPU holds
+ * the second-dimension rows ii = shard_index (mod G); pass 0,1 for the whole database. */
+int b200pir_db_create(b200pir_ctx* ctx, uint64_t shard_index, uint64_t shard_count, b200pir_db** out);
+void b200pir_db_destroy(b200pir_db* db);
+/* Upload one (instance,trial) slice in the reference layout [z][ii][j] (server.rs:263-266). */
+int b200pir_db_upload_slice(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, const uint64_t* words, size_t n_words);
+/* Whole db: &[u64] of instances*n^2 slices. */
+int b200pir_db_upload(b200pir_ctx* ctx, b200pir_db* db, const uint64_t* words, size_t n_words);
+/* One preprocessed item polynomial: 2048 packed words (lib/server/src/db/loading.rs:34-41 pack_ntt_poly,
+ * :317-359 update_item_raw -> db.upsert(inst_trial*num_items + db_idx)); item_idx = j*num_per + ii. */
+int b200pir_db_upsert_item(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, uint64_t item_idx, const uint64_t* poly);
+/* Synthetic database generated on the GPU: plaintext coefficient = splitmix64(seed, ((slice*items+item)*2048+z)) % p,
+ * then recenter_mod / NTT / pack as generate_random_db_and_get_item does (server.rs:223-275). */
+int b200pir_db_fill_synthetic(b200pir_ctx* ctx, b200pir_db* db, uint64_t seed);
+
+/* ---- public parameters: replaces &PublicParameters (client.rs:146-152), all matrices in NTT form ---- */
+/* v_packing: num_packing x (n+1) x t_conv ; v_expansion_left: g x 2 x t_exp_left ;
+ * v_expansion_right: (stop_round+1) x 2 x t_exp_right or NULL (-> left, server.rs:549) ; v_conversion: 2 x 2 t_conv.
+ * Expansion / conversion may be NULL when expand_queries == 0. */
+int b200pir_pp_create(b200pir_ctx* ctx, const uint64_t* v_packing, const uint64_t* v_expansion_left,
+                      const uint64_t* v_expansion_right, const uint64_t* v_conversion, b200pir_pp** out);
+void b200pir_pp_destroy(b200pir_pp* pp);
+
+/* ---- stage-level entry points (each == one reference function, host buffers) ----------------------- */
+/* ntt.rs:67-113 ntt_forward / :212-258 ntt_inverse over `count` polys of [2][2048] u64, in place. */
+int b200pir_ntt_forward(b200pir_ctx* ctx, uint64_t* polys, size_t count);
+int b200pir_ntt_inverse(b200pir_ctx* ctx, uint64_t* polys, size_t count);
+/* poly.rs:613-623 to_ntt / :646-663 from_ntt over `count` polys. */
+int b200pir_to_ntt(b200pir_ctx* ctx, uint64_t* out_ntt, const uint64_t* raw, size_t count);
+int b200pir_from_ntt(b200pir_ctx* ctx, uint64_t* out_raw, const uint64_t* ntt, size_t count);
+/* server.rs:155-221 multiply_reg_by_database on slice `slice`: out = num_per x PolyMatrixNTT(2,1). */
+int b200pir_multiply_reg_by_database(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, const uint64_t* v_firstdim,
+                                     uint64_t* out);
+/* server.rs:388-427 fold_ciphertexts: v_cts = num x PolyMatrixRaw(2,1) in place (result in v_cts[0]);
+ * v_folding / v_folding_neg = log2(num) x PolyMatrixNTT(2, 2 t_gsw). */
+int b200pir_fold_ciphertexts(b200pir_ctx* ctx, uint64_t* v_cts, size_t num, const uint64_t* v_folding,
+                             const uint64_t* v_folding_neg);
+/* server.rs:505-523 get_v_folding_neg */
+int b200pir_get_v_folding_neg(b200pir_ctx* ctx, uint64_t* out, const uint64_t* v_folding);
+/* server.rs:19-121 coefficient_expansion over v = 2^g x PolyMatrixNTT(2,1), in place */
+int b200pir_coefficient_expansion(b200pir_ctx* ctx, b200pir_pp* pp, uint64_t* v);
+/* server.rs:525-591 expand_query: query ct (PolyMatrixRaw 2x1) -> v_firstdim [z][j][r], v_folding nu_2 x (2 x 2 t_gsw) */
+int b200pir_expand_query(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* query_ct, uint64_t* out_v_firstdim,
+                         uint64_t* out_v_folding);
+/* server.rs:429-468 pack (version 0) / lib/server/src/compute/pack.rs:45-98 (version 1):
+ * v_ct = n*n x PolyMatrixRaw(2,1) of one instance -> PolyMatrixNTT(n+1, n) */
+int b200pir_pack(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* v_ct, uint64_t* out_ntt);
+/* server.rs:470-503 encode: instances x PolyMatrixRaw(n+1, n) -> response bytes */
+int b200pir_encode(b200pir_ctx* ctx, const uint64_t* v_packed_raw, uint8_t* out, size_t* out_len);
+
+/* ---- the drop-in: spiral_rs::server::process_query (server.rs:650-741) ------------------------------- */
+/* expand_queries != 0: query_ct = Query.ct (PolyMatrixRaw 2x1), v_buf = v_ct = NULL.
+ * expand_queries == 0: query_ct = NULL, v_buf = Query.v_buf ([z][j][r]), v_ct = nu_2 x PolyMatrixRaw(2, 2 t_gsw).
+ * out: response_bytes bytes. */
+int b200pir_process_query(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_ct,
+                          const uint64_t* v_buf, const uint64_t* v_ct, uint8_t* out, size_t* out_len);
+/* `count` queries of one client in one call; the database is streamed once per group of up to 4 queries.
+ * queries: count x PolyMatrixRaw(2,1); out: count x response_bytes. */
+int b200pir_process_query_batch(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts,
+                                size_t count, uint8_t* out, size_t* out_len_each);
+/* Device-resident variants for measurement and multi-GPU composition: inputs/outputs are DEVICE pointers
+ * and nothing is synchronised (stream-ordered).  query_dev: count x PolyMatrixRaw(2,1) (u64);
+ * out_dev: count x response_bytes. */
+int b200pir_process_query_batch_dev(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
+                                    size_t count, uint8_t* out_dev);
+/* Multi-GPU row sharding (DESIGN.md "multi-GPU"): stage A = expansion + first dimension + local fold rounds
+ * on this GPU's rows; writes this rank's surviving ciphertexts (count x slices x PolyMatrixRaw(2,1)) to
+ * `partial_dev`.  Stage B = remaining log2(world) fold rounds + pack + encode over the all-gathered
+ * `gathered_dev` ([world][count][slices][2][2048] u64). */
+int b200pir_query_stage_a_dev(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
+                              size_t count, uint64_t* partial_dev);
+int b200pir_query_stage_b_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* gathered_dev, size_t world,
+                              size_t count, uint8_t* out_dev);
+
+/* Per-stage device time of the last profiled call, in milliseconds, measured with CUDA events on the
+ * context's stream.  Enable with b200pir_ctx_set_option(ctx, "profile", 1).
+ * out[0..7] = expand, first-dim multiply, from_ntt, fold, pack, encode, total, multiply launches */
+int b200pir_last_stage_ms(b200pir_ctx* ctx, double* out8);
+
+/* ---- DoublePIR: matrix_mul_vec_packed(a, b, basis=10, compression=3) (lib/doublepir/src/matrix/kernels.rs:118-178) */
+int b200pir_dpir_create(int device, const uint32_t* a, uint64_t rows, uint64_t cols, b200pir_dpir** out);
+/* synthetic a: word(i,k) = low 30 bits of splitmix64(seed, i*cols+k) */
+int b200pir_dpir_create_synthetic(int device, uint64_t rows, uint64_t cols, uint64_t seed, b200pir_dpir** out);
+void b200pir_dpir_destroy(b200pir_dpir* m);
+int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream);
+/* b: 3*cols u32 ; out: rows u32 */
+int b200pir_dpir_matvec_packed(b200pir_dpir* m, const uint32_t* b, uint32_t* out);
+int b200pir_dpir_matvec_packed_dev(b200pir_dpir* m, const uint32_t* b_dev, uint32_t* out_dev, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

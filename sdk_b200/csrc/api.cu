@@ -1,0 +1,1062 @@
+// C-ABI implementation (include/b200pir.h): contexts, HBM-resident handles and the host-side
+// orchestration of spiral_rs::server::process_query (lib/spiral-rs/src/server.rs:650-741) as a
+// stream of sm_100a kernel launches.  No CPU fallback exists anywhere on this path: every entry
+// point either runs on the GPU or returns an error.
+#include "../../include/b200pir.h"
+#include "kernels.h"
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b200pir;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------- host-side number theory
+// (independent re-derivation of Params::init, params.rs:224-296; the oracle is never linked here)
+typedef unsigned __int128 u128;
+uint64_t mulmod(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)((u128)a * b % m); }
+uint64_t powmod(uint64_t a, uint64_t e, uint64_t m) {
+  uint64_t r = 1 % m;
+  a %= m;
+  while (e) { if (e & 1) r = mulmod(r, a, m); a = mulmod(a, a, m); e >>= 1; }
+  return r;
+}
+uint64_t invmod(uint64_t a, uint64_t m) {    // m prime or gcd(a,m)=1
+  __int128 r0 = a % m, r1 = m, s0 = 1, s1 = 0;
+  while (r1 != 0) { __int128 q = r0 / r1, t = r0 - q * r1; r0 = r1; r1 = t; t = s0 - q * s1; s0 = s1; s1 = t; }
+  if (r0 != 1) throw Error(B200PIR_E_BADARG, "invmod: not invertible");
+  s0 %= (__int128)m;
+  if (s0 < 0) s0 += m;
+  return (uint64_t)s0;
+}
+unsigned bitrev(unsigned x, int bits) {
+  unsigned r = 0;
+  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+// minimal primitive 2N-th root (number_theory.rs:14-55)
+uint64_t min_primitive_root(uint64_t degree, uint64_t q) {
+  if ((q - 1) % degree) throw Error(B200PIR_E_BADARG, "modulus is not NTT friendly");
+  uint64_t quot = (q - 1) / degree, root = 0;
+  for (uint64_t c = 2; c < 4096; c++) {
+    uint64_t r = powmod(c, quot, q);
+    if (powmod(r, degree / 2, q) == q - 1) { root = r; break; }
+  }
+  if (!root) throw Error(B200PIR_E_BADARG, "no primitive root found");
+  uint64_t gsq = mulmod(root, root, q), cur = root, best = root;
+  for (uint64_t i = 0; i < degree; i++) { if (cur < best) best = cur; cur = mulmod(cur, gsq, q); }
+  return best;
+}
+// tables of ntt.rs:39-65 as (W, W') pairs
+void build_tables(uint64_t q, std::vector<Twiddle>& fwd, std::vector<Twiddle>& inv) {
+  const int N = NTT_N, LG = NTT_LOG_N;
+  uint64_t root = min_primitive_root(2 * N, q), iroot = invmod(root, q);
+  fwd.assign(N, Twiddle{0, 0});
+  inv.assign(N, Twiddle{0, 0});
+  auto fill = [&](std::vector<Twiddle>& t, uint64_t r, bool halve) {
+    uint64_t power = r;
+    std::vector<uint64_t> v(N, 0);
+    for (int i = 1; i < N; i++) { v[bitrev(i, LG)] = power; power = mulmod(power, r, q); }
+    v[0] = 1;
+    for (int i = 0; i < N; i++) {
+      uint64_t w = v[i];
+      if (halve) w = (w & 1) ? (w + q) >> 1 : w >> 1;          // div2_uint_mod, arith.rs:78-89
+      t[i].w = (uint32_t)w;
+      t[i].wp = (uint32_t)((w << 32) / q);                      // scale_powers_u32, ntt.rs:29-37
+    }
+  };
+  fill(fwd, root, false);
+  fill(inv, iroot, true);
+}
+uint64_t log2_ceil_u64(uint64_t a) { return (uint64_t)std::ceil(std::log2((double)a)); }
+int bits_per(int t) {                        // gadget.rs:3-9 with modulus_log2 = 56
+  if (t == 56) return 1;
+  return 56 / t + 1;
+}
+const uint64_t kQ2Values[37] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 12289ULL, 12289ULL, 61441ULL, 65537ULL,
+                                65537ULL, 520193ULL, 786433ULL, 786433ULL, 3604481ULL, 7340033ULL, 16515073ULL,
+                                33292289ULL, 67043329ULL, 132120577ULL, 268369921ULL, 469762049ULL, 1073479681ULL,
+                                2013265921ULL, 4293918721ULL, 8588886017ULL, 17175674881ULL, 34359214081ULL,
+                                68718428161ULL};   // params.rs:8-46
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t count) { alloc(count); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) B200_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+enum Stage { ST_EXPAND = 0, ST_MUL, ST_FROMNTT, ST_FOLD, ST_PACK, ST_ENCODE, ST_COUNT };
+
+}  // namespace
+
+struct b200pir_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::recursive_mutex mu;
+  b200pir_params hp;
+  // derived (params.rs:116-200)
+  int dim0, num_per, slices, trials, g, stop_round, num_packing;
+  int bits_gsw, bits_conv, bits_left, bits_right;
+  bool has_right;
+  uint64_t q2, q1, setup_bytes, query_bytes, response_bytes;
+  int q1_bits;
+  DevParams dp;
+  DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1
+  DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
+  // options
+  int mul_variant = 0, max_group = 4, profile = 0;
+  // workspace, sized for `ws_queries` queries
+  size_t ws_queries = 0, ws_rows = 0;
+  DevBuf<uint64_t> w_query;      // [Q][2][2048] raw
+  DevBuf<uint32_t> w_v;          // [Q][2^g][2][2][2048]
+  DevBuf<uint4> w_qdev;          // [Q][dim0][2048]
+  DevBuf<uint32_t> w_vfold, w_vfold_neg;   // [Q][nu_2][2][2t][2][2048]
+  DevBuf<uint32_t> w_mult;       // [Q][slices][rows][2][2][2048]
+  DevBuf<uint64_t> w_cts;        // [Q][slices][rows][2][2048]
+  DevBuf<uint64_t> w_packed;     // [Q][inst][n+1][n][2048]
+  DevBuf<uint8_t> w_resp;        // [Q][response_bytes]
+  // profiling
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  size_t event_next = 0;
+  int mul_launches = 0;
+  double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  size_t v_words() const { return ((size_t)1 << g) * 4 * POLY; }
+  size_t fold_words() const { return (size_t)hp.nu_2 * 2 * 2 * hp.t_gsw * 2 * POLY; }
+  MulGeom geom(int rows) const { return MulGeom{dim0, rows, slices}; }
+
+  cudaEvent_t get_event() {
+    if (event_next == event_pool.size()) {
+      cudaEvent_t e;
+      B200_CUDA(cudaEventCreate(&e));
+      event_pool.push_back(e);
+    }
+    return event_pool[event_next++];
+  }
+  struct Scope {
+    b200pir_ctx* c; int stage; cudaEvent_t a = nullptr;
+    Scope(b200pir_ctx* ctx, int st) : c(ctx), stage(st) {
+      if (c->profile) { a = c->get_event(); cudaEventRecord(a, c->stream); }
+    }
+    ~Scope() {
+      if (c->profile) { cudaEvent_t b = c->get_event(); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); }
+    }
+  };
+  void prof_reset() { spans.clear(); event_next = 0; mul_launches = 0; }
+  void prof_collect() {
+    if (!profile) return;
+    B200_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 8; i++) last_ms[i] = 0;
+    for (auto& s : spans) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s.a, s.b);
+      last_ms[s.stage] += ms;
+      last_ms[6] += ms;
+    }
+    last_ms[7] = mul_launches;
+  }
+  void ensure_workspace(size_t queries, size_t rows) {
+    if (queries <= ws_queries && rows <= ws_rows) return;
+    queries = std::max(queries, ws_queries);
+    rows = std::max(rows, ws_rows);
+    w_query.ensure(queries * 2 * POLY);
+    if (hp.expand_queries) w_v.ensure(queries * v_words());
+    w_qdev.ensure(queries * (size_t)dim0 * POLY);
+    w_vfold.ensure(queries * std::max<size_t>(fold_words(), 1));
+    w_vfold_neg.ensure(queries * std::max<size_t>(fold_words(), 1));
+    w_mult.ensure(queries * slices * rows * 4 * POLY);
+    w_cts.ensure(queries * slices * rows * 2 * POLY);
+    w_packed.ensure(queries * hp.instances * (hp.n + 1) * hp.n * POLY);
+    w_resp.ensure(queries * response_bytes);
+    ws_queries = queries;
+    ws_rows = rows;
+  }
+};
+
+struct b200pir_db {
+  b200pir_ctx* ctx;
+  Shard shard;
+  int rows;                 // local second-dimension rows
+  DevBuf<uint4> d;          // [slice][row][dim0/2][2048]
+};
+
+struct b200pir_pp {
+  b200pir_ctx* ctx;
+  DevBuf<uint32_t> pack, left, right, conv;    // ntt32
+};
+
+struct b200pir_dpir {
+  int device;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  uint64_t rows, cols;
+  DevBuf<uint32_t> a;
+  DevBuf<uint32_t> b, out;
+};
+
+namespace {
+
+int fail(const std::exception& e) {
+  g_last_error = e.what();
+  const Error* pe = dynamic_cast<const Error*>(&e);
+  return pe ? pe->code : B200PIR_E_CUDA;
+}
+#define API_BEGIN try {
+#define API_END                                     \
+  }                                                 \
+  catch (const std::exception& e) { return fail(e); } \
+  return 0;
+
+struct Guard {
+  std::lock_guard<std::recursive_mutex> lk;
+  explicit Guard(b200pir_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+// upload u64 NTT-form matrices (words < 2^32) as ntt32
+void upload_ntt32(b200pir_ctx* c, DevBuf<uint32_t>& dst, const uint64_t* host, size_t words) {
+  dst.alloc(words);
+  DevBuf<uint64_t> tmp(words);
+  B200_CUDA(cudaMemcpyAsync(tmp.p, host, words * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(dst.p, tmp.p, words, c->stream);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// ---- pipeline pieces (all stream-ordered, device pointers)
+
+// server.rs:525-591 for one query.  v: [2^g][4][2048]; writes q_dev and v_fold.
+void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw, uint32_t* v, uint4* q_dev,
+                      uint32_t* v_fold) {
+  const auto& hp = c->hp;
+  cudaStream_t s = c->stream;
+  B200_CUDA(cudaMemsetAsync(v, 0, c->v_words() * 4, s));
+  launch_to_ntt(c->dp, v, query_raw, 2, s);                       // v[0] = query.ct.ntt()
+  const int g = c->g;
+  const int stop_round = hp.nu_2 > 0 ? c->stop_round : 0;
+  const int max_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
+  for (int r = 0; r < g; r++) {
+    const int num_in = 1 << r;
+    launch_expand_scalar(c->dp, v, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    ExpandRound R;
+    R.r = r; R.num_in = num_in; R.stop_round = stop_round; R.max_bits_to_gen_right = max_right;
+    R.t_auto = (POLY >> r) + 1;
+    R.t_left = (int)hp.t_exp_left; R.bits_left = c->bits_left;
+    R.w_left = pp->left.p + (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
+    if (hp.nu_2 > 0 && c->has_right) {
+      // v_w_right has stop_round+1 matrices; rounds beyond that never take the right branch for a
+      // processed (even) index except r == 0 (server.rs:60-73), so clamp the pointer for safety.
+      int rr = r <= c->stop_round ? r : c->stop_round;
+      R.t_right = (int)hp.t_exp_right; R.bits_right = c->bits_right;
+      R.w_right = pp->right.p + (size_t)rr * 2 * hp.t_exp_right * 2 * POLY;
+    } else {
+      R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;   // unwrap_or(v_w_left), server.rs:549
+    }
+    launch_expand_round(c->dp, v, R, s);
+  }
+  const int factor = hp.nu_2 > 0 ? 2 : 1;
+  launch_reorient(c->geom(c->num_per), q_dev, v, factor, s);
+  if (hp.nu_2 > 0)
+    launch_regev_to_gsw(c->dp, v_fold, v, (int)hp.nu_2, 2, 1, pp->conv.p, (int)hp.t_gsw, (int)hp.t_conv, c->bits_conv, s);
+}
+
+// fold `num` ciphertexts per batch entry with matrices k = k0, k0-1, ...
+void run_fold(b200pir_ctx* c, uint64_t* cts, size_t batch, size_t batch_stride, size_t num, int k0,
+              const uint32_t* vfold, const uint32_t* vfold_neg, int slices_per_query) {
+  const size_t mat = (size_t)2 * 2 * c->hp.t_gsw * 2 * POLY;
+  int k = k0;
+  for (size_t half = num / 2; half >= 1; half /= 2, k--) {
+    launch_fold_round(c->dp, cts, batch, batch_stride, (int)half, vfold + (size_t)k * mat, vfold_neg + (size_t)k * mat,
+                      c->fold_words(), slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+  }
+}
+
+// expansion (or direct upload) for `count` queries already in w_query / w_qdev,w_vfold
+void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
+  b200pir_ctx::Scope sc(c, ST_EXPAND);
+  if (c->hp.expand_queries) {
+    for (size_t qi = 0; qi < count; qi++)
+      run_expand_query(c, pp, c->w_query.p + qi * 2 * POLY, c->w_v.p + qi * c->v_words(),
+                       c->w_qdev.p + qi * (size_t)c->dim0 * POLY, c->w_vfold.p + qi * c->fold_words());
+  }
+  if (c->hp.nu_2 > 0)
+    launch_folding_neg(c->dp, c->w_vfold_neg.p, c->w_vfold.p, (int)(count * c->hp.nu_2), (int)c->hp.t_gsw, c->bits_gsw,
+                       c->stream);
+}
+
+// first dimension + from_ntt + local fold.  Leaves survivors at w_cts[(qi*slices + slice)*rows*2*POLY].
+void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
+  const int rows = db->rows;
+  MulGeom G = c->geom(rows);
+  const size_t q_stride = (size_t)c->dim0 * POLY;
+  const size_t out_stride = (size_t)c->slices * rows * 4 * POLY;
+  {
+    b200pir_ctx::Scope sc(c, ST_MUL);
+    size_t qi = 0;
+    while (qi < count) {
+      int nq = 1;
+      if (count - qi >= 4 && c->max_group >= 4) nq = 4;
+      else if (count - qi >= 2 && c->max_group >= 2) nq = 2;
+      launch_multiply(c->dp, G, db->d.p, c->w_qdev.p + qi * q_stride, c->w_mult.p + qi * out_stride, 0, c->slices, nq,
+                      q_stride, out_stride, c->mul_variant, c->stream);
+      c->mul_launches++;
+      qi += nq;
+    }
+  }
+  {
+    b200pir_ctx::Scope sc(c, ST_FROMNTT);
+    launch_from_ntt(c->dp, c->w_cts.p, c->w_mult.p, count * c->slices * rows * 2, c->stream);
+  }
+  {
+    b200pir_ctx::Scope sc(c, ST_FOLD);
+    if (rows > 1)
+      run_fold(c, c->w_cts.p, count * c->slices, (size_t)rows * 2 * POLY, rows, (int)c->hp.nu_2 - 1, c->w_vfold.p,
+               c->w_vfold_neg.p, c->slices);
+  }
+}
+
+// pack + encode for `count` queries whose folded ciphertexts sit at folded + ((qi*slices)+t)*ct_stride
+void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* folded, size_t ct_stride, size_t count,
+                     uint8_t* out_dev) {
+  const auto& hp = c->hp;
+  const size_t packed_words = (size_t)hp.instances * (hp.n + 1) * hp.n * POLY;
+  {
+    b200pir_ctx::Scope sc(c, ST_PACK);
+    for (size_t qi = 0; qi < count; qi++)
+      launch_pack(c->dp, c->w_packed.p + qi * packed_words, folded + qi * c->slices * ct_stride, ct_stride, pp->pack.p,
+                  (int)hp.n, (int)hp.instances, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+  }
+  {
+    b200pir_ctx::Scope sc(c, ST_ENCODE);
+    for (size_t qi = 0; qi < count; qi++)
+      launch_encode(c->dp, out_dev + qi * c->response_bytes, c->response_bytes, c->w_packed.p + qi * packed_words,
+                    (int)hp.n, (int)hp.instances, c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
+  }
+}
+
+void check_db(b200pir_ctx* c, b200pir_db* db) {
+  if (!db || db->ctx != c) throw Error(B200PIR_E_BADARG, "db handle does not belong to this context");
+}
+void check_pp(b200pir_ctx* c, b200pir_pp* pp) {
+  if (!pp || pp->ctx != c) throw Error(B200PIR_E_BADARG, "pp handle does not belong to this context");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200pir_last_error(void) { return g_last_error.c_str(); }
+int b200pir_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** out) {
+  API_BEGIN
+  if (!params || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw Error(B200PIR_E_BADARG, "no such CUDA device (this library has no CPU path)");
+  B200_CUDA(cudaSetDevice(device));
+  std::unique_ptr<b200pir_ctx> c(new b200pir_ctx());
+  c->device = device;
+  c->hp = *params;
+  auto& hp = c->hp;
+  if (hp.q2_bits < 14) hp.q2_bits = 14;                       // util.rs:230, params.rs:7
+  if (hp.q2_bits > 36) throw Error(B200PIR_E_BADARG, "q2_bits out of range");
+  if (hp.instances == 0) hp.instances = 1;
+  if (hp.n < 1 || hp.n > 4) throw Error(B200PIR_E_UNSUPPORTED, "n must be 1..4");
+  if (hp.nu_1 < 1 || hp.nu_1 > 16 || hp.nu_2 > 16) throw Error(B200PIR_E_BADARG, "nu_1/nu_2 out of range");
+  if (hp.version > 1) throw Error(B200PIR_E_BADARG, "unknown version");
+  if (hp.p < 2 || (hp.p & (hp.p - 1)) || hp.p > (1u << 20)) throw Error(B200PIR_E_BADARG, "p must be a power of two <= 2^20");
+  for (uint64_t t : {hp.t_gsw, hp.t_conv, hp.t_exp_left, hp.t_exp_right})
+    if (t < 2 || t > 56) throw Error(B200PIR_E_UNSUPPORTED, "gadget dimensions must be in 2..56");
+  if (hp.db_item_size == 0) hp.db_item_size = hp.instances * hp.n * hp.n * 2048 * log2_ceil_u64(hp.p) / 8;
+  c->dim0 = 1 << hp.nu_1;
+  c->num_per = 1 << hp.nu_2;
+  c->trials = (int)(hp.n * hp.n);
+  c->slices = (int)(hp.instances * c->trials);
+  c->g = (int)log2_ceil_u64(hp.t_gsw * hp.nu_2 + c->dim0);
+  c->stop_round = hp.nu_2 ? (int)log2_ceil_u64(hp.t_gsw * hp.nu_2) : 0;
+  if (c->g > 11) throw Error(B200PIR_E_UNSUPPORTED, "expansion needs more than 2048 slots");
+  c->num_packing = hp.version == 0 ? (int)hp.n : 2;
+  c->has_right = hp.expand_queries && (hp.version == 0 || hp.t_exp_right != hp.t_exp_left);
+  c->bits_gsw = bits_per((int)hp.t_gsw);
+  c->bits_conv = bits_per((int)hp.t_conv);
+  c->bits_left = bits_per((int)hp.t_exp_left);
+  c->bits_right = bits_per((int)hp.t_exp_right);
+  c->q2 = kQ2Values[hp.q2_bits];
+  c->q1 = 4 * hp.p;
+  c->q1_bits = (int)log2_ceil_u64(c->q1);
+  {
+    uint64_t bits = hp.instances * (hp.q2_bits * hp.n * 2048 + (uint64_t)c->q1_bits * hp.n * hp.n * 2048);
+    c->response_bytes = ((bits + 63) / 64) * 8;
+    uint64_t sz = (uint64_t)c->num_packing * hp.n * hp.t_conv;
+    if (hp.expand_queries) {
+      uint64_t right = (uint64_t)(c->stop_round + 1) * hp.t_exp_right;
+      if (hp.version > 0 && hp.t_exp_left == hp.t_exp_right) right = 0;
+      sz += (uint64_t)c->g * hp.t_exp_left + right + 2 * hp.t_conv;
+    }
+    c->setup_bytes = 32 + sz * 2048 * 8;
+    uint64_t qp = hp.expand_queries ? 1 : (uint64_t)c->dim0 + hp.nu_2 * 2 * hp.t_gsw;
+    c->query_bytes = 32 + qp * 2048 * 8;
+  }
+  B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // tables
+  const uint64_t q0 = 268369921ULL, q1m = 249561089ULL;            // util.rs:246-247
+  std::vector<Twiddle> f0, i0, f1, i1;
+  build_tables(q0, f0, i0);
+  build_tables(q1m, f1, i1);
+  c->d_tw.alloc(4 * POLY);
+  B200_CUDA(cudaMemcpy(c->d_tw.p, f0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(c->d_tw.p + POLY, i0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(c->d_tw.p + 2 * POLY, f1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(c->d_tw.p + 3 * POLY, i1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  DevParams& dp = c->dp;
+  dp.q[0] = (uint32_t)q0; dp.q[1] = (uint32_t)q1m;
+  dp.cr1[0] = (uint64_t)(((u128)1 << 64) / q0);
+  dp.cr1[1] = (uint64_t)(((u128)1 << 64) / q1m);
+  dp.modulus = q0 * q1m;
+  dp.cr1_mod = (uint64_t)(((u128)1 << 64) / dp.modulus);
+  dp.q1_inv_mod_q0 = (uint32_t)invmod(q1m % q0, q0);
+  dp.fwd[0] = c->d_tw.p; dp.inv[0] = c->d_tw.p + POLY; dp.fwd[1] = c->d_tw.p + 2 * POLY; dp.inv[1] = c->d_tw.p + 3 * POLY;
+  // v_neg1 (params.rs:98-107): NTT of -(X^{N - 2^i})
+  {
+    std::vector<uint32_t> h((size_t)NTT_LOG_N * 2 * POLY, 0);
+    for (int i = 0; i < NTT_LOG_N; i++) {
+      int idx = POLY - (1 << i);
+      h[((size_t)i * 2 + 0) * POLY + idx] = (uint32_t)(q0 - 1);
+      h[((size_t)i * 2 + 1) * POLY + idx] = (uint32_t)(q1m - 1);
+    }
+    c->d_neg1.alloc(h.size());
+    B200_CUDA(cudaMemcpy(c->d_neg1.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    launch_ntt32(dp, c->d_neg1.p, NTT_LOG_N, false, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  B200_CUDA(cudaGetLastError());
+  *out = c.release();
+  API_END
+}
+
+void b200pir_ctx_destroy(b200pir_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+int b200pir_ctx_set_stream(b200pir_ctx* c, void* cuda_stream) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  Guard gd(c);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  API_END
+}
+int b200pir_ctx_synchronize(b200pir_ctx* c) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  Guard gd(c);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
+  API_BEGIN
+  if (!c || !key) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  std::string k(key);
+  if (k == "mul_variant") c->mul_variant = (int)value;
+  else if (k == "batch") { if (value != 1 && value != 2 && value != 4) throw Error(B200PIR_E_BADARG, "batch must be 1, 2 or 4"); c->max_group = (int)value; }
+  else if (k == "profile") c->profile = value ? 1 : 0;
+  else throw Error(B200PIR_E_BADARG, "unknown option " + k);
+  API_END
+}
+int b200pir_ctx_sizes(b200pir_ctx* c, uint64_t* setup_bytes, uint64_t* query_bytes, uint64_t* response_bytes) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  if (setup_bytes) *setup_bytes = c->setup_bytes;
+  if (query_bytes) *query_bytes = c->query_bytes;
+  if (response_bytes) *response_bytes = c->response_bytes;
+  API_END
+}
+
+// ---------------------------------------------------------------- database
+int b200pir_db_create(b200pir_ctx* c, uint64_t shard_index, uint64_t shard_count, b200pir_db** out) {
+  API_BEGIN
+  if (!c || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  if (shard_count == 0) { shard_count = 1; shard_index = 0; }
+  if (shard_index >= shard_count || (shard_count & (shard_count - 1)) || (uint64_t)c->num_per % shard_count)
+    throw Error(B200PIR_E_BADARG, "shard_count must be a power of two dividing num_per");
+  std::unique_ptr<b200pir_db> db(new b200pir_db());
+  db->ctx = c;
+  db->shard = Shard{(int)shard_index, (int)shard_count};
+  db->rows = c->num_per / (int)shard_count;
+  size_t cells = (size_t)c->slices * db->rows * (c->dim0 / 2) * POLY;
+  db->d.alloc(cells);
+  B200_CUDA(cudaMemsetAsync(db->d.p, 0, cells * sizeof(uint4), c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  *out = db.release();
+  API_END
+}
+void b200pir_db_destroy(b200pir_db* db) {
+  if (!db) return;
+  cudaSetDevice(db->ctx->device);
+  delete db;
+}
+int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, const uint64_t* words, size_t n_words) {
+  API_BEGIN
+  if (!c || !words) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  const size_t slice_words = (size_t)c->dim0 * c->num_per * POLY;
+  if (slice >= (uint64_t)c->slices) throw Error(B200PIR_E_SHAPE, "slice out of range");
+  if (n_words != slice_words) throw Error(B200PIR_E_SHAPE, "slice must hold dim0*num_per*2048 words");
+  // reference layout is z-major: stage a range of z at a time (<= 64 MiB)
+  const size_t per_z = (size_t)c->dim0 * c->num_per;
+  int zc = (int)std::max<size_t>(1, std::min<size_t>(POLY, ((size_t)64 << 20) / (per_z * 8)));
+  DevBuf<uint64_t> stage(per_z * zc);
+  MulGeom G = c->geom(db->rows);
+  uint4* dst = db->d.p + (size_t)slice * db->rows * (c->dim0 / 2) * POLY;
+  for (int z0 = 0; z0 < POLY; z0 += zc) {
+    int cur = std::min(zc, POLY - z0);
+    B200_CUDA(cudaMemcpyAsync(stage.p, words + (size_t)z0 * per_z, per_z * cur * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_db_retile_chunk(G, db->shard, dst, stage.p, z0, cur, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_db_upload(b200pir_ctx* c, b200pir_db* db, const uint64_t* words, size_t n_words) {
+  if (!c) { g_last_error = "null ctx"; return B200PIR_E_BADARG; }
+  const size_t slice_words = (size_t)c->dim0 * c->num_per * POLY;
+  if (n_words != slice_words * c->slices) { g_last_error = "db must hold slices*dim0*num_per*2048 words"; return B200PIR_E_SHAPE; }
+  for (int s = 0; s < c->slices; s++) {
+    int rc = b200pir_db_upload_slice(c, db, s, words + (size_t)s * slice_words, slice_words);
+    if (rc) return rc;
+  }
+  return 0;
+}
+int b200pir_db_upsert_item(b200pir_ctx* c, b200pir_db* db, uint64_t slice, uint64_t item_idx, const uint64_t* poly) {
+  API_BEGIN
+  if (!c || !poly) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  if (slice >= (uint64_t)c->slices || item_idx >= (uint64_t)c->dim0 * c->num_per) throw Error(B200PIR_E_SHAPE, "index out of range");
+  int ii = (int)(item_idx % c->num_per), j = (int)(item_idx / c->num_per);
+  if (ii % db->shard.count != db->shard.index) return 0;           // row lives on another GPU
+  DevBuf<uint64_t> tmp(POLY);
+  B200_CUDA(cudaMemcpyAsync(tmp.p, poly, POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_db_upsert(c->geom(db->rows), db->d.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
+  // the host RwLock gives upserts exclusive access (bin/server.rs:35,49): finish before returning
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  API_END
+}
+int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  Guard gd(c);
+  check_db(c, db);
+  MulGeom G = c->geom(db->rows);
+  // keep each launch's grid below 2^31 CTAs
+  size_t per_slice = (size_t)db->rows * (c->dim0 / 2);
+  int step = (int)std::max<size_t>(1, std::min<size_t>(c->slices, ((size_t)1 << 30) / per_slice));
+  for (int s0 = 0; s0 < c->slices; s0 += step)
+    launch_db_synth(c->dp, G, db->shard, db->d.p, seed, c->hp.p, s0, std::min(step, c->slices - s0), c->stream);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// ---------------------------------------------------------------- public parameters
+int b200pir_pp_create(b200pir_ctx* c, const uint64_t* v_packing, const uint64_t* left, const uint64_t* right,
+                      const uint64_t* conv, b200pir_pp** out) {
+  API_BEGIN
+  if (!c || !out || !v_packing) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  const auto& hp = c->hp;
+  std::unique_ptr<b200pir_pp> pp(new b200pir_pp());
+  pp->ctx = c;
+  const size_t W = 2 * POLY;
+  upload_ntt32(c, pp->pack, v_packing, (size_t)c->num_packing * (hp.n + 1) * hp.t_conv * W);
+  if (hp.expand_queries) {
+    if (!left || !conv) throw Error(B200PIR_E_BADARG, "expansion parameters missing");
+    upload_ntt32(c, pp->left, left, (size_t)c->g * 2 * hp.t_exp_left * W);
+    if (c->has_right) {
+      if (!right) throw Error(B200PIR_E_BADARG, "v_expansion_right missing");
+      upload_ntt32(c, pp->right, right, (size_t)(c->stop_round + 1) * 2 * hp.t_exp_right * W);
+    }
+    upload_ntt32(c, pp->conv, conv, (size_t)2 * 2 * hp.t_conv * W);
+  }
+  *out = pp.release();
+  API_END
+}
+void b200pir_pp_destroy(b200pir_pp* pp) {
+  if (!pp) return;
+  cudaSetDevice(pp->ctx->device);
+  delete pp;
+}
+
+// ---------------------------------------------------------------- stage-level entry points
+static int ntt_host(b200pir_ctx* c, uint64_t* polys, size_t count, bool inverse) {
+  API_BEGIN
+  if (!c || (!polys && count)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  if (count == 0) return 0;
+  DevBuf<uint64_t> d(count * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(d.p, polys, d.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_ntt_u64(c->dp, d.p, count, inverse, c->stream);
+  B200_CUDA(cudaMemcpyAsync(polys, d.p, d.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_ntt_forward(b200pir_ctx* c, uint64_t* polys, size_t count) { return ntt_host(c, polys, count, false); }
+int b200pir_ntt_inverse(b200pir_ctx* c, uint64_t* polys, size_t count) { return ntt_host(c, polys, count, true); }
+
+int b200pir_to_ntt(b200pir_ctx* c, uint64_t* out_ntt, const uint64_t* raw, size_t count) {
+  API_BEGIN
+  if (!c || !out_ntt || !raw) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  DevBuf<uint64_t> in(count * POLY), wide(count * 2 * POLY);
+  DevBuf<uint32_t> o(count * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(in.p, raw, in.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_to_ntt(c->dp, o.p, in.p, count, c->stream);
+  launch_widen(wide.p, o.p, o.n, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out_ntt, wide.p, wide.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_from_ntt(b200pir_ctx* c, uint64_t* out_raw, const uint64_t* ntt, size_t count) {
+  API_BEGIN
+  if (!c || !out_raw || !ntt) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  DevBuf<uint64_t> wide(count * 2 * POLY), o(count * POLY);
+  DevBuf<uint32_t> in(count * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(wide.p, ntt, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(in.p, wide.p, in.n, c->stream);
+  launch_from_ntt(c->dp, o.p, in.p, count, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out_raw, o.p, o.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_multiply_reg_by_database(b200pir_ctx* c, b200pir_db* db, uint64_t slice, const uint64_t* v_firstdim,
+                                     uint64_t* out) {
+  API_BEGIN
+  if (!c || !v_firstdim || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  if (slice >= (uint64_t)c->slices) throw Error(B200PIR_E_SHAPE, "slice out of range");
+  const int rows = db->rows;
+  MulGeom G = c->geom(rows);
+  DevBuf<uint64_t> vq((size_t)c->dim0 * 2 * POLY);
+  DevBuf<uint4> qd((size_t)c->dim0 * POLY);
+  DevBuf<uint32_t> o((size_t)c->slices * rows * 4 * POLY);
+  DevBuf<uint64_t> wide((size_t)rows * 4 * POLY);
+  B200_CUDA(cudaMemcpyAsync(vq.p, v_firstdim, vq.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_query_to_dev(G, qd.p, vq.p, c->stream);
+  launch_multiply(c->dp, G, db->d.p, qd.p, o.p, (int)slice, 1, 1, 0, 0, c->mul_variant, c->stream);
+  launch_widen(wide.p, o.p + (size_t)slice * rows * 4 * POLY, wide.n, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out, wide.p, wide.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_fold_ciphertexts(b200pir_ctx* c, uint64_t* v_cts, size_t num, const uint64_t* v_folding,
+                             const uint64_t* v_folding_neg) {
+  API_BEGIN
+  if (!c || !v_cts) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  if (num == 0 || (num & (num - 1))) throw Error(B200PIR_E_SHAPE, "number of ciphertexts must be a power of two");
+  if (num == 1) return 0;                                          // server.rs:394-396
+  if (!v_folding || !v_folding_neg) throw Error(B200PIR_E_BADARG, "null argument");
+  int dims = 0;
+  while (((size_t)1 << dims) < num) dims++;
+  if (dims > (int)c->hp.nu_2) throw Error(B200PIR_E_SHAPE, "more ciphertexts than 2^nu_2");
+  const size_t mat = (size_t)2 * 2 * c->hp.t_gsw * 2 * POLY;
+  DevBuf<uint64_t> cts(num * 2 * POLY), wide(dims * mat);
+  DevBuf<uint32_t> vf(c->fold_words()), vfn(c->fold_words());
+  B200_CUDA(cudaMemcpyAsync(cts.p, v_cts, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
+  B200_CUDA(cudaMemcpyAsync(wide.p, v_folding, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(vf.p, wide.p, wide.n, c->stream);
+  B200_CUDA(cudaMemcpyAsync(wide.p, v_folding_neg, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(vfn.p, wide.p, wide.n, c->stream);
+  run_fold(c, cts.p, 1, num * 2 * POLY, num, dims - 1, vf.p, vfn.p, 1);
+  B200_CUDA(cudaMemcpyAsync(v_cts, cts.p, cts.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_get_v_folding_neg(b200pir_ctx* c, uint64_t* out, const uint64_t* v_folding) {
+  API_BEGIN
+  if (!c || !out || !v_folding) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  const size_t words = c->fold_words();
+  if (!words) return 0;
+  DevBuf<uint64_t> wide(words);
+  DevBuf<uint32_t> in(words), o(words);
+  B200_CUDA(cudaMemcpyAsync(wide.p, v_folding, words * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(in.p, wide.p, words, c->stream);
+  launch_folding_neg(c->dp, o.p, in.p, (int)c->hp.nu_2, (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+  launch_widen(wide.p, o.p, words, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out, wide.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint64_t* v) {
+  API_BEGIN
+  if (!c || !v) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "context was created with expand_queries = 0");
+  const auto& hp = c->hp;
+  const size_t words = c->v_words();
+  DevBuf<uint64_t> wide(words);
+  DevBuf<uint32_t> dv(words);
+  B200_CUDA(cudaMemcpyAsync(wide.p, v, words * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(dv.p, wide.p, words, c->stream);
+  const int stop_round = hp.nu_2 > 0 ? c->stop_round : 0;
+  for (int r = 0; r < c->g; r++) {
+    const int num_in = 1 << r;
+    launch_expand_scalar(c->dp, dv.p, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, c->stream);
+    ExpandRound R;
+    R.r = r; R.num_in = num_in; R.stop_round = stop_round;
+    R.max_bits_to_gen_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
+    R.t_auto = (POLY >> r) + 1;
+    R.t_left = (int)hp.t_exp_left; R.bits_left = c->bits_left;
+    R.w_left = pp->left.p + (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
+    if (hp.nu_2 > 0 && c->has_right) {
+      int rr = r <= c->stop_round ? r : c->stop_round;
+      R.t_right = (int)hp.t_exp_right; R.bits_right = c->bits_right;
+      R.w_right = pp->right.p + (size_t)rr * 2 * hp.t_exp_right * 2 * POLY;
+    } else {
+      R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;
+    }
+    launch_expand_round(c->dp, dv.p, R, c->stream);
+  }
+  launch_widen(wide.p, dv.p, words, c->stream);
+  B200_CUDA(cudaMemcpyAsync(v, wide.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_ct, uint64_t* out_v_firstdim,
+                         uint64_t* out_v_folding) {
+  API_BEGIN
+  if (!c || !query_ct || !out_v_firstdim) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "context was created with expand_queries = 0");
+  c->ensure_workspace(1, 1);
+  B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_ct, 2 * POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p);
+  // q_dev -> reference layout [z][j][r]
+  const size_t qwords = (size_t)c->dim0 * 2 * POLY;
+  std::vector<uint32_t> hq(qwords * 2);
+  B200_CUDA(cudaMemcpyAsync(hq.data(), c->w_qdev.p, hq.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  for (int j = 0; j < c->dim0; j++)
+    for (int z = 0; z < POLY; z++) {
+      const uint32_t* cell = hq.data() + (((size_t)(j >> 1) * 2 + (j & 1)) * POLY + z) * 4;
+      out_v_firstdim[((size_t)z * c->dim0 + j) * 2 + 0] = (uint64_t)cell[0] | ((uint64_t)cell[1] << 32);
+      out_v_firstdim[((size_t)z * c->dim0 + j) * 2 + 1] = (uint64_t)cell[2] | ((uint64_t)cell[3] << 32);
+    }
+  if (out_v_folding && c->fold_words()) {
+    DevBuf<uint64_t> wide(c->fold_words());
+    launch_widen(wide.p, c->w_vfold.p, c->fold_words(), c->stream);
+    B200_CUDA(cudaMemcpyAsync(out_v_folding, wide.p, wide.n * 8, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_pack(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* v_ct, uint64_t* out_ntt) {
+  API_BEGIN
+  if (!c || !v_ct || !out_ntt) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  const auto& hp = c->hp;
+  const size_t nn = hp.n * hp.n, outp = (hp.n + 1) * hp.n;
+  DevBuf<uint64_t> cts(nn * 2 * POLY), raw(outp * POLY), wide(outp * 2 * POLY);
+  DevBuf<uint32_t> o(outp * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(cts.p, v_ct, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_pack(c->dp, raw.p, cts.p, 2 * POLY, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+  // the reference's pack returns the NTT-form matrix (server.rs:467); the kernel already applied .raw()
+  launch_to_ntt(c->dp, o.p, raw.p, outp, c->stream);
+  launch_widen(wide.p, o.p, o.n, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out_ntt, wide.p, wide.n * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_encode(b200pir_ctx* c, const uint64_t* v_packed_raw, uint8_t* out, size_t* out_len) {
+  API_BEGIN
+  if (!c || !v_packed_raw || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  const auto& hp = c->hp;
+  const size_t words = (size_t)hp.instances * (hp.n + 1) * hp.n * POLY;
+  DevBuf<uint64_t> in(words);
+  DevBuf<uint8_t> o(c->response_bytes);
+  B200_CUDA(cudaMemcpyAsync(in.p, v_packed_raw, words * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_encode(c->dp, o.p, c->response_bytes, in.p, (int)hp.n, (int)hp.instances, c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
+  B200_CUDA(cudaMemcpyAsync(out, o.p, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  if (out_len) *out_len = c->response_bytes;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// ---------------------------------------------------------------- process_query
+int b200pir_process_query_batch_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
+                                    size_t count, uint8_t* out_dev) {
+  API_BEGIN
+  if (!c || !out_dev || !query_cts_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  check_pp(c, pp);
+  if (db->shard.count != 1) throw Error(B200PIR_E_BADARG, "sharded database: use the stage_a / stage_b entry points");
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "batch entry point needs expand_queries");
+  if (count == 0) return 0;
+  c->ensure_workspace(count, db->rows);
+  c->prof_reset();
+  B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts_dev, count * 2 * POLY * 8, cudaMemcpyDeviceToDevice, c->stream));
+  run_prepare(c, pp, count);
+  run_first_dim_and_fold(c, db, count);
+  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, count, out_dev);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_process_query_batch(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts, size_t count,
+                                uint8_t* out, size_t* out_len_each) {
+  API_BEGIN
+  if (!c || !out || !query_cts) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  check_pp(c, pp);
+  c->ensure_workspace(count, db->rows);
+  DevBuf<uint64_t> q(count * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(q.p, query_cts, q.n * 8, cudaMemcpyHostToDevice, c->stream));
+  int rc = b200pir_process_query_batch_dev(c, db, pp, q.p, count, c->w_resp.p);
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, count * c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  c->prof_collect();
+  if (out_len_each) *out_len_each = c->response_bytes;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_ct, const uint64_t* v_buf,
+                          const uint64_t* v_ct, uint8_t* out, size_t* out_len) {
+  if (!c) { g_last_error = "null ctx"; return B200PIR_E_BADARG; }
+  if (c->hp.expand_queries) {
+    if (!query_ct) { g_last_error = "query_ct is NULL"; return B200PIR_E_BADARG; }
+    return b200pir_process_query_batch(c, db, pp, query_ct, 1, out, out_len);
+  }
+  API_BEGIN
+  if (!v_buf || (!v_ct && c->hp.nu_2) || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  check_pp(c, pp);
+  if (db->shard.count != 1) throw Error(B200PIR_E_BADARG, "sharded database: use the stage_a / stage_b entry points");
+  c->ensure_workspace(1, db->rows);
+  c->prof_reset();
+  // server.rs:666-678: v_reg_reoriented = query.v_buf ; v_folding = v_ct.map(ntt)
+  DevBuf<uint64_t> vq((size_t)c->dim0 * 2 * POLY);
+  B200_CUDA(cudaMemcpyAsync(vq.p, v_buf, vq.n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_query_to_dev(c->geom(db->rows), c->w_qdev.p, vq.p, c->stream);
+  const size_t npolys = (size_t)c->hp.nu_2 * 2 * 2 * c->hp.t_gsw;
+  DevBuf<uint64_t> raw(std::max<size_t>(npolys, 1) * POLY);
+  if (npolys) {
+    B200_CUDA(cudaMemcpyAsync(raw.p, v_ct, npolys * POLY * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_to_ntt(c->dp, c->w_vfold.p, raw.p, npolys, c->stream);
+  }
+  run_prepare(c, pp, 1);
+  run_first_dim_and_fold(c, db, 1);
+  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, 1, c->w_resp.p);
+  B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  c->prof_collect();
+  if (out_len) *out_len = c->response_bytes;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_query_stage_a_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count,
+                              uint64_t* partial_dev) {
+  API_BEGIN
+  if (!c || !query_cts_dev || !partial_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  check_pp(c, pp);
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "needs expand_queries");
+  c->ensure_workspace(count, db->rows);
+  c->prof_reset();
+  B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts_dev, count * 2 * POLY * 8, cudaMemcpyDeviceToDevice, c->stream));
+  run_prepare(c, pp, count);
+  run_first_dim_and_fold(c, db, count);
+  // gather the survivors [count][slices] (stride rows*2*2048) into a dense buffer
+  B200_CUDA(cudaMemcpy2DAsync(partial_dev, 2 * POLY * 8, c->w_cts.p, (size_t)db->rows * 2 * POLY * 8, 2 * POLY * 8,
+                              count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* gathered_dev, size_t world, size_t count,
+                              uint8_t* out_dev) {
+  API_BEGIN
+  if (!c || !gathered_dev || !out_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (world == 0 || (world & (world - 1)) || world > (size_t)c->num_per) throw Error(B200PIR_E_SHAPE, "bad world size");
+  c->ensure_workspace(count, world);
+  // gathered: [world][count][slices][2][2048]  ->  w_cts as [count][slices][world][2][2048]
+  const size_t ct = 2 * POLY;
+  for (size_t w = 0; w < world; w++)
+    B200_CUDA(cudaMemcpy2DAsync(c->w_cts.p + w * ct, world * ct * 8, gathered_dev + w * count * c->slices * ct, ct * 8,
+                                ct * 8, count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
+  int dims = 0;
+  while (((size_t)1 << dims) < world) dims++;
+  {
+    b200pir_ctx::Scope sc(c, ST_FOLD);
+    if (world > 1)
+      run_fold(c, c->w_cts.p, count * c->slices, world * ct, world, dims - 1, c->w_vfold.p, c->w_vfold_neg.p, c->slices);
+  }
+  run_pack_encode(c, pp, c->w_cts.p, world * ct, count, out_dev);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+int b200pir_last_stage_ms(b200pir_ctx* c, double* out8) {
+  API_BEGIN
+  if (!c || !out8) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  c->prof_collect();
+  for (int i = 0; i < 8; i++) out8[i] = c->last_ms[i];
+  API_END
+}
+
+// ---------------------------------------------------------------- DoublePIR
+namespace {
+__global__ void k_dpir_synth(uint32_t* a, size_t words, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  a[i] = (uint32_t)z & 0x3FFFFFFFu;
+}
+b200pir_dpir* dpir_new(int device, uint64_t rows, uint64_t cols) {
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw Error(B200PIR_E_BADARG, "no such CUDA device (this library has no CPU path)");
+  if (rows == 0 || cols == 0) throw Error(B200PIR_E_SHAPE, "empty matrix");
+  B200_CUDA(cudaSetDevice(device));
+  std::unique_ptr<b200pir_dpir> m(new b200pir_dpir());
+  m->device = device; m->rows = rows; m->cols = cols;
+  B200_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  m->a.alloc(rows * cols);
+  m->b.alloc(3 * cols);
+  m->out.alloc(rows);
+  return m.release();
+}
+}  // namespace
+
+int b200pir_dpir_create(int device, const uint32_t* a, uint64_t rows, uint64_t cols, b200pir_dpir** out) {
+  API_BEGIN
+  if (!a || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  b200pir_dpir* m = dpir_new(device, rows, cols);
+  cudaError_t e = cudaMemcpy(m->a.p, a, rows * cols * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { b200pir_dpir_destroy(m); throw Error(B200PIR_E_CUDA, cudaGetErrorString(e)); }
+  *out = m;
+  API_END
+}
+int b200pir_dpir_create_synthetic(int device, uint64_t rows, uint64_t cols, uint64_t seed, b200pir_dpir** out) {
+  API_BEGIN
+  if (!out) throw Error(B200PIR_E_BADARG, "null argument");
+  b200pir_dpir* m = dpir_new(device, rows, cols);
+  size_t words = rows * cols;
+  const size_t chunk = (size_t)1 << 30;
+  for (size_t off = 0; off < words; off += chunk) {
+    size_t cur = std::min(chunk, words - off);
+    k_dpir_synth<<<(unsigned)((cur + 255) / 256), 256, 0, m->stream>>>(m->a.p + off, cur, seed + off);
+  }
+  cudaError_t e = cudaStreamSynchronize(m->stream);
+  if (e != cudaSuccess) { b200pir_dpir_destroy(m); throw Error(B200PIR_E_CUDA, cudaGetErrorString(e)); }
+  *out = m;
+  API_END
+}
+void b200pir_dpir_destroy(b200pir_dpir* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream) {
+  API_BEGIN
+  if (!m) throw Error(B200PIR_E_BADARG, "null handle");
+  cudaSetDevice(m->device);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+  m->stream = (cudaStream_t)cuda_stream;
+  m->own_stream = false;
+  API_END
+}
+int b200pir_dpir_matvec_packed_dev(b200pir_dpir* m, const uint32_t* b_dev, uint32_t* out_dev, int variant) {
+  API_BEGIN
+  if (!m || !b_dev || !out_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  cudaSetDevice(m->device);
+  launch_dpir_matvec(out_dev, m->a.p, b_dev, m->rows, m->cols, variant, m->stream);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_dpir_matvec_packed(b200pir_dpir* m, const uint32_t* b, uint32_t* out) {
+  API_BEGIN
+  if (!m || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  cudaSetDevice(m->device);
+  B200_CUDA(cudaMemcpyAsync(m->b.p, b, 3 * m->cols * 4, cudaMemcpyHostToDevice, m->stream));
+  launch_dpir_matvec(m->out.p, m->a.p, m->b.p, m->rows, m->cols, 0, m->stream);
+  B200_CUDA(cudaMemcpyAsync(out, m->out.p, m->rows * 4, cudaMemcpyDeviceToHost, m->stream));
+  B200_CUDA(cudaStreamSynchronize(m->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+}  // extern "C"

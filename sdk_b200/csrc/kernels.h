@@ -1,0 +1,95 @@
+// Launch wrappers (host side) for the sm_100a kernels.  All pointers are DEVICE pointers unless
+// noted; every launch goes to the given stream and returns immediately.
+//
+// Device formats
+//   ntt32 poly : uint32_t [n(2)][z(2048)]  residues mod q_n in the reference's (bit-reversed) NTT order
+//   raw poly   : uint64_t [z(2048)]        coefficients in [0, q]  (q itself can occur: reference quirk,
+//                                           lib/spiral-rs/src/poly.rs:387-405)
+//   matrices   : row-major [row][col] of polys, as PolyMatrixRaw / PolyMatrixNTT (poly.rs:59-71)
+#pragma once
+#include "common.cuh"
+
+namespace b200pir {
+
+static const int POLY = 2048;
+
+// ---- generic transforms (K3/K4 of SURVEY §2.3)
+// u64 ABI format [poly][n][z]  <->  in place forward / inverse NTT (ntt.rs:67-113 / :212-258)
+void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s);
+// ntt32 in place
+void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s);
+// poly.rs:613-638 to_ntt: raw u64 -> ntt32 (reduce mod q_n, forward NTT)
+void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s);
+// poly.rs:646-663 from_ntt: ntt32 -> raw u64 (inverse NTT both moduli + CRT lift)
+void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s);
+// format converters for the C ABI (u64 [n][z] words < 2^32  <->  ntt32)
+void launch_widen(uint64_t* out, const uint32_t* in, size_t words, cudaStream_t s);
+void launch_narrow(uint32_t* out, const uint64_t* in, size_t words, cudaStream_t s);
+
+// ---- first dimension (K1): server.rs:155-221
+struct MulGeom { int dim0, num_per, slices; };
+// db_dev : uint4 [slice][ii][jp = j/2][z] = {w(2jp).lo, w(2jp).hi, w(2jp+1).lo, w(2jp+1).hi}
+// q_dev  : uint4 [jp][jb][z] = {a[j][r0].lo, a[j][r0].hi, a[j][r1].lo, a[j][r1].hi},  j = 2jp+jb
+// out    : ntt32 [slice][ii][r][n][z]
+// `nq` queries are processed per DB pass (q_dev / out strided by q_stride / out_stride uint4 / u32).
+void launch_multiply(const DevParams& P, const MulGeom& G, const uint4* db_dev, const uint4* q_dev, uint32_t* out,
+                     int slice_begin, int slice_count, int nq, size_t q_stride, size_t out_stride, int variant,
+                     cudaStream_t s);
+// reference layout v_firstdim u64 [z][j][r]  ->  q_dev
+void launch_query_to_dev(const MulGeom& G, uint4* q_dev, const uint64_t* v_firstdim, cudaStream_t s);
+// Row sharding of the second-dimension index: this GPU holds global rows ii = il*count + index
+// (il = local row, G.num_per local rows).  index=0,count=1 is the whole database.
+struct Shard { int index, count; };
+// reference layout u64 [zc][num_per_global][dim0] (z in [z0,z0+zc))  ->  db_dev slice (local rows)
+void launch_db_retile_chunk(const MulGeom& G, Shard sh, uint4* db_dev_slice, const uint64_t* ref_chunk, int z0, int zc,
+                            cudaStream_t s);
+// one item poly (2048 packed words, lo|hi<<32) -> its place in db_dev   (lib/server db/loading.rs:317-359)
+void launch_db_upsert(const MulGeom& G, uint4* db_dev, int slice, int il, int j, const uint64_t* poly, cudaStream_t s);
+// synthetic DB: plaintext coeff = splitmix64(seed, ((slice*items + item)*2048 + z)) % p, recentred, NTT'd, packed
+// (server.rs:223-275 with a counter PRNG; item = j*num_per_global + ii)
+void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_dev, uint64_t seed, uint64_t pt_modulus,
+                     int slice_begin, int slice_count, cudaStream_t s);
+
+// ---- second dimension
+// mult output ntt32 [cnt][r][n][z] -> raw ciphertexts u64 [cnt][r][z]   (server.rs:707-709)
+// (== launch_from_ntt with 2*cnt polys)
+// fold (server.rs:388-427): one launch per round.  cts: raw [batch][num][2][2048] (in place);
+// step (b,i) : ct[i] <- from_ntt(Cneg * G^-1(ct[i]) + C * G^-1(ct[half+i]))
+void launch_fold_round(const DevParams& P, uint64_t* cts, size_t batch, size_t batch_stride /*u64 words*/, int half,
+                       const uint32_t* c_pos, const uint32_t* c_neg, size_t c_batch_stride /*u32 words, per query*/,
+                       int slices_per_query, int t_gsw, int bits, cudaStream_t s);
+// server.rs:505-523 get_v_folding_neg, computed pointwise: neg = (q_n - C) + G  (NTT is linear and the
+// gadget matrix is constant-coefficient, so this is the same canonical value)
+void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_folding, int count, int t_gsw, int bits,
+                        cudaStream_t s);
+
+// ---- query expansion (server.rs:19-151, 525-591)
+// v: ntt32 [2^g][2][n][z].  One round = scalar-multiply launch + expand launch.
+void launch_expand_scalar(const DevParams& P, uint32_t* v, int num_in, const uint32_t* neg1_r, cudaStream_t s);
+struct ExpandRound {
+  int r, num_in, stop_round, max_bits_to_gen_right, t_auto;
+  const uint32_t* w_left;   // ntt32 [2][t_exp_left]  for this round (or null when r == 0 / unused)
+  const uint32_t* w_right;  // ntt32 [2][t_exp_right]
+  int t_left, t_right, bits_left, bits_right;
+};
+void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, cudaStream_t s);
+// util.rs:323-355 reorient: v[idx_factor*j] -> q_dev
+void launch_reorient(const MulGeom& G, uint4* q_dev, const uint32_t* v, int idx_factor, cudaStream_t s);
+// server.rs:123-151: v_gsw[i] (ntt32 [2][2 t_gsw]) from v_inp[idx_factor*(i t_gsw + j) + idx_offset]
+void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v, int count, int idx_factor,
+                         int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv, cudaStream_t s);
+
+// ---- packing + encoding (server.rs:429-503; lib/server compute/pack.rs)
+// folded: raw ciphertexts, ct (inst, t) at folded + (inst*n*n + t)*ct_stride (u64 words);
+// w: ntt32 packing matrices; out: raw [inst][n+1][n][2048]
+void launch_pack(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+                 const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
+                 cudaStream_t s);
+void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,
+                   uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s);
+
+// ---- DoublePIR packed matvec (K6): lib/doublepir/src/matrix/kernels.rs:14-178
+void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols, int variant,
+                        cudaStream_t s);
+
+}  // namespace b200pir

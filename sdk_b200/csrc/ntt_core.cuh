@@ -1,0 +1,231 @@
+// 2048-point negacyclic NTT over one 28-bit CRT modulus, computed cooperatively by a group of
+// 256 threads holding 8 coefficients each (sm_100a; also compiles as plain C++ so the index /
+// twiddle logic can be emulated thread-by-thread on the CPU, tests/test_ntt_core_emulation.py).
+//
+// Semantics follow the reference's scalar transforms exactly (lib/spiral-rs/src/ntt.rs:67-113
+// forward, :212-258 inverse): Cooley-Tukey / Gentleman-Sande stages with the bit-reversed
+// twiddle table `table[m + i]`, Harvey lazy butterflies with W' = floor(W 2^32 / q), final
+// correction to the canonical range [0, q).  Outputs are therefore the canonical residues in the
+// reference's (bit-reversed) order; only the work decomposition is different:
+//
+//   stage bits   10 9 8 | 7 6 5 | 4 3 2 | 1 0       (stage mm pairs indices differing in bit 10-mm)
+//   pass            A       B       C      D
+//   thread owns  e = a*256 + tid            (A: a = bits 10..8)      "strided layout"
+//                e = hi*256 + a*32 + lo     (B: tid = hi*32 + lo)
+//                e = H*32 + a*4 + l2        (C: tid = H*4 + l2)
+//                e = tid*8 + k              (D: k = bits 2..0)       "contiguous layout"
+//
+// Between passes the 8 values go through shared memory with the padding phys(e) = e + 4*(e>>5)
+// (2304 words per transform), which makes every access pattern above bank-conflict free,
+// including the 128-bit accesses of pass D.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NTT_HD __host__ __device__ __forceinline__
+#else
+#define NTT_HD inline
+#endif
+
+namespace b200pir {
+
+static const int NTT_N = 2048;
+static const int NTT_LOG_N = 11;
+static const int NTT_THREADS = 256;          // threads cooperating on one transform
+static const int NTT_SMEM_WORDS = 2048 + 4 * 64;
+
+struct Twiddle { uint32_t w, wp; };          // W and W' = floor(W * 2^32 / q)
+
+NTT_HD uint32_t ntt_mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+NTT_HD uint32_t ntt_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+NTT_HD int ntt_phys(int e) { return e + 4 * (e >> 5); }
+
+// Forward (CT) butterfly, ntt.rs:92-103.  x,y in [0,4q) -> x',y' in [0,4q).
+NTT_HD void bfly_fwd(uint32_t& x, uint32_t& y, Twiddle tw, uint32_t q, uint32_t two_q) {
+  uint32_t cx = ntt_min(x, x - two_q);                 // x - 2q if x >= 2q (unsigned wrap + min)
+  uint32_t qt = ntt_mulhi(y, tw.wp);
+  uint32_t t = tw.w * y - qt * q;                      // in [0, 2q)
+  x = cx + t;
+  y = cx + two_q - t;
+}
+// Inverse (GS) butterfly with the halving folded in, ntt.rs:236-248.  x,y in [0,2q) -> [0,2q).
+NTT_HD void bfly_inv(uint32_t& x, uint32_t& y, Twiddle tw, uint32_t q, uint32_t two_q) {
+  uint32_t tt = two_q - y + x;                         // in (0, 4q)
+  uint32_t s = x + y;
+  uint32_t cx = ntt_min(s, s - two_q);                 // x + y - 2q if x + y >= 2q
+  uint32_t ht = ntt_mulhi(tt, tw.wp);
+  x = (cx + ((tt & 1u) ? q : 0u)) >> 1;
+  y = tw.w * tt - ht * q;
+}
+// final correction, ntt.rs:107-111 / :253-256
+NTT_HD uint32_t ntt_canon(uint32_t v, uint32_t q, uint32_t two_q) {
+  v = ntt_min(v, v - two_q);
+  return ntt_min(v, v - q);
+}
+
+// Three butterfly stages over the 3 index bits held in registers (a = 0..7, bit2 = first stage).
+// tw_base[s] is the table offset 2^mm of stage s; grp[s] the group index of the thread's a=0
+// element at that stage (group of element a is grp[s] + (a >> (3 - s))).
+NTT_HD void radix8_fwd(uint32_t (&x)[8], const Twiddle* tab, int m0, int g0, uint32_t q, uint32_t two_q) {
+  // stage s=0: pairs (a, a+4); group = g0                    table idx m0 + g0
+  // stage s=1: pairs (a, a+2); group = 2*g0 + (a>>2)         table idx 2*m0 + ...
+  // stage s=2: pairs (a, a+1); group = 4*g0 + (a>>1)
+  Twiddle t0 = tab[m0 + g0];
+#pragma unroll
+  for (int a = 0; a < 4; a++) bfly_fwd(x[a], x[a + 4], t0, q, two_q);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    Twiddle t1 = tab[2 * m0 + 2 * g0 + h];
+#pragma unroll
+    for (int a = 0; a < 2; a++) bfly_fwd(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
+  }
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    Twiddle t2 = tab[4 * m0 + 4 * g0 + h];
+    bfly_fwd(x[2 * h], x[2 * h + 1], t2, q, two_q);
+  }
+}
+NTT_HD void radix8_inv(uint32_t (&x)[8], const Twiddle* tab, int m0, int g0, uint32_t q, uint32_t two_q) {
+  // exact reverse order of radix8_fwd
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    Twiddle t2 = tab[4 * m0 + 4 * g0 + h];
+    bfly_inv(x[2 * h], x[2 * h + 1], t2, q, two_q);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    Twiddle t1 = tab[2 * m0 + 2 * g0 + h];
+#pragma unroll
+    for (int a = 0; a < 2; a++) bfly_inv(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
+  }
+  Twiddle t0 = tab[m0 + g0];
+#pragma unroll
+  for (int a = 0; a < 4; a++) bfly_inv(x[a], x[a + 4], t0, q, two_q);
+}
+
+// ---- per-pass thread-local steps.  `tid` in [0,256).  smem = this transform's 2304-word buffer.
+// Pass A (stages 0..2) on the strided layout; then store.
+NTT_HD void fwd_pass_a(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  radix8_fwd(x, tab, 1, 0, q, two_q);                                  // m = 1,2,4 ; group base 0
+#pragma unroll
+  for (int a = 0; a < 8; a++) smem[ntt_phys(a * 256 + tid)] = x[a];
+}
+// Pass B (stages 3..5): e = hi*256 + a*32 + lo
+NTT_HD void fwd_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  int hi = tid >> 5, lo = tid & 31;
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(hi * 256 + a * 32 + lo)];
+  radix8_fwd(x, tab, 8, hi, q, two_q);                                 // m = 8,16,32
+#pragma unroll
+  for (int a = 0; a < 8; a++) smem[ntt_phys(hi * 256 + a * 32 + lo)] = x[a];
+}
+// Pass C (stages 6..8): e = H*32 + a*4 + l2
+NTT_HD void fwd_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  int H = tid >> 2, l2 = tid & 3;
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(H * 32 + a * 4 + l2)];
+  radix8_fwd(x, tab, 64, H, q, two_q);                                 // m = 64,128,256
+#pragma unroll
+  for (int a = 0; a < 8; a++) smem[ntt_phys(H * 32 + a * 4 + l2)] = x[a];
+}
+// Pass D (stages 9,10) on the contiguous layout e = tid*8 + k, then canonicalise.
+NTT_HD void fwd_pass_d(int tid, uint32_t (&x)[8], const uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  int base = ntt_phys(tid * 8);                                         // 8 contiguous words (two 16-byte chunks)
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = smem[base + k];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {                                         // stage 9: m=512, group = 2*tid + h, pairs (k, k+2)
+    Twiddle t = tab[512 + 2 * tid + h];
+    bfly_fwd(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
+    bfly_fwd(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
+  }
+#pragma unroll
+  for (int h = 0; h < 4; h++) {                                         // stage 10: m=1024, group = 4*tid + h
+    Twiddle t = tab[1024 + 4 * tid + h];
+    bfly_fwd(x[2 * h], x[2 * h + 1], t, q, two_q);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = ntt_canon(x[k], q, two_q);
+}
+
+// Inverse: contiguous layout in (values in [0,2q)), strided layout out (canonical).
+NTT_HD void inv_pass_d(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {                                         // stage mm=10
+    Twiddle t = tab[1024 + 4 * tid + h];
+    bfly_inv(x[2 * h], x[2 * h + 1], t, q, two_q);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {                                         // stage mm=9
+    Twiddle t = tab[512 + 2 * tid + h];
+    bfly_inv(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
+    bfly_inv(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
+  }
+  int base = ntt_phys(tid * 8);
+#pragma unroll
+  for (int k = 0; k < 8; k++) smem[base + k] = x[k];
+}
+NTT_HD void inv_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  int H = tid >> 2, l2 = tid & 3;
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(H * 32 + a * 4 + l2)];
+  radix8_inv(x, tab, 64, H, q, two_q);
+#pragma unroll
+  for (int a = 0; a < 8; a++) smem[ntt_phys(H * 32 + a * 4 + l2)] = x[a];
+}
+NTT_HD void inv_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+  int hi = tid >> 5, lo = tid & 31;
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(hi * 256 + a * 32 + lo)];
+  radix8_inv(x, tab, 8, hi, q, two_q);
+#pragma unroll
+  for (int a = 0; a < 8; a++) smem[ntt_phys(hi * 256 + a * 32 + lo)] = x[a];
+}
+NTT_HD void inv_pass_a(int tid, uint32_t (&x)[8], const uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(a * 256 + tid)];
+  radix8_inv(x, tab, 1, 0, q, two_q);
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = ntt_canon(x[a], q, two_q);
+}
+
+#if defined(__CUDACC__)
+// Group-cooperative transforms.  `gsync()` must synchronise the 256 threads of the group (and
+// order their shared-memory accesses).  On entry to either function the group's smem buffer must
+// not be in use; on return it may still be read by slower threads, so callers issue gsync()
+// before the next transform reuses it (both functions start with that barrier themselves).
+template <typename Sync>
+__device__ __forceinline__ void ntt_forward_group(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab,
+                                                  uint32_t q, Sync gsync) {
+  const uint32_t two_q = 2 * q;
+  gsync();
+  fwd_pass_a(tid, x, smem, tab, q, two_q);
+  gsync();
+  fwd_pass_b(tid, x, smem, tab, q, two_q);
+  gsync();
+  fwd_pass_c(tid, x, smem, tab, q, two_q);
+  gsync();
+  fwd_pass_d(tid, x, smem, tab, q, two_q);
+}
+template <typename Sync>
+__device__ __forceinline__ void ntt_inverse_group(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab,
+                                                  uint32_t q, Sync gsync) {
+  const uint32_t two_q = 2 * q;
+  gsync();
+  inv_pass_d(tid, x, smem, tab, q, two_q);
+  gsync();
+  inv_pass_c(tid, x, smem, tab, q, two_q);
+  gsync();
+  inv_pass_b(tid, x, smem, tab, q, two_q);
+  gsync();
+  inv_pass_a(tid, x, smem, tab, q, two_q);
+}
+#endif
+
+}  // namespace b200pir

@@ -1,0 +1,635 @@
+// Ring-arithmetic kernels for the Spiral second dimension, query expansion and packing (sm_100a).
+//
+// Every kernel here runs CTAs of 512 threads = two groups of 256; group g works modulo q_g, so the
+// two CRT halves of a polynomial are transformed side by side and can be CRT-lifted inside the CTA.
+// A "digit external product" (gadget-decompose a raw polynomial, forward-NTT each digit polynomial,
+// multiply-accumulate with the columns of an NTT-domain key matrix) is the common inner loop of
+// fold_ciphertexts (server.rs:388-427), coefficient_expansion (:19-121), regev_to_gsw (:123-151)
+// and pack (:429-468): it is written once (digits_mac) and fused with the surrounding inverse
+// transforms, automorphisms and CRT lifts so intermediates never leave the SM.
+#include "kernels.h"
+
+namespace b200pir {
+
+namespace {
+
+constexpr int CTA = 512;
+
+struct Grp {
+  int tid;              // 0..255 inside the group
+  int n;                // modulus index handled by this group
+  uint32_t q;
+  uint64_t cr1;
+  const Twiddle* fwd;
+  const Twiddle* inv;
+  uint32_t* smem;       // this group's NTT exchange buffer (NTT_SMEM_WORDS)
+};
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+__device__ __forceinline__ Grp make_grp(const DevParams& P, uint32_t* ntt_smem) {
+  Grp g;
+  g.n = threadIdx.x >> 8;
+  g.tid = threadIdx.x & 255;
+  g.q = P.q[g.n];
+  g.cr1 = P.cr1[g.n];
+  g.fwd = P.fwd[g.n];
+  g.inv = P.inv[g.n];
+  g.smem = ntt_smem + g.n * NTT_SMEM_WORDS;
+  return g;
+}
+
+// contiguous-layout load/store of 8 ntt32 words (two 16-byte accesses)
+__device__ __forceinline__ void ld8(uint32_t (&x)[8], const uint32_t* p) {
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void ld8_ro(uint32_t (&x)[8], const uint32_t* p) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void st8(uint32_t* p, const uint32_t (&x)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<uint4*>(p + 4) = make_uint4(x[4], x[5], x[6], x[7]);
+}
+
+template <int ROWS>
+__device__ __forceinline__ void acc_reduce(uint64_t (&acc)[ROWS][8], const Grp& g) {
+#pragma unroll
+  for (int r = 0; r < ROWS; r++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[r][k] = barrett64(acc[r][k], g.cr1, g.q);
+}
+
+// acc[r][.] += sum_k  C[r][col0 + k*col_step] (.) NTT(digit_k(v))     (pointwise, this group's modulus)
+// v[a] = raw coefficient at index a*256 + tid (strided layout).  c0 points at element (row 0, first
+// column) of this group's modulus, offset by tid*8.  `cnt` counts products held per accumulator.
+template <int ROWS>
+__device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
+                                           int bits, const uint32_t* c0, size_t col_step, size_t row_step,
+                                           const Grp& g) {
+  const uint64_t mask = (1ull << bits) - 1;
+  for (int k = 0; k < ndig; k++) {
+    uint32_t x[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a] = gadget_digit(v[a], k, bits, mask);
+    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+    const uint32_t* c = c0 + (size_t)k * col_step;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      uint32_t cv[8];
+      ld8_ro(cv, c + (size_t)r * row_step);
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x[e] * cv[e];
+    }
+    if (++cnt >= 200) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+  }
+}
+
+// CRT-lift one polynomial whose two residue vectors sit in the two groups' registers (strided layout,
+// canonical) and hand the 4 coefficients this thread is responsible for to `sink(z, value)`.
+// res: 2*2048-word exchange buffer.  Thread (g,tid) lifts z = a*256 + tid for a in [4g, 4g+4).
+template <typename Sink>
+__device__ __forceinline__ void crt_lift(const uint32_t (&x)[8], uint32_t* res, const Grp& g, const DevParams& P,
+                                         Sink sink) {
+  __syncthreads();                       // previous users of `res` are done
+#pragma unroll
+  for (int a = 0; a < 8; a++) res[g.n * POLY + a * 256 + g.tid] = x[a];
+  __syncthreads();
+#pragma unroll
+  for (int a4 = 0; a4 < 4; a4++) {
+    int z = (g.n * 4 + a4) * 256 + g.tid;
+    sink(z, crt_compose(res[z], res[POLY + z], P));
+  }
+}
+
+// ------------------------------------------------------------------ plain transforms
+__global__ void __launch_bounds__(CTA) k_ntt32(DevParams P, uint32_t* polys, int inverse) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  Grp g = make_grp(P, ntt_smem);
+  uint32_t* p = polys + ((size_t)blockIdx.x * 2 + g.n) * POLY;
+  uint32_t x[8];
+  if (!inverse) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a] = p[a * 256 + g.tid];
+    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+    st8(p + g.tid * 8, x);
+  } else {
+    ld8(x, p + g.tid * 8);
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+#pragma unroll
+    for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
+  }
+}
+// u64 ABI words (ntt.rs:68 / :213 operate on &mut [u64]); values are truncated to 32 bits exactly as
+// the reference's forward butterfly does (`as u32`, ntt.rs:93-94).
+__global__ void __launch_bounds__(CTA) k_ntt_u64(DevParams P, uint64_t* polys, int inverse) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  Grp g = make_grp(P, ntt_smem);
+  uint64_t* p = polys + ((size_t)blockIdx.x * 2 + g.n) * POLY;
+  uint32_t x[8];
+  if (!inverse) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a] = (uint32_t)p[a * 256 + g.tid];
+    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+#pragma unroll
+    for (int k = 0; k < 8; k++) p[g.tid * 8 + k] = x[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = (uint32_t)p[g.tid * 8 + k];
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+#pragma unroll
+    for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
+  }
+}
+__global__ void __launch_bounds__(CTA) k_to_ntt(DevParams P, uint32_t* out, const uint64_t* raw) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  Grp g = make_grp(P, ntt_smem);
+  const uint64_t* src = raw + (size_t)blockIdx.x * POLY;
+  uint32_t x[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) x[a] = barrett64(src[a * 256 + g.tid], g.cr1, g.q);
+  ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+  st8(out + ((size_t)blockIdx.x * 2 + g.n) * POLY + g.tid * 8, x);
+}
+__global__ void __launch_bounds__(CTA) k_from_ntt(DevParams P, uint64_t* out, const uint32_t* in) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  __shared__ uint32_t res[2 * POLY];
+  Grp g = make_grp(P, ntt_smem);
+  uint32_t x[8];
+  ld8(x, in + ((size_t)blockIdx.x * 2 + g.n) * POLY + g.tid * 8);
+  ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+  uint64_t* dst = out + (size_t)blockIdx.x * POLY;
+  crt_lift(x, res, g, P, [&](int z, uint64_t v) { dst[z] = v; });
+}
+__global__ void k_widen(uint64_t* out, const uint32_t* in, size_t words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) out[i] = in[i];
+}
+__global__ void k_narrow(uint32_t* out, const uint64_t* in, size_t words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) out[i] = (uint32_t)in[i];
+}
+
+// ------------------------------------------------------------------ fold (one round)
+// server.rs:405-425.  CTA = one (batch entry, i) step.
+__global__ void __launch_bounds__(CTA, 1)
+k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const uint32_t* c_pos, const uint32_t* c_neg,
+             size_t c_batch_stride, int slices_per_query, int t_gsw, int bits) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  __shared__ uint32_t res[2 * POLY];
+  Grp g = make_grp(P, ntt_smem);
+  const int b = blockIdx.x / half, i = blockIdx.x % half;
+  uint64_t* base = cts + (size_t)b * batch_stride;
+  const size_t qoff = (size_t)(b / slices_per_query) * c_batch_stride;
+  const int cols = 2 * t_gsw;
+  const size_t col_step = (size_t)2 * 2 * POLY;          // column index advances by rdim = 2 per digit
+  const size_t row_step = (size_t)cols * 2 * POLY;
+
+  uint64_t acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[r][e] = 0;
+  int cnt = 0;
+#pragma unroll 1
+  for (int src = 0; src < 2; src++) {
+    const uint64_t* ct = base + (size_t)(src == 0 ? i : half + i) * 2 * POLY;
+    const uint32_t* C = (src == 0 ? c_neg : c_pos) + qoff;
+#pragma unroll 1
+    for (int rho = 0; rho < 2; rho++) {
+      uint64_t v[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) v[a] = ct[rho * POLY + a * 256 + g.tid];
+      // G^-1 row index = rho + 2k  -> key-matrix column rho + 2k
+      const uint32_t* c0 = C + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
+      digits_mac<2>(acc, cnt, v, t_gsw, bits, c0, col_step, row_step, g);
+    }
+  }
+  uint64_t* dst = base + (size_t)i * 2 * POLY;
+#pragma unroll 1
+  for (int r = 0; r < 2; r++) {
+    uint32_t x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = barrett64(acc[r][e], g.cr1, g.q);
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    uint64_t* d = dst + r * POLY;
+    crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
+  }
+}
+
+// neg[k][r][c] = (q_n - C[k][r][c]) + G[r][c]   with G[i][i + 2j] = 2^{bits*j}  (gadget.rs:11-32)
+__global__ void k_folding_neg(DevParams P, uint32_t* out, const uint32_t* vf, size_t total, int t_gsw, int bits) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int n = (int)((idx / POLY) & 1);
+  size_t poly = idx / (2 * POLY);            // ((k*2 + r)*cols + c)
+  int cols = 2 * t_gsw;
+  int c = (int)(poly % cols);
+  int r = (int)((poly / cols) & 1);
+  uint32_t q = P.q[n];
+  uint32_t v = vf[idx];
+  uint32_t neg = v == 0 ? 0u : q - v;
+  uint32_t gval = 0;
+  if ((c & 1) == r) {
+    int j = c >> 1;
+    if (bits * j < 64) gval = barrett64(1ull << (bits * j), P.cr1[n], q);
+  }
+  out[idx] = addmod(neg, gval, q);
+}
+
+// ------------------------------------------------------------------ query expansion
+// server.rs:105-110: v[num_in + i] = v[i] (.) neg1
+__global__ void k_expand_scalar(DevParams P, uint32_t* v, int num_in, const uint32_t* neg1) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // over num_in * 2 rows * 2 mod * 2048
+  size_t total = (size_t)num_in * 4 * POLY;
+  if (idx >= total) return;
+  int z = (int)(idx % POLY);
+  int n = (int)((idx / POLY) & 1);
+  uint32_t a = v[idx], b = neg1[n * POLY + z];
+  v[total + idx] = barrett64((uint64_t)a * b, P.cr1[n], P.q[n]);
+}
+
+// server.rs:39-103 action_expand for ciphertext index blockIdx.x of round R.r (in place on v).
+__global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* v, ExpandRound R) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint64_t* autom = reinterpret_cast<uint64_t*>(res + 2 * POLY);      // [2][2048]
+  Grp g = make_grp(P, ntt_smem);
+
+  const int i = blockIdx.x;
+  const int ih = i < R.num_in ? i : i - R.num_in;       // index within its half (server.rs:112-119)
+  if ((R.stop_round > 0 && R.r > R.stop_round && (ih & 1)) ||
+      (R.stop_round > 0 && R.r == R.stop_round && (ih & 1) && (ih / 2) >= R.max_bits_to_gen_right))
+    return;
+  const bool left = (R.r != 0) && ((ih & 1) == 0);
+  const uint32_t* W = left ? R.w_left : R.w_right;
+  const int t_exp = left ? R.t_left : R.t_right;
+  const int bits = left ? R.bits_left : R.bits_right;
+
+  uint32_t* vi = v + (size_t)i * 4 * POLY;
+  uint32_t keep[2][8];
+  // from_ntt + automorph (poly.rs:393-405), scattered into shared memory
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    uint32_t x[8];
+    ld8(x, vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
+#pragma unroll
+    for (int e = 0; e < 8; e++) keep[rho][e] = x[e];
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    uint64_t* au = autom + rho * POLY;
+    const int t_auto = R.t_auto;
+    const uint64_t Q = P.modulus;
+    crt_lift(x, res, g, P, [&](int z, uint64_t val) {
+      unsigned prod = (unsigned)z * (unsigned)t_auto;
+      unsigned num = prod >> NTT_LOG_N, rem = prod & (POLY - 1);
+      au[rem] = (num & 1u) ? Q - val : val;             // zero maps to q, as in the reference
+    });
+  }
+  __syncthreads();
+  uint64_t acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[r][e] = 0;
+  int cnt = 0;
+  {
+    uint64_t vv[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) vv[a] = autom[a * 256 + g.tid];
+    // gadget_invert_rdim(.., rdim = 1): digit k -> key column k  (server.rs:82-89)
+    const uint32_t* c0 = W + (size_t)g.n * POLY + g.tid * 8;
+    digits_mac<2>(acc, cnt, vv, t_exp, bits, c0, (size_t)2 * POLY, (size_t)t_exp * 2 * POLY, g);
+  }
+  uint32_t y[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) y[a] = barrett64(autom[POLY + a * 256 + g.tid], g.cr1, g.q);
+  ntt_forward_group(g.tid, y, g.smem, g.fwd, g.q, CtaSync());
+#pragma unroll
+  for (int rho = 0; rho < 2; rho++) {
+    uint32_t o[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      uint32_t s = addmod(keep[rho][e], barrett64(acc[rho][e], g.cr1, g.q), g.q);
+      o[e] = rho ? addmod(s, y[e], g.q) : s;
+    }
+    st8(vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8, o);
+  }
+}
+
+// util.rs:323-355
+__global__ void k_reorient(MulGeom G, uint4* q_dev, const uint32_t* v, int idx_factor) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // over dim0 * 2048
+  if (idx >= (size_t)G.dim0 * POLY) return;
+  int z = (int)(idx % POLY), j = (int)(idx / POLY);
+  const uint32_t* ct = v + (size_t)idx_factor * j * 4 * POLY;
+  uint4 o = make_uint4(ct[z], ct[POLY + z], ct[2 * POLY + z], ct[3 * POLY + z]);
+  q_dev[((size_t)(j >> 1) * 2 + (j & 1)) * POLY + z] = o;
+}
+
+// server.rs:134-150.  CTA = (gsw index i, digit j).
+__global__ void __launch_bounds__(CTA, 1)
+k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, int idx_offset, const uint32_t* v_conv,
+               int t_gsw, int t_conv, int bits_conv) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint64_t* raw = reinterpret_cast<uint64_t*>(res + 2 * POLY);        // [2][2048]
+  Grp g = make_grp(P, ntt_smem);
+  const int i = blockIdx.x / t_gsw, j = blockIdx.x % t_gsw;
+  const int idx_inp = idx_factor * (i * t_gsw + j) + idx_offset;
+  const uint32_t* inp = v + (size_t)idx_inp * 4 * POLY;
+  const int cols = 2 * t_gsw;
+  uint32_t* out = v_gsw + (size_t)i * 2 * cols * 2 * POLY;
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    uint32_t x[8];
+    ld8(x, inp + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
+    st8(out + (((size_t)rho * cols + 2 * j + 1) * 2 + g.n) * POLY + g.tid * 8, x);      // ct.copy_into(.., 0, 2j+1)
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    uint64_t* d = raw + rho * POLY;
+    crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
+  }
+  __syncthreads();
+  uint64_t acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[r][e] = 0;
+  int cnt = 0;
+  const int ccols = 2 * t_conv;
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    uint64_t vv[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) vv[a] = raw[rho * POLY + a * 256 + g.tid];
+    const uint32_t* c0 = v_conv + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
+    digits_mac<2>(acc, cnt, vv, t_conv, bits_conv, c0, (size_t)2 * 2 * POLY, (size_t)ccols * 2 * POLY, g);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    uint32_t o[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) o[e] = barrett64(acc[r][e], g.cr1, g.q);
+    st8(out + (((size_t)r * cols + 2 * j) * 2 + g.n) * POLY + g.tid * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ pack (v0: server.rs:429-468; v1: lib/server pack.rs:45-98)
+template <int ROWS>
+__global__ void __launch_bounds__(CTA, 1)
+k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride, const uint32_t* v_packing, int t_conv,
+       int bits, int version) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint64_t* rawbuf = reinterpret_cast<uint64_t*>(res + 2 * POLY);     // [2048]
+  Grp g = make_grp(P, ntt_smem);
+  constexpr int n = ROWS - 1;
+  const int inst = blockIdx.x / n, c = blockIdx.x % n;
+  const size_t mat_words = (size_t)ROWS * t_conv * 2 * POLY;
+  const size_t row_step = (size_t)t_conv * 2 * POLY, col_step = (size_t)2 * POLY;
+
+  uint32_t vint[ROWS][8];
+#pragma unroll
+  for (int m = 0; m < ROWS; m++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) vint[m][e] = 0;
+
+#pragma unroll 1
+  for (int r = 0; r < n; r++) {
+    const uint64_t* ct = folded + ((size_t)inst * n * n + (size_t)r * n + c) * ct_stride;
+    const uint32_t* W = v_packing + (version == 0 ? (size_t)r * mat_words : 0);
+    uint64_t acc[ROWS][8];
+#pragma unroll
+    for (int m = 0; m < ROWS; m++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[m][e] = 0;
+    int cnt = 0;
+    {
+      uint64_t vv[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) vv[a] = ct[a * 256 + g.tid];
+      digits_mac<ROWS>(acc, cnt, vv, t_conv, bits, W + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
+    }
+    uint32_t y[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) y[a] = barrett64(ct[POLY + a * 256 + g.tid], g.cr1, g.q);
+    ntt_forward_group(g.tid, y, g.smem, g.fwd, g.q, CtaSync());
+    uint32_t prod[ROWS][8];
+#pragma unroll
+    for (int m = 0; m < ROWS; m++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) prod[m][e] = barrett64(acc[m][e], g.cr1, g.q);
+    if (version == 0) {
+      // add_into_at(v_int, ct_2_ntt, 1 + r, 0); add_into(v_int, prod)
+#pragma unroll
+      for (int m = 0; m < ROWS; m++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          uint32_t s = addmod(vint[m][e], prod[m][e], g.q);
+          vint[m][e] = (m == 1 + r) ? addmod(s, y[e], g.q) : s;
+        }
+    } else {
+      // add_into_at(prod, ct_2_ntt, 1, 0); then r row shifts through w_shift (= v_packing[1])
+#pragma unroll
+      for (int e = 0; e < 8; e++) prod[1][e] = addmod(prod[1][e], y[e], g.q);
+      const uint32_t* Wshift = v_packing + mat_words;
+#pragma unroll 1
+      for (int sft = 0; sft < r; sft++) {
+        uint32_t x[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = prod[0][e];
+        ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+        crt_lift(x, res, g, P, [&](int z, uint64_t val) { rawbuf[z] = val; });
+        __syncthreads();
+        uint64_t vv[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) vv[a] = rawbuf[a * 256 + g.tid];
+#pragma unroll
+        for (int m = 0; m < ROWS; m++)
+#pragma unroll
+          for (int e = 0; e < 8; e++) acc[m][e] = 0;
+        cnt = 0;
+        digits_mac<ROWS>(acc, cnt, vv, t_conv, bits, Wshift + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
+        uint32_t np[ROWS][8];
+#pragma unroll
+        for (int m = 0; m < ROWS; m++)
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            uint32_t p1 = barrett64(acc[m][e], g.cr1, g.q);
+            // shifted rest rows: new[1] = old[n]; new[1+k] = old[k] (k = 1..n-1); new[0] gets nothing
+            uint32_t p2 = (m == 0) ? 0u : (m == 1 ? prod[n][e] : prod[m - 1][e]);
+            np[m][e] = addmod(p1, p2, g.q);
+          }
+#pragma unroll
+        for (int m = 0; m < ROWS; m++)
+#pragma unroll
+          for (int e = 0; e < 8; e++) prod[m][e] = np[m][e];
+      }
+#pragma unroll
+      for (int m = 0; m < ROWS; m++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) vint[m][e] = addmod(vint[m][e], prod[m][e], g.q);
+    }
+  }
+  // result.copy_into(v_int, 0, c); packed_ct.raw()   (server.rs:464, :736)
+#pragma unroll 1
+  for (int m = 0; m < ROWS; m++) {
+    uint32_t x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = vint[m][e];
+    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    uint64_t* d = out_raw + (((size_t)inst * ROWS + m) * n + c) * POLY;
+    crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
+  }
+}
+
+// ------------------------------------------------------------------ encode (server.rs:470-503)
+// arith.rs:429-444
+__device__ __forceinline__ uint64_t rescale_dev(uint64_t a, uint64_t inp_mod, uint64_t out_mod) {
+  typedef __int128 i128;
+  long long inp_mod_i = (long long)inp_mod;
+  long long inp_val = (long long)(a % inp_mod);
+  if (inp_val >= inp_mod_i / 2) inp_val -= inp_mod_i;
+  long long sign = inp_val >= 0 ? 1 : -1;
+  i128 val = (i128)inp_val * (i128)out_mod;
+  i128 result = (val + (i128)(sign * (inp_mod_i / 2))) / (i128)inp_mod;
+  i128 om = (i128)out_mod;
+  result = (result + (i128)((inp_mod / out_mod) * out_mod) + 2 * om) % om;
+  return (uint64_t)((result + om) % om);
+}
+// One thread per output 64-bit word.  Stream = per instance: n*2048 values of q2_bits (row 0 of the
+// packed matrix), then n*n*2048 values of q1_bits (rows 1..n), LSB-first (util.rs:303-321).
+__global__ void k_encode(DevParams P, uint64_t* out, size_t out_words, const uint64_t* packed, int n, int instances,
+                         uint64_t q2, int q2_bits, uint64_t q1, int q1_bits) {
+  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= out_words) return;
+  const uint64_t first_cnt = (uint64_t)n * POLY, rest_cnt = (uint64_t)n * n * POLY;
+  const uint64_t inst_bits = first_cnt * q2_bits + rest_cnt * q1_bits;
+  uint64_t lo_bit = (uint64_t)w * 64, hi_bit = lo_bit + 64;
+  uint64_t word = 0;
+  uint64_t bit = lo_bit;
+  while (bit < hi_bit) {
+    uint64_t inst = bit / inst_bits;
+    if (inst >= (uint64_t)instances) break;
+    uint64_t off = bit - inst * inst_bits;
+    const uint64_t* pk = packed + inst * (uint64_t)(n + 1) * n * POLY;
+    uint64_t vstart, val;
+    int vb;
+    if (off < first_cnt * q2_bits) {
+      uint64_t vi = off / q2_bits;
+      vstart = inst * inst_bits + vi * q2_bits;
+      vb = q2_bits;
+      val = rescale_dev(pk[vi], P.modulus, q2);
+    } else {
+      uint64_t o2 = off - first_cnt * q2_bits;
+      uint64_t vi = o2 / q1_bits;
+      vstart = inst * inst_bits + first_cnt * q2_bits + vi * q1_bits;
+      vb = q1_bits;
+      val = rescale_dev(pk[first_cnt + vi], P.modulus, q1);
+    }
+    val &= (vb >= 64) ? ~0ull : ((1ull << vb) - 1);
+    // bits [vstart, vstart+vb) of the stream hold val; copy the part overlapping this word
+    if (vstart >= lo_bit) word |= val << (vstart - lo_bit);
+    else word |= val >> (lo_bit - vstart);
+    bit = vstart + vb;
+  }
+  out[w] = word;
+}
+
+inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
+const size_t kDynSmemBig = (size_t)(2 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t)2 * POLY * 8;
+
+}  // namespace
+
+void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s) {
+  if (count) k_ntt_u64<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+}
+void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s) {
+  if (count) k_ntt32<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+}
+void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s) {
+  if (count) k_to_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out, raw);
+}
+void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
+  if (count) k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);
+}
+void launch_widen(uint64_t* out, const uint32_t* in, size_t words, cudaStream_t s) {
+  if (words) k_widen<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
+}
+void launch_narrow(uint32_t* out, const uint64_t* in, size_t words, cudaStream_t s) {
+  if (words) k_narrow<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
+}
+void launch_fold_round(const DevParams& P, uint64_t* cts, size_t batch, size_t batch_stride, int half,
+                       const uint32_t* c_pos, const uint32_t* c_neg, size_t c_batch_stride, int slices_per_query,
+                       int t_gsw, int bits, cudaStream_t s) {
+  if (batch == 0 || half == 0) return;
+  k_fold_round<<<(unsigned)(batch * half), CTA, 0, s>>>(P, cts, batch_stride, half, c_pos, c_neg, c_batch_stride,
+                                                        slices_per_query, t_gsw, bits);
+}
+void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_folding, int count, int t_gsw, int bits,
+                        cudaStream_t s) {
+  size_t total = (size_t)count * 2 * 2 * t_gsw * 2 * POLY;
+  if (total) k_folding_neg<<<grid1d(total, 256), 256, 0, s>>>(P, out, v_folding, total, t_gsw, bits);
+}
+void launch_expand_scalar(const DevParams& P, uint32_t* v, int num_in, const uint32_t* neg1_r, cudaStream_t s) {
+  size_t total = (size_t)num_in * 4 * POLY;
+  k_expand_scalar<<<grid1d(total, 256), 256, 0, s>>>(P, v, num_in, neg1_r);
+}
+void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
+    attr_set = true;
+  }
+  k_expand_round<<<(unsigned)(2 * R.num_in), CTA, kDynSmemBig, s>>>(P, v, R);
+}
+void launch_reorient(const MulGeom& G, uint4* q_dev, const uint32_t* v, int idx_factor, cudaStream_t s) {
+  size_t total = (size_t)G.dim0 * POLY;
+  k_reorient<<<grid1d(total, 256), 256, 0, s>>>(G, q_dev, v, idx_factor);
+}
+void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v, int count, int idx_factor,
+                         int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv, cudaStream_t s) {
+  if (count == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_regev_to_gsw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
+    attr_set = true;
+  }
+  k_regev_to_gsw<<<(unsigned)(count * t_gsw), CTA, kDynSmemBig, s>>>(P, v_gsw, v, idx_factor, idx_offset, v_conv, t_gsw,
+                                                                     t_conv, bits_conv);
+}
+template <int ROWS>
+static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+                          const uint32_t* v_packing, int instances, int t_conv, int bits_conv, int version,
+                          cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_pack<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
+    attr_set = true;
+  }
+  k_pack<ROWS><<<(unsigned)(instances * (ROWS - 1)), CTA, kDynSmemBig, s>>>(P, out_raw, folded, ct_stride, v_packing,
+                                                                           t_conv, bits_conv, version);
+}
+void launch_pack(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+                 const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
+                 cudaStream_t s) {
+  switch (n) {
+    case 1: launch_pack_t<2>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 2: launch_pack_t<3>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 3: launch_pack_t<4>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 4: launch_pack_t<5>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
+    default: throw Error(-2, "pack: n must be 1..4");
+  }
+}
+void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,
+                   uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s) {
+  size_t words = out_bytes / 8;
+  k_encode<<<grid1d(words, 128), 128, 0, s>>>(P, reinterpret_cast<uint64_t*>(out), words, packed_raw, n, instances, q2,
+                                              q2_bits, q1, q1_bits);
+}
+
+}  // namespace b200pir

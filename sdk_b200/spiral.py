@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's Spiral server interface over the C ABI.
+
+Names, argument meaning and error behaviour follow lib/spiral-rs/src/{server,ntt,poly}.rs: the same
+functions exist (process_query, multiply_reg_by_database, fold_ciphertexts, ntt_forward, ...),
+they take the same data in the same layouts (numpy uint64 arrays standing in for &[u64] /
+AlignedMemory64), and shape violations raise (the reference panics).  All arithmetic happens in the
+CUDA library; this module never computes."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import LIB, CParams, check, B200PirError  # noqa: F401
+
+POLY_LEN = 2048          # lib/spiral-rs/src/util.rs:246
+CRT_COUNT = 2
+MODULI = (268369921, 249561089)   # util.rs:247
+
+
+def _ptr(a, dtype=np.uint64):
+    if a is None:
+        return None
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("expected a C-contiguous numpy array of dtype %s" % np.dtype(dtype).name)
+    return a.ctypes.data
+
+
+class Params:
+    """spiral_rs::params::Params (params.rs:49-82) + the GPU context built from it."""
+
+    FIELDS = ("n", "nu_1", "nu_2", "p", "q2_bits", "t_gsw", "t_conv", "t_exp_left", "t_exp_right", "instances",
+              "db_item_size", "version")
+
+    def __init__(self, device=0, expand_queries=True, **kw):
+        cp = CParams()
+        for k in self.FIELDS:
+            v = int(kw.get(k, 1 if k == "instances" else 0))
+            setattr(cp, k, v)
+            setattr(self, k, v)
+        cp.expand_queries = 1 if expand_queries else 0
+        self.expand_queries = bool(expand_queries)
+        h = C.c_void_p()
+        check(LIB.b200pir_ctx_create(C.byref(cp), int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+        self.poly_len = POLY_LEN
+        self.crt_count = CRT_COUNT
+        self.dim0 = 1 << self.nu_1
+        self.num_per = 1 << self.nu_2
+        self.slices = self.instances * self.n * self.n
+        sb, qb, rb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(LIB.b200pir_ctx_sizes(self._h, C.byref(sb), C.byref(qb), C.byref(rb)))
+        self.setup_bytes, self.query_bytes, self.response_bytes = sb.value, qb.value, rb.value
+
+    @classmethod
+    def from_json(cls, obj, device=0):
+        """params_from_json_obj (util.rs:224-263)."""
+        kw = dict(n=obj["n"], nu_1=obj["nu_1"], nu_2=obj["nu_2"], p=obj["p"], q2_bits=obj["q2_bits"],
+                  t_gsw=obj["t_gsw"], t_conv=obj["t_conv"], t_exp_left=obj["t_exp_left"],
+                  t_exp_right=obj["t_exp_right"], instances=obj.get("instances", 1),
+                  db_item_size=obj.get("db_item_size", 0), version=obj.get("version", 0))
+        return cls(device=device, expand_queries="direct_upload" not in obj, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            LIB.b200pir_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        check(LIB.b200pir_ctx_set_option(self._h, key.encode(), int(value)))
+
+    def set_stream(self, cuda_stream):
+        check(LIB.b200pir_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def synchronize(self):
+        check(LIB.b200pir_ctx_synchronize(self._h))
+
+    def last_stage_ms(self):
+        out = (C.c_double * 8)()
+        check(LIB.b200pir_last_stage_ms(self._h, out))
+        keys = ("expand", "multiply", "from_ntt", "fold", "pack", "encode", "total", "multiply_launches")
+        return dict(zip(keys, list(out)))
+
+
+class Database:
+    """The `db: &[u64]` argument of process_query, resident in HBM."""
+
+    def __init__(self, params, shard_index=0, shard_count=1):
+        self.params = params
+        h = C.c_void_p()
+        check(LIB.b200pir_db_create(params._h, shard_index, shard_count, C.byref(h)))
+        self._h = h
+        self.shard_index, self.shard_count = shard_index, shard_count
+
+    @classmethod
+    def from_words(cls, params, db):
+        """db: the reference's dense layout [instance][trial][z][ii][j] (server.rs:263-266)."""
+        self = cls(params)
+        check(LIB.b200pir_db_upload(params._h, self._h, _ptr(db), db.size))
+        return self
+
+    def upload_slice(self, slice_idx, words):
+        check(LIB.b200pir_db_upload_slice(self.params._h, self._h, slice_idx, _ptr(words), words.size))
+
+    def upsert_item(self, slice_idx, item_idx, poly):
+        if poly.size != POLY_LEN:
+            raise ValueError("item polynomial must have 2048 packed words")
+        check(LIB.b200pir_db_upsert_item(self.params._h, self._h, slice_idx, item_idx, _ptr(poly)))
+
+    def fill_synthetic(self, seed):
+        check(LIB.b200pir_db_fill_synthetic(self.params._h, self._h, seed))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            LIB.b200pir_db_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PublicParameters:
+    """spiral_rs::client::PublicParameters (client.rs:146-152), NTT form, resident in HBM."""
+
+    def __init__(self, params, v_packing, v_expansion_left=None, v_expansion_right=None, v_conversion=None):
+        self.params = params
+        h = C.c_void_p()
+        check(LIB.b200pir_pp_create(params._h, _ptr(v_packing), _ptr(v_expansion_left), _ptr(v_expansion_right),
+                                    _ptr(v_conversion), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            LIB.b200pir_pp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Query:
+    """spiral_rs::client::Query (client.rs:262-267) after deserialisation."""
+
+    def __init__(self, ct=None, v_buf=None, v_ct=None):
+        self.ct, self.v_buf, self.v_ct = ct, v_buf, v_ct
+
+
+# ---- lib/spiral-rs/src/ntt.rs
+def ntt_forward(params, operand_overall):
+    """ntt.rs:67-113.  In place over one or more [crt][2048] u64 polynomials."""
+    if operand_overall.size % (CRT_COUNT * POLY_LEN):
+        raise ValueError("operand must hold whole [2][2048] polynomials")
+    check(LIB.b200pir_ntt_forward(params._h, _ptr(operand_overall), operand_overall.size // (CRT_COUNT * POLY_LEN)))
+
+
+def ntt_inverse(params, operand_overall):
+    """ntt.rs:212-258."""
+    if operand_overall.size % (CRT_COUNT * POLY_LEN):
+        raise ValueError("operand must hold whole [2][2048] polynomials")
+    check(LIB.b200pir_ntt_inverse(params._h, _ptr(operand_overall), operand_overall.size // (CRT_COUNT * POLY_LEN)))
+
+
+# ---- lib/spiral-rs/src/poly.rs
+def to_ntt(params, raw):
+    """poly.rs:613-623 (PolyMatrixRaw -> PolyMatrixNTT, any shape flattened)."""
+    count = raw.size // POLY_LEN
+    out = np.zeros(count * CRT_COUNT * POLY_LEN, dtype=np.uint64)
+    check(LIB.b200pir_to_ntt(params._h, _ptr(out), _ptr(raw), count))
+    return out
+
+
+def from_ntt(params, ntt):
+    """poly.rs:646-663."""
+    count = ntt.size // (CRT_COUNT * POLY_LEN)
+    out = np.zeros(count * POLY_LEN, dtype=np.uint64)
+    check(LIB.b200pir_from_ntt(params._h, _ptr(out), _ptr(ntt), count))
+    return out
+
+
+# ---- lib/spiral-rs/src/server.rs
+def multiply_reg_by_database(params, db, slice_idx, v_firstdim):
+    """server.rs:155-221 on one (instance, trial) slice; returns num_per x PolyMatrixNTT(2,1)."""
+    if v_firstdim.size != params.dim0 * 2 * POLY_LEN:
+        raise ValueError("v_firstdim must hold dim0*2*poly_len words")
+    rows = params.num_per // db.shard_count
+    out = np.zeros(rows * 4 * POLY_LEN, dtype=np.uint64)
+    check(LIB.b200pir_multiply_reg_by_database(params._h, db._h, slice_idx, _ptr(v_firstdim), _ptr(out)))
+    return out
+
+
+def fold_ciphertexts(params, v_cts, v_folding, v_folding_neg):
+    """server.rs:388-427.  v_cts (num x 2 x 2048) is folded in place; result in v_cts[0]."""
+    num = v_cts.size // (2 * POLY_LEN)
+    check(LIB.b200pir_fold_ciphertexts(params._h, _ptr(v_cts), num, _ptr(v_folding), _ptr(v_folding_neg)))
+
+
+def get_v_folding_neg(params, v_folding):
+    """server.rs:505-523."""
+    out = np.zeros_like(v_folding)
+    check(LIB.b200pir_get_v_folding_neg(params._h, _ptr(out), _ptr(v_folding)))
+    return out
+
+
+def coefficient_expansion(params, public_params, v):
+    """server.rs:19-121, in place over v = 2^g x PolyMatrixNTT(2,1)."""
+    check(LIB.b200pir_coefficient_expansion(params._h, public_params._h, _ptr(v)))
+
+
+def expand_query(params, public_params, query):
+    """server.rs:525-591 -> (v_reg_reoriented, v_folding)."""
+    v_reg = np.zeros(params.dim0 * 2 * POLY_LEN, dtype=np.uint64)
+    v_fold = np.zeros(max(1, params.nu_2 * 2 * 2 * params.t_gsw * CRT_COUNT * POLY_LEN), dtype=np.uint64)
+    check(LIB.b200pir_expand_query(params._h, public_params._h, _ptr(query.ct), _ptr(v_reg), _ptr(v_fold)))
+    return v_reg, v_fold
+
+
+def pack(params, public_params, v_ct):
+    """server.rs:429-468 / lib/server/src/compute/pack.rs (by params.version)."""
+    out = np.zeros((params.n + 1) * params.n * CRT_COUNT * POLY_LEN, dtype=np.uint64)
+    check(LIB.b200pir_pack(params._h, public_params._h, _ptr(v_ct), _ptr(out)))
+    return out
+
+
+def encode(params, v_packed_ct):
+    """server.rs:470-503."""
+    out = np.zeros(params.response_bytes, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(LIB.b200pir_encode(params._h, _ptr(v_packed_ct), _ptr(out, np.uint8), C.byref(n)))
+    return out[: n.value]
+
+
+def process_query(params, public_params, query, db):
+    """spiral_rs::server::process_query (server.rs:650-741) -> response bytes."""
+    out = np.zeros(params.response_bytes, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(LIB.b200pir_process_query(params._h, db._h, public_params._h, _ptr(query.ct), _ptr(query.v_buf),
+                                    _ptr(query.v_ct), _ptr(out, np.uint8), C.byref(n)))
+    return out[: n.value]
+
+
+def process_query_batch(params, public_params, query_cts, db):
+    """`count` expanded-mode queries of one client; the database is streamed once per group."""
+    count = query_cts.size // (2 * POLY_LEN)
+    out = np.zeros(count * params.response_bytes, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(LIB.b200pir_process_query_batch(params._h, db._h, public_params._h, _ptr(query_cts), count,
+                                          _ptr(out, np.uint8), C.byref(n)))
+    return out.reshape(count, params.response_bytes)

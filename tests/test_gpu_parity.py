@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, stage by stage and end to end.
+Bit-exact: every comparison is array equality on integers/bytes."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+SEED_DB = 0xB1755
+Q0, Q1 = 268369921, 249561089
+
+
+def _gpu():
+    import sdk_b200.spiral as S
+    return S
+
+
+_cache = {}
+
+
+def setup_case(name, expand=True):
+    """oracle params + client + keys + DB, and the matching GPU context / handles (cached per module)."""
+    key = (name, expand)
+    if key in _cache:
+        return _cache[key]
+    S = _gpu()
+    P = O.Params.named(name, expand_queries=expand)
+    cl = O.Client(P, 1234)
+    pp = cl.generate_keys()
+    db = P.generate_db(SEED_DB)
+    G = S.Params(expand_queries=expand, **P.kw)
+    gdb = S.Database.from_words(G, db)
+    gpp = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
+    _cache[key] = (S, P, cl, pp, db, G, gdb, gpp)
+    return _cache[key]
+
+
+CASES = ["T", "T1", "T0"]
+
+
+# ------------------------------------------------------------------ primitives
+def test_sizes_match_reference_formulas():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    for name in ("E0", "E1", "S8", "T1", "T0"):
+        Po = O.Params.named(name)
+        Gp = S.Params(**Po.kw)
+        assert (Gp.setup_bytes, Gp.query_bytes, Gp.response_bytes) == (Po.setup_bytes, Po.query_bytes, Po.response_bytes())
+        Gp.close()
+
+
+def test_ntt_forward_inverse_match_oracle():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    rng = np.random.default_rng(1)
+    count = 37
+    v = np.empty((count, 2, 2048), dtype=np.uint64)
+    v[:, 0, :] = rng.integers(0, Q0, (count, 2048), dtype=np.uint64)
+    v[:, 1, :] = rng.integers(0, Q1, (count, 2048), dtype=np.uint64)
+    v[0] = 0
+    v[1, 0, :] = Q0 - 1
+    v[1, 1, :] = Q1 - 1
+    v[2] = 0
+    v[2, :, 0] = 100                       # ntt.rs:400-409 KAT input
+    v = v.reshape(-1)
+    ref = P.ntt_forward(v)
+    got = v.copy()
+    S.ntt_forward(G, got)
+    assert np.array_equal(got, ref)
+    assert np.all(got.reshape(count, 2, 2048)[2] == 100)
+    back = got.copy()
+    S.ntt_inverse(G, back)
+    assert np.array_equal(back, P.ntt_inverse(ref))
+    assert np.array_equal(back, v)
+
+
+def test_ntt_forward_lazy_inputs():
+    # to_ntt_no_reduce feeds un-reduced (< 4q) values (poly.rs:625-638)
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    rng = np.random.default_rng(2)
+    v = rng.integers(0, 4 * Q1, 5 * 2 * 2048, dtype=np.uint64)
+    got = v.copy()
+    S.ntt_forward(G, got)
+    assert np.array_equal(got, P.ntt_forward(v))
+
+
+def test_to_ntt_from_ntt_match_oracle():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, P.modulus, 9 * 2048, dtype=np.uint64)
+    raw[:2048] = 0
+    raw[2048:4096] = P.modulus            # the non-canonical value q
+    raw[4096:6144] = P.modulus - 1
+    ntt = S.to_ntt(G, raw)
+    assert np.array_equal(ntt, P.to_ntt(raw))
+    assert np.array_equal(S.from_ntt(G, ntt), P.from_ntt(ntt))
+    ntt_r = np.concatenate([rng.integers(0, Q0, 2048, dtype=np.uint64), rng.integers(0, Q1, 2048, dtype=np.uint64)])
+    assert np.array_equal(S.from_ntt(G, ntt_r), P.from_ntt(ntt_r))
+
+
+# ------------------------------------------------------------------ first dimension
+@pytest.mark.parametrize("name", CASES)
+def test_multiply_reg_by_database_matches_oracle(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    rng = np.random.default_rng(4)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    slice_words = P.dim0 * P.num_per * P.N
+    for s in sorted({0, P.slices - 1}):
+        ref = P.multiply_reg_by_database(db[s * slice_words:(s + 1) * slice_words], v)
+        for variant in (0, 1, 2, 3):
+            G.set_option("mul_variant", variant)
+            got = S.multiply_reg_by_database(G, gdb, s, v)
+            assert np.array_equal(got, ref), (name, s, variant)
+    G.set_option("mul_variant", 0)
+
+
+def test_multiply_worst_case_operands_do_not_overflow():
+    # all residues q-1, dim0 = 64: checks the 64-bit accumulation / periodic reduction path
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
+    dbw = np.full(P.dim0 * P.num_per * P.N, w, dtype=np.uint64)
+    v = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
+    d2 = S.Database(G)
+    for s in range(P.slices):
+        d2.upload_slice(s, dbw)
+    got = S.multiply_reg_by_database(G, d2, 1, v)
+    assert np.array_equal(got, P.multiply_reg_by_database(dbw, v))
+    d2.close()
+
+
+def test_multiply_long_first_dimension_reduction():
+    # dim0 = 1024 (nu_1 = 10) with maximal operands exercises the mid-loop reduction (>256 products)
+    S = _gpu()
+    kw = dict(O.PARAM_SETS["T"])
+    kw.update(nu_1=10, nu_2=1, n=1, db_item_size=2048)
+    P = O.Params(**kw)
+    G = S.Params(**kw)
+    w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
+    rng = np.random.default_rng(5)
+    dbw = np.full(P.dim0 * P.num_per * P.N, w, dtype=np.uint64)
+    dbw[::7] = rng.integers(0, Q0, dbw[::7].size, dtype=np.uint64) | (rng.integers(0, Q1, dbw[::7].size, dtype=np.uint64) << np.uint64(32))
+    v = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
+    gdb = S.Database.from_words(G, dbw)
+    assert np.array_equal(S.multiply_reg_by_database(G, gdb, 0, v), P.multiply_reg_by_database(dbw, v))
+    gdb.close()
+    G.close()
+
+
+def test_synthetic_db_matches_oracle_generator():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    d2 = S.Database(G)
+    d2.fill_synthetic(SEED_DB)
+    rng = np.random.default_rng(6)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    for s in range(P.slices):
+        assert np.array_equal(S.multiply_reg_by_database(G, d2, s, v), S.multiply_reg_by_database(G, gdb, s, v))
+    d2.close()
+
+
+def test_upsert_item_equals_bulk_upload():
+    # lib/server db/loading.rs:317-359: one preprocessed item poly replaces db[idx]
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    d2 = S.Database(G)       # all-zero database
+    slice_words = P.dim0 * P.num_per * P.N
+    sl = db[:slice_words].reshape(P.N, P.num_per, P.dim0)
+    rng = np.random.default_rng(7)
+    items = [0, 5, P.dim0 * P.num_per - 1, 77]
+    for it in items:
+        ii, j = it % P.num_per, it // P.num_per
+        d2.upsert_item(0, it, np.ascontiguousarray(sl[:, ii, j]))
+    sparse = np.zeros_like(sl)
+    for it in items:
+        ii, j = it % P.num_per, it // P.num_per
+        sparse[:, ii, j] = sl[:, ii, j]
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    assert np.array_equal(S.multiply_reg_by_database(G, d2, 0, v), P.multiply_reg_by_database(sparse.reshape(-1), v))
+    d2.close()
+
+
+# ------------------------------------------------------------------ second dimension
+@pytest.mark.parametrize("name", CASES)
+def test_fold_and_folding_neg_match_oracle(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    q = cl.generate_query(3)
+    resp, d = P.process_query(pp, q, db, dump=True)
+    assert np.array_equal(S.get_v_folding_neg(G, d["v_folding"]), d["v_folding_neg"])
+    inter = P.from_ntt(d["first_mult"])
+    ref = P.fold_ciphertexts(inter, d["v_folding"], d["v_folding_neg"])
+    got = inter.copy()
+    S.fold_ciphertexts(G, got, d["v_folding"], d["v_folding_neg"])
+    # the reference leaves partially folded values in slots >= 1; every slot must agree
+    assert np.array_equal(got, ref)
+    # a sub-fold (len 2) uses only v_folding[0]  (server.rs:398-420)
+    two = inter[: 2 * 2 * P.N].copy()
+    ref2 = P.fold_ciphertexts(two, d["v_folding"], d["v_folding_neg"])
+    S.fold_ciphertexts(G, two, d["v_folding"], d["v_folding_neg"])
+    assert np.array_equal(two, ref2)
+    one = inter[: 2 * P.N].copy()
+    S.fold_ciphertexts(G, one, d["v_folding"], d["v_folding_neg"])      # len 1: no-op (server.rs:394-396)
+    assert np.array_equal(one, inter[: 2 * P.N])
+
+
+# ------------------------------------------------------------------ expansion
+@pytest.mark.parametrize("name", CASES)
+def test_expand_query_matches_oracle(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    q = cl.generate_query(P.dim0 * P.num_per - 2)
+    vreg_ref, vf_ref = P.expand_query(pp, q["ct"])
+    vreg, vf = S.expand_query(G, gpp, S.Query(ct=q["ct"]))
+    assert np.array_equal(vreg, vreg_ref)
+    assert np.array_equal(vf, vf_ref)
+
+
+def test_coefficient_expansion_matches_oracle_all_slots():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T0")
+    q = cl.generate_query(9)
+    v = np.zeros((1 << P.g) * 2 * P.W, dtype=np.uint64)
+    v[: 2 * P.W] = P.to_ntt(q["ct"])
+    ref = P.coefficient_expansion(v, pp)
+    got = v.copy()
+    S.coefficient_expansion(G, gpp, got)
+    assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ pack / encode
+@pytest.mark.parametrize("name", CASES)
+def test_pack_and_encode_match_oracle(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    q = cl.generate_query(11)
+    resp, d = P.process_query(pp, q, db, dump=True)
+    nn = P.n * P.n
+    for inst in range(P.instances):
+        cts = d["folded"][inst * nn * 2 * P.N:(inst + 1) * nn * 2 * P.N]
+        assert np.array_equal(S.pack(G, gpp, cts), P.pack(cts, pp["pack"]))
+    assert np.array_equal(S.encode(G, d["packed"]), P.encode(d["packed"]))
+    assert np.array_equal(S.encode(G, d["packed"]), resp)
+    # extreme inputs to rescale (arith.rs:429-444): 0, q/2 boundaries, q-1
+    ext = d["packed"].copy()
+    ext[:6] = [0, 1, P.modulus // 2 - 1, P.modulus // 2, P.modulus // 2 + 1, P.modulus - 1]
+    assert np.array_equal(S.encode(G, ext), P.encode(ext))
+
+
+# ------------------------------------------------------------------ end to end
+@pytest.mark.parametrize("name", CASES)
+def test_process_query_bytes_and_decode(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    for idx in (0, 77 % (P.dim0 * P.num_per), P.dim0 * P.num_per - 1):
+        q = cl.generate_query(idx)
+        ref = P.process_query(pp, q, db)
+        got = S.process_query(G, gpp, S.Query(ct=q["ct"]), gdb)
+        assert np.array_equal(got, ref), (name, idx)
+        assert np.array_equal(cl.decode_response(got), P.db_plain_item(SEED_DB, idx))
+
+
+def test_process_query_direct_upload():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T", expand=False)
+    q = cl.generate_query(42)
+    ref = P.process_query(pp, q, db)
+    got = S.process_query(G, gpp, S.Query(v_buf=q["v_buf"], v_ct=q["v_ct"]), gdb)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(cl.decode_response(got), P.db_plain_item(SEED_DB, 42))
+
+
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_process_query_batch_equals_single(group):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    idxs = [1, 200, 33, 255, 128, 7, 64]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    G.set_option("batch", group)
+    out = S.process_query_batch(G, gpp, qs, gdb)
+    G.set_option("batch", 4)
+    for k, i in enumerate(idxs):
+        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
+        assert np.array_equal(out[k], ref), (group, k)
+        assert np.array_equal(cl.decode_response(out[k]), P.db_plain_item(SEED_DB, i))
+
+
+def test_error_behaviour():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    with pytest.raises(S.B200PirError):
+        S.multiply_reg_by_database(G, gdb, 99, np.zeros(P.dim0 * 2 * P.N, dtype=np.uint64))      # slice out of range
+    with pytest.raises(S.B200PirError):
+        S.fold_ciphertexts(G, np.zeros(3 * 2 * P.N, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64))
+    with pytest.raises(S.B200PirError):
+        S.Params(device=99, **P.kw)
+    with pytest.raises(S.B200PirError):
+        S.Database.from_words(G, np.zeros(17, dtype=np.uint64))
+
+
+# ------------------------------------------------------------------ DoublePIR
+@pytest.mark.parametrize("rows,cols", [(43, 37), (64, 1366), (29, 256), (1000, 5)])
+def test_dpir_matvec_matches_oracle(rows, cols):
+    import sdk_b200.doublepir as D
+    rng = np.random.default_rng(rows * 131 + cols)
+    a = rng.integers(0, 2**30, rows * cols, dtype=np.uint32)
+    b = rng.integers(0, 2**32, 3 * cols, dtype=np.uint32)
+    m = D.PackedMatrix(a, rows, cols)
+    assert np.array_equal(D.matrix_mul_vec_packed(m, b), O.dpir_matvec_packed(a, b, rows, cols))
+    m.close()
