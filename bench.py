@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — PIR server queries/sec on the "1 GiB DB" Spiral workload (BASELINE.json configs[1]).
+
+A step = one pass of the hot path (spiral_rs::server::process_query, lib/spiral-rs/src/server.rs:650-741)
+over one batch of `--batch` synthetic queries against the HBM-resident database.
+
+  * `value`     : queries/s with the queries already resident in HBM (device-timed, CUDA events,
+                  barrier + synchronize on both sides, max over ranks)
+  * `e2e`       : the same metric through the C-ABI call with HOST buffers (pinned): the H2D copy of
+                  the query ciphertexts and the D2H read of the response bytes are inside the timed region
+  * `roofline`  : the dominant kernel (multiply_reg_by_database, server.rs:155-221), algorithmic bytes
+                  per launch / its CUDA-event duration measured live in the timed region, against the
+                  measured HBM peak of MEASURED_PEAKS.json
+  * `cpu_baseline` / `--impl reference` : the CPU restatement of the reference (oracle/, "port": no Rust
+                  toolchain exists in the image) on the host cores, on a bounded sample
+
+Workloads: N=1 -> S8 = 2^17 Spiral items x 8 KiB = 2^20 x 1 KiB records, 1 GiB of
+plaintext = 8 GiB HBM-resident.  N>1 (weak scaling) -> the same per-GPU shard, database N times larger
+(nu_2 = 8 + log2 N), second-dimension rows sharded ii mod N, one NCCL all-gather of the surviving
+ciphertexts per batch (DESIGN.md "multi-GPU").
+
+Synthetic data: the server computation is data-oblivious, so public parameters and query ciphertexts
+are uniformly random residues of the right shape; the database is generated on the GPU from a
+counter PRNG (plaintext -> NTT -> packed words).  Correctness is covered by tests/, not here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q0, Q1 = 268369921, 249561089
+POLY = 2048
+
+S8 = dict(n=2, nu_1=9, nu_2=8, p=256, q2_bits=22, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1,
+          db_item_size=8192, version=0)
+WORKLOADS = {
+    "S8": S8,                                     # 8 GiB HBM-resident = 1 GiB plaintext (configs[1])
+    "S1": dict(n=2, nu_1=9, nu_2=5, p=256, q2_bits=22, t_gsw=7, t_conv=3, t_exp_left=5, t_exp_right=5, instances=1,
+               db_item_size=8192, version=1),     # 1 GiB HBM-resident
+    "T": dict(n=2, nu_1=6, nu_2=2, p=256, q2_bits=20, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1,
+              db_item_size=8192, version=0),      # unit-test size (CI smoke of this script)
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def derived(kw):
+    import math
+    dim0, num_per = 1 << kw["nu_1"], 1 << kw["nu_2"]
+    slices = kw["instances"] * kw["n"] ** 2
+    g = math.ceil(math.log2(kw["t_gsw"] * kw["nu_2"] + dim0))
+    stop_round = math.ceil(math.log2(kw["t_gsw"] * kw["nu_2"])) if kw["nu_2"] else 0
+    num_packing = kw["n"] if kw["version"] == 0 else 2
+    has_right = kw["version"] == 0 or kw["t_exp_right"] != kw["t_exp_left"]
+    return dict(dim0=dim0, num_per=num_per, slices=slices, g=g, stop_round=stop_round, num_packing=num_packing,
+                has_right=has_right)
+
+
+def random_ntt(rng, npolys):
+    import numpy as np
+    a = np.empty((npolys, 2, POLY), dtype=np.uint64)
+    a[:, 0, :] = rng.integers(0, Q0, (npolys, POLY), dtype=np.uint64)
+    a[:, 1, :] = rng.integers(0, Q1, (npolys, POLY), dtype=np.uint64)
+    return a.reshape(-1)
+
+
+def synthetic_pp(kw, rng):
+    d = derived(kw)
+    pp = dict(pack=random_ntt(rng, d["num_packing"] * (kw["n"] + 1) * kw["t_conv"]),
+              left=random_ntt(rng, d["g"] * 2 * kw["t_exp_left"]),
+              right=random_ntt(rng, (d["stop_round"] + 1) * 2 * kw["t_exp_right"]) if d["has_right"] else None,
+              conv=random_ntt(rng, 2 * 2 * kw["t_conv"]))
+    return pp
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks line')."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, batch):
+    """dram bytes per launch of the multiply kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            d = json.load(f)
+        return d.get("%s_batch%d" % (workload, batch))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------- CPU legs
+def cpu_process_query_sample(kw, threads=None, sample_rows=64):
+    """Time the oracle's process_query (CPU restatement of the reference) on a bounded sample:
+    the full query expansion plus a `sample_rows`-row slab of every slice (multiply + fold + pack),
+    scaling the row-proportional part to the full num_per.  Returns seconds per query (estimate)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as O
+    if threads:
+        O.LIB.orc_set_num_threads(int(threads))
+    cores = int(O.LIB.orc_num_threads())
+    full_rows = 1 << kw["nu_2"]
+    rows = min(sample_rows, full_rows)
+    skw = dict(kw)
+    skw["nu_2"] = rows.bit_length() - 1
+    P = O.Params(**skw)
+    Pfull = O.Params(**kw)
+    rng = np.random.default_rng(7)
+    pp = synthetic_pp(skw, rng)
+    pp_full = synthetic_pp(kw, rng)
+    q = dict(ct=rng.integers(0, P.modulus, 2 * POLY, dtype=np.uint64))
+    db = (rng.integers(0, Q0, P.slices * P.dim0 * P.num_per * POLY, dtype=np.uint64)
+          | (rng.integers(0, Q1, P.slices * P.dim0 * P.num_per * POLY, dtype=np.uint64) << np.uint64(32)))
+    t0 = time.perf_counter()
+    Pfull.expand_query(pp_full, q["ct"])                       # full-size expansion (g rounds of the real config)
+    t_expand_full = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    P.expand_query(pp, q["ct"])
+    t_expand_small = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    P.process_query(pp, q, db)
+    t_small = time.perf_counter() - t0
+    row_part = max(t_small - t_expand_small, 0.0)
+    est = t_expand_full + row_part * (full_rows / rows)
+    sample = ("oracle process_query: full query expansion (%.2fs) + %d of %d second-dimension rows of every slice "
+              "(multiply+fold+pack %.2fs, scaled x%d)" % (t_expand_full, rows, full_rows, row_part, full_rows // rows))
+    return est, cores, sample
+
+
+def run_reference_arm(args, kw, workload_name, rank, world):
+    if rank != 0:
+        return
+    per_step = []
+    est = cores = sample = None
+    for i in range(args.warmup + args.steps):
+        est, cores, sample = cpu_process_query_sample(kw, sample_rows=32)
+        if i >= args.warmup:
+            per_step.append(est)
+    sec = sum(per_step) / len(per_step)
+    qps = 1.0 / sec
+    out = {
+        "impl": "reference", "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name, "params": kw, "batch": 1},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "1")))
+    ap.add_argument("--mul-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    N = max(world, 1)
+
+    name = args.workload or "S8"
+    kw = dict(WORKLOADS[name])
+    import math
+    if N > 1:
+        if N & (N - 1):
+            raise SystemExit("--gpus must be a power of two")
+        kw["nu_2"] += int(math.log2(N))                 # weak scaling: same per-GPU shard, N x larger database
+        workload_name = "%s x%d (nu_2=%d), rows sharded ii mod %d" % (name, N, kw["nu_2"], N)
+    else:
+        workload_name = {"S8": "S8: Spiral 2^20 x 1 KiB records (2^17 items x 8 KiB), 1 GiB plaintext = 8 GiB HBM-resident",
+                         "S1": "S1: 1 GiB HBM-resident (2^14 items x 8 KiB)", "T": "T: unit-test size"}[name]
+
+    if args.impl == "reference":
+        run_reference_arm(args, kw, workload_name, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import sdk_b200.spiral as S
+    from sdk_b200._lib import LIB, check
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if N > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    d = derived(kw)
+    B = args.batch
+    G = S.Params(device=local_rank, **kw)
+    stream = torch.cuda.current_stream()
+    G.set_stream(stream.cuda_stream)
+    G.set_option("mul_variant", args.mul_variant)
+    G.set_option("batch", 4 if B >= 4 else (2 if B >= 2 else 1))
+    gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N)
+    gdb.fill_synthetic(0xB1755)
+    rng = np.random.default_rng(20260923)
+    pp = synthetic_pp(kw, rng)
+    gpp = S.PublicParameters(G, pp["pack"], pp["left"], pp["right"], pp["conv"])
+    modulus = Q0 * Q1
+    rb = G.response_bytes
+    q_words = B * 2 * POLY
+    # pinned host buffers for the e2e leg
+    h_q = torch.empty(q_words, dtype=torch.int64).pin_memory()
+    h_q.numpy().view(np.uint64)[:] = rng.integers(0, modulus, q_words, dtype=np.uint64)
+    h_out = torch.empty(B * rb, dtype=torch.uint8).pin_memory()
+    d_q = h_q.cuda(non_blocking=False)
+    d_out = torch.zeros(B * rb, dtype=torch.uint8, device="cuda")
+    rows_local = d["num_per"] // N
+    if N > 1:
+        d_partial = torch.zeros(B * d["slices"] * 2 * POLY, dtype=torch.int64, device="cuda")
+        d_gather = torch.zeros(N * B * d["slices"] * 2 * POLY, dtype=torch.int64, device="cuda")
+
+    def step_dev():
+        if N == 1:
+            check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), B, d_out.data_ptr()))
+        else:
+            check(LIB.b200pir_query_stage_a_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), B, d_partial.data_ptr()))
+            dist.all_gather_into_tensor(d_gather, d_partial)
+            check(LIB.b200pir_query_stage_b_dev(G._h, gpp._h, d_gather.data_ptr(), N, B, d_out.data_ptr()))
+
+    def step_e2e():
+        if N == 1:
+            n = C.c_size_t(0)
+            check(LIB.b200pir_process_query_batch(G._h, gdb._h, gpp._h, h_q.data_ptr(), B, h_out.data_ptr(), C.byref(n)))
+        else:
+            d_q.copy_(h_q, non_blocking=True)
+            step_dev()
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    G.set_option("profile", 2)
+    launches0 = LIB.b200pir_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = LIB.b200pir_kernel_launches() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    stage = G.last_stage_ms()
+    G.set_option("profile", 0)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    qps = B * 1e3 / ms_per_step
+
+    # ---- end to end (host buffers, copies inside the timed region)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_qps = B * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (multiply_reg_by_database)
+    mul_launches = max(int(stage["multiply_launches"]), 1)
+    mul_ms = stage["multiply"] / mul_launches
+    nq_per_launch = B * args.steps / mul_launches
+    db_bytes = d["slices"] * d["dim0"] * rows_local * POLY * 8
+    alg_bytes = db_bytes + nq_per_launch * (d["dim0"] * POLY * 16 + d["slices"] * rows_local * 4 * POLY * 4)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (mul_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_multiply (multiply_reg_by_database, server.rs:155-221)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(name, B), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mul_ms,
+                "kernel_share_of_step": stage["multiply"] / max(stage["total"], 1e-9)}
+
+    if rank == 0:
+        cpu = None
+        if N == 1 and not args.no_cpu_baseline:
+            try:
+                est, cores, sample = cpu_process_query_sample(kw)
+                cpu = {"value": 1.0 / est, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as e:      # the oracle is only a reported baseline; never fail the bench on it
+                cpu = {"value": None, "unit": "queries/s", "cores": None, "kind": "port", "sample": "failed: %r" % (e,)}
+        out = {
+            "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
+            "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name, "params": kw, "batch": B, "db_bytes_per_gpu": db_bytes,
+                       "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
+                       "parallelism": "rows ii mod %d + 1 NCCL all-gather" % N if N > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (database %.1f GiB per GPU streamed every step)" % (db_bytes / 2**30)},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 2 * POLY * 8,
+                    "d2h_bytes_per_step": B * rb if N == 1 else B * rb},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
+            "single_query_latency_ms": ms_per_step if B == 1 else None,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

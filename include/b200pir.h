@@ -51,7 +51,8 @@ void b200pir_ctx_destroy(b200pir_ctx* ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this context. */
 int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
-/* knobs: "mul_variant" (kernel tiling), "batch" (queries per database pass: 1, 2 or 4), "profile" (0/1);
+/* knobs: "mul_variant" (kernel tiling), "batch" (queries per database pass: 1, 2 or 4), "profile" (0 off, 1 per call,
+ * 2 accumulate over calls until set again);
  * unknown keys -> B200PIR_E_BADARG */
 int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);
 /* params.setup_bytes / query_bytes / response length (params.rs:146-182, server.rs:476-481) */
@@ -137,6 +138,8 @@ int b200pir_query_stage_b_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* 
  * context's stream.  Enable with b200pir_ctx_set_option(ctx, "profile", 1).
  * out[0..7] = expand, first-dim multiply, from_ntt, fold, pack, encode, total, multiply launches */
 int b200pir_last_stage_ms(b200pir_ctx* ctx, double* out8);
+/* Number of CUDA kernels this library has launched from the calling host thread since load. */
+unsigned long long b200pir_kernel_launches(void);
 
 /* ---- DoublePIR: matrix_mul_vec_packed(a, b, basis=10, compression=3) (lib/doublepir/src/matrix/kernels.rs:118-178) */
 int b200pir_dpir_create(int device, const uint32_t* a, uint64_t rows, uint64_t cols, b200pir_dpir** out);

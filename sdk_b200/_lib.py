@@ -59,6 +59,7 @@ def _load():
         "b200pir_query_stage_a_dev": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, u64p]),
         "b200pir_query_stage_b_dev": (C.c_int, [vp, vp, u64p, C.c_size_t, C.c_size_t, u8p]),
         "b200pir_last_stage_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
+        "b200pir_kernel_launches": (C.c_ulonglong, []),
         "b200pir_dpir_create": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_create_synthetic": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_destroy": (None, [vp]),

@@ -14,6 +14,8 @@
 
 using namespace b200pir;
 
+namespace b200pir { thread_local unsigned long long g_kernel_launches = 0; }
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -164,7 +166,8 @@ struct b200pir_ctx {
       if (c->profile) { cudaEvent_t b = c->get_event(); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); }
     }
   };
-  void prof_reset() { spans.clear(); event_next = 0; mul_launches = 0; }
+  // profile == 1: per call; profile == 2: accumulate over calls until the option is set again
+  void prof_reset() { if (profile == 2) return; spans.clear(); event_next = 0; mul_launches = 0; }
   void prof_collect() {
     if (!profile) return;
     B200_CUDA(cudaStreamSynchronize(stream));
@@ -492,7 +495,11 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   std::string k(key);
   if (k == "mul_variant") c->mul_variant = (int)value;
   else if (k == "batch") { if (value != 1 && value != 2 && value != 4) throw Error(B200PIR_E_BADARG, "batch must be 1, 2 or 4"); c->max_group = (int)value; }
-  else if (k == "profile") c->profile = value ? 1 : 0;
+  else if (k == "profile") {
+    if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
+    c->profile = (int)value;
+    c->spans.clear(); c->event_next = 0; c->mul_launches = 0;
+  }
   else throw Error(B200PIR_E_BADARG, "unknown option " + k);
   API_END
 }
@@ -842,6 +849,13 @@ int b200pir_encode(b200pir_ctx* c, const uint64_t* v_packed_raw, uint8_t* out, s
 }
 
 // ---------------------------------------------------------------- process_query
+static void run_query_batch_resident(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, size_t count, uint8_t* out_dev) {
+  // queries are already in c->w_query
+  run_prepare(c, pp, count);
+  run_first_dim_and_fold(c, db, count);
+  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, count, out_dev);
+}
+
 int b200pir_process_query_batch_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
                                     size_t count, uint8_t* out_dev) {
   API_BEGIN
@@ -855,9 +869,7 @@ int b200pir_process_query_batch_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* 
   c->ensure_workspace(count, db->rows);
   c->prof_reset();
   B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts_dev, count * 2 * POLY * 8, cudaMemcpyDeviceToDevice, c->stream));
-  run_prepare(c, pp, count);
-  run_first_dim_and_fold(c, db, count);
-  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, count, out_dev);
+  run_query_batch_resident(c, db, pp, count, out_dev);
   B200_CUDA(cudaGetLastError());
   API_END
 }
@@ -869,14 +881,16 @@ int b200pir_process_query_batch(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, 
   Guard gd(c);
   check_db(c, db);
   check_pp(c, pp);
+  if (db->shard.count != 1) throw Error(B200PIR_E_BADARG, "sharded database: use the stage_a / stage_b entry points");
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "batch entry point needs expand_queries");
+  if (count == 0) return 0;
   c->ensure_workspace(count, db->rows);
-  DevBuf<uint64_t> q(count * 2 * POLY);
-  B200_CUDA(cudaMemcpyAsync(q.p, query_cts, q.n * 8, cudaMemcpyHostToDevice, c->stream));
-  int rc = b200pir_process_query_batch_dev(c, db, pp, q.p, count, c->w_resp.p);
-  if (rc) return rc;
+  c->prof_reset();
+  B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts, count * 2 * POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  run_query_batch_resident(c, db, pp, count, c->w_resp.p);
   B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, count * c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
-  c->prof_collect();
+  if (c->profile == 1) c->prof_collect();
   if (out_len_each) *out_len_each = c->response_bytes;
   B200_CUDA(cudaGetLastError());
   API_END
@@ -912,7 +926,7 @@ int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const 
   run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, 1, c->w_resp.p);
   B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
-  c->prof_collect();
+  if (c->profile == 1) c->prof_collect();
   if (out_len) *out_len = c->response_bytes;
   B200_CUDA(cudaGetLastError());
   API_END
@@ -962,6 +976,8 @@ int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* ga
   B200_CUDA(cudaGetLastError());
   API_END
 }
+
+unsigned long long b200pir_kernel_launches(void) { return g_kernel_launches; }
 
 int b200pir_last_stage_ms(b200pir_ctx* c, double* out8) {
   API_BEGIN

@@ -13,6 +13,9 @@ namespace b200pir {
 
 static const int POLY = 2048;
 
+// number of kernels this library has launched from the calling thread (bench.py reports it)
+extern thread_local unsigned long long g_kernel_launches;
+
 // ---- generic transforms (K3/K4 of SURVEY §2.3)
 // u64 ABI format [poly][n][z]  <->  in place forward / inverse NTT (ntt.rs:67-113 / :212-258)
 void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s);

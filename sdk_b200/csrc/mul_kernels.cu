@@ -20,7 +20,7 @@ namespace b200pir {
 namespace {
 
 template <int R, int NQ, int UNROLL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_multiply(DevParams P, MulGeom G, const uint4* __restrict__ db, const uint4* __restrict__ qv, uint32_t* __restrict__ out,
            int slice_begin, size_t q_stride, size_t out_stride) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +99,7 @@ void launch_mul_t(const DevParams& P, const MulGeom& G, const uint4* db, const u
   while (rowgroups % groups) groups--;
   dim3 block(128, groups);
   dim3 grid(POLY / 128, rowgroups / groups, slice_count);
+  ++g_kernel_launches;
   k_multiply<R, NQ, UNROLL><<<grid, block, 0, s>>>(P, G, db, q, out, slice_begin, q_stride, out_stride);
 }
 
@@ -271,14 +272,17 @@ void launch_multiply(const DevParams& P, const MulGeom& G, const uint4* db_dev, 
 }
 void launch_query_to_dev(const MulGeom& G, uint4* q_dev, const uint64_t* v_firstdim, cudaStream_t s) {
   size_t total = (size_t)G.dim0 * POLY;
+  ++g_kernel_launches;
   k_query_to_dev<<<grid1d(total, 256), 256, 0, s>>>(G, q_dev, v_firstdim);
 }
 void launch_db_retile_chunk(const MulGeom& G, Shard sh, uint4* db_dev_slice, const uint64_t* ref_chunk, int z0, int zc,
                             cudaStream_t s) {
   size_t total = (size_t)G.num_per * (G.dim0 >> 1) * zc;
+  ++g_kernel_launches;
   k_db_retile<<<grid1d(total, 256), 256, 0, s>>>(G, sh, db_dev_slice, ref_chunk, z0, zc);
 }
 void launch_db_upsert(const MulGeom& G, uint4* db_dev, int slice, int il, int j, const uint64_t* poly, cudaStream_t s) {
+  ++g_kernel_launches;
   k_db_upsert<<<POLY / 256, 256, 0, s>>>(G, db_dev, slice, il, j, poly);
 }
 void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_dev, uint64_t seed, uint64_t pt_modulus,
@@ -292,6 +296,7 @@ void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_d
     cudaFuncSetAttribute(k_db_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
+  ++g_kernel_launches;
   k_db_synth<<<(unsigned)ctas, 512, smem, s>>>(P, G, sh, db_dev, seed, pt_modulus, slice_begin);
 }
 void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols, int variant,
@@ -305,9 +310,11 @@ void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, siz
   if (grid == 0) return;
   if (rows_per_warp == 2) {
     cudaFuncSetAttribute(k_dpir_matvec<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_kernel_launches;
     k_dpir_matvec<2><<<grid, 256, smem, s>>>(out, a, b, rows, cols, cols_pad);
   } else {
     cudaFuncSetAttribute(k_dpir_matvec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_kernel_launches;
     k_dpir_matvec<4><<<grid, 256, smem, s>>>(out, a, b, rows, cols, cols_pad);
   }
 }

@@ -546,37 +546,39 @@ const size_t kDynSmemBig = (size_t)(2 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t
 }  // namespace
 
 void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s) {
-  if (count) k_ntt_u64<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+  if (count) ++g_kernel_launches, k_ntt_u64<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
 }
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s) {
-  if (count) k_ntt32<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+  if (count) ++g_kernel_launches, k_ntt32<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
 }
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s) {
-  if (count) k_to_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out, raw);
+  if (count) ++g_kernel_launches, k_to_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out, raw);
 }
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
-  if (count) k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);
+  if (count) ++g_kernel_launches, k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);
 }
 void launch_widen(uint64_t* out, const uint32_t* in, size_t words, cudaStream_t s) {
-  if (words) k_widen<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
+  if (words) ++g_kernel_launches, k_widen<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
 }
 void launch_narrow(uint32_t* out, const uint64_t* in, size_t words, cudaStream_t s) {
-  if (words) k_narrow<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
+  if (words) ++g_kernel_launches, k_narrow<<<grid1d(words, 256), 256, 0, s>>>(out, in, words);
 }
 void launch_fold_round(const DevParams& P, uint64_t* cts, size_t batch, size_t batch_stride, int half,
                        const uint32_t* c_pos, const uint32_t* c_neg, size_t c_batch_stride, int slices_per_query,
                        int t_gsw, int bits, cudaStream_t s) {
   if (batch == 0 || half == 0) return;
+  ++g_kernel_launches;
   k_fold_round<<<(unsigned)(batch * half), CTA, 0, s>>>(P, cts, batch_stride, half, c_pos, c_neg, c_batch_stride,
                                                         slices_per_query, t_gsw, bits);
 }
 void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_folding, int count, int t_gsw, int bits,
                         cudaStream_t s) {
   size_t total = (size_t)count * 2 * 2 * t_gsw * 2 * POLY;
-  if (total) k_folding_neg<<<grid1d(total, 256), 256, 0, s>>>(P, out, v_folding, total, t_gsw, bits);
+  if (total) ++g_kernel_launches, k_folding_neg<<<grid1d(total, 256), 256, 0, s>>>(P, out, v_folding, total, t_gsw, bits);
 }
 void launch_expand_scalar(const DevParams& P, uint32_t* v, int num_in, const uint32_t* neg1_r, cudaStream_t s) {
   size_t total = (size_t)num_in * 4 * POLY;
+  ++g_kernel_launches;
   k_expand_scalar<<<grid1d(total, 256), 256, 0, s>>>(P, v, num_in, neg1_r);
 }
 void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, cudaStream_t s) {
@@ -585,10 +587,12 @@ void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, 
     cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
     attr_set = true;
   }
+  ++g_kernel_launches;
   k_expand_round<<<(unsigned)(2 * R.num_in), CTA, kDynSmemBig, s>>>(P, v, R);
 }
 void launch_reorient(const MulGeom& G, uint4* q_dev, const uint32_t* v, int idx_factor, cudaStream_t s) {
   size_t total = (size_t)G.dim0 * POLY;
+  ++g_kernel_launches;
   k_reorient<<<grid1d(total, 256), 256, 0, s>>>(G, q_dev, v, idx_factor);
 }
 void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v, int count, int idx_factor,
@@ -599,6 +603,7 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v,
     cudaFuncSetAttribute(k_regev_to_gsw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
     attr_set = true;
   }
+  ++g_kernel_launches;
   k_regev_to_gsw<<<(unsigned)(count * t_gsw), CTA, kDynSmemBig, s>>>(P, v_gsw, v, idx_factor, idx_offset, v_conv, t_gsw,
                                                                      t_conv, bits_conv);
 }
@@ -611,6 +616,7 @@ static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint64_t*
     cudaFuncSetAttribute(k_pack<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
     attr_set = true;
   }
+  ++g_kernel_launches;
   k_pack<ROWS><<<(unsigned)(instances * (ROWS - 1)), CTA, kDynSmemBig, s>>>(P, out_raw, folded, ct_stride, v_packing,
                                                                            t_conv, bits_conv, version);
 }
@@ -628,6 +634,7 @@ void launch_pack(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, 
 void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,
                    uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s) {
   size_t words = out_bytes / 8;
+  ++g_kernel_launches;
   k_encode<<<grid1d(words, 128), 128, 0, s>>>(P, reinterpret_cast<uint64_t*>(out), words, packed_raw, n, instances, q2,
                                               q2_bits, q1, q1_bits);
 }
