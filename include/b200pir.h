@@ -94,7 +94,9 @@ int b200pir_from_ntt(b200pir_ctx* ctx, uint64_t* out_raw, const uint64_t* ntt, s
 int b200pir_multiply_reg_by_database(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, const uint64_t* v_firstdim,
                                      uint64_t* out);
 /* server.rs:388-427 fold_ciphertexts: v_cts = num x PolyMatrixRaw(2,1) in place (result in v_cts[0]);
- * v_folding / v_folding_neg = log2(num) x PolyMatrixNTT(2, 2 t_gsw). */
+ * v_folding / v_folding_neg = log2(num) x PolyMatrixNTT(2, 2 t_gsw).  v_folding_neg may be NULL, meaning
+ * get_v_folding_neg(v_folding) as process_query always passes (server.rs:680): the library then uses its
+ * fast path, which never materialises the negated matrices (same bytes). */
 int b200pir_fold_ciphertexts(b200pir_ctx* ctx, uint64_t* v_cts, size_t num, const uint64_t* v_folding,
                              const uint64_t* v_folding_neg);
 /* server.rs:505-523 get_v_folding_neg */
@@ -126,12 +128,12 @@ int b200pir_process_query_batch(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp
 int b200pir_process_query_batch_dev(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
                                     size_t count, uint8_t* out_dev);
 /* Multi-GPU row sharding (DESIGN.md "multi-GPU"): stage A = expansion + first dimension + local fold rounds
- * on this GPU's rows; writes this rank's surviving ciphertexts (count x slices x PolyMatrixRaw(2,1)) to
- * `partial_dev`.  Stage B = remaining log2(world) fold rounds + pack + encode over the all-gathered
- * `gathered_dev` ([world][count][slices][2][2048] u64). */
+ * on this GPU's rows; writes this rank's surviving ciphertexts to `partial_dev` as count x slices ciphertexts
+ * in residue form (u32 [row(2)][crt(2)][2048] = coefficients mod q0 / q1, 32 KiB each).  Stage B = remaining
+ * log2(world) fold rounds + pack + encode over the all-gathered `gathered_dev` ([world][count][slices][2][2][2048]). */
 int b200pir_query_stage_a_dev(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
-                              size_t count, uint64_t* partial_dev);
-int b200pir_query_stage_b_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* gathered_dev, size_t world,
+                              size_t count, uint32_t* partial_dev);
+int b200pir_query_stage_b_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world,
                               size_t count, uint8_t* out_dev);
 
 /* Per-stage device time of the last profiled call, in milliseconds, measured with CUDA events on the

@@ -133,8 +133,10 @@ struct b200pir_ctx {
   DevBuf<uint32_t> w_v;          // [Q][2^g][2][2][2048]
   DevBuf<uint4> w_qdev;          // [Q][dim0][2048]
   DevBuf<uint32_t> w_vfold, w_vfold_neg;   // [Q][nu_2][2][2t][2][2048]
-  DevBuf<uint32_t> w_mult;       // [Q][slices][rows][2][2][2048]
-  DevBuf<uint64_t> w_cts;        // [Q][slices][rows][2][2048]
+  DevBuf<uint32_t> w_mult;       // [Q][slices][rows][2][2][2048]  NTT form, then residue form in place
+  DevBuf<uint32_t> w_cts;        // ping-pong partner of w_mult for the fold rounds (same size)
+  const uint32_t* folded = nullptr;   // where the last fold left its survivors
+  size_t folded_stride = 0;           // u32 words between consecutive (query, slice) survivors
   DevBuf<uint64_t> w_packed;     // [Q][inst][n+1][n][2048]
   DevBuf<uint8_t> w_resp;        // [Q][response_bytes]
   // profiling
@@ -190,7 +192,7 @@ struct b200pir_ctx {
     w_vfold.ensure(queries * std::max<size_t>(fold_words(), 1));
     w_vfold_neg.ensure(queries * std::max<size_t>(fold_words(), 1));
     w_mult.ensure(queries * slices * rows * 4 * POLY);
-    w_cts.ensure(queries * slices * rows * 2 * POLY);
+    w_cts.ensure(queries * slices * rows * 4 * POLY);
     w_packed.ensure(queries * hp.instances * (hp.n + 1) * hp.n * POLY);
     w_resp.ensure(queries * response_bytes);
     ws_queries = queries;
@@ -294,6 +296,22 @@ void run_fold(b200pir_ctx* c, uint64_t* cts, size_t batch, size_t batch_stride, 
   }
 }
 
+// Fast path on residue-form ciphertexts: ping-pong between `a` (input of the first round) and `b`.
+// Returns the buffer holding the survivors (entry 0 of each batch element).
+const uint32_t* run_fold_res(b200pir_ctx* c, uint32_t* a, uint32_t* b, size_t batch, size_t batch_stride, size_t num,
+                             int k0, const uint32_t* vfold, int slices_per_query) {
+  const size_t mat = (size_t)2 * 2 * c->hp.t_gsw * 2 * POLY;
+  int k = k0;
+  uint32_t* src = a;
+  uint32_t* dst = b;
+  for (size_t half = num / 2; half >= 1; half /= 2, k--) {
+    launch_fold_res(c->dp, src, dst, batch, batch_stride, (int)half, vfold + (size_t)k * mat, c->fold_words(),
+                    slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+    std::swap(src, dst);
+  }
+  return src;
+}
+
 // expansion (or direct upload) for `count` queries already in w_query / w_qdev,w_vfold
 void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
   b200pir_ctx::Scope sc(c, ST_EXPAND);
@@ -302,9 +320,7 @@ void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
       run_expand_query(c, pp, c->w_query.p + qi * 2 * POLY, c->w_v.p + qi * c->v_words(),
                        c->w_qdev.p + qi * (size_t)c->dim0 * POLY, c->w_vfold.p + qi * c->fold_words());
   }
-  if (c->hp.nu_2 > 0)
-    launch_folding_neg(c->dp, c->w_vfold_neg.p, c->w_vfold.p, (int)(count * c->hp.nu_2), (int)c->hp.t_gsw, c->bits_gsw,
-                       c->stream);
+  // v_folding_neg (server.rs:680) is not materialised: the fold fast path uses G - C_k implicitly.
 }
 
 // first dimension + from_ntt + local fold.  Leaves survivors at w_cts[(qi*slices + slice)*rows*2*POLY].
@@ -327,19 +343,22 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
     }
   }
   {
+    // server.rs:707-709 from_ntt, minus the CRT lift: inverse NTT of every CRT half in place -> residue form
     b200pir_ctx::Scope sc(c, ST_FROMNTT);
-    launch_from_ntt(c->dp, c->w_cts.p, c->w_mult.p, count * c->slices * rows * 2, c->stream);
+    launch_ntt32(c->dp, c->w_mult.p, count * c->slices * rows * 2, true, c->stream);
   }
   {
     b200pir_ctx::Scope sc(c, ST_FOLD);
+    c->folded = c->w_mult.p;
+    c->folded_stride = (size_t)rows * 4 * POLY;
     if (rows > 1)
-      run_fold(c, c->w_cts.p, count * c->slices, (size_t)rows * 2 * POLY, rows, (int)c->hp.nu_2 - 1, c->w_vfold.p,
-               c->w_vfold_neg.p, c->slices);
+      c->folded = run_fold_res(c, c->w_mult.p, c->w_cts.p, count * c->slices, (size_t)rows * 4 * POLY, rows,
+                               (int)c->hp.nu_2 - 1, c->w_vfold.p, c->slices);
   }
 }
 
 // pack + encode for `count` queries whose folded ciphertexts sit at folded + ((qi*slices)+t)*ct_stride
-void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* folded, size_t ct_stride, size_t count,
+void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* folded, size_t ct_stride, size_t count,
                      uint8_t* out_dev) {
   const auto& hp = c->hp;
   const size_t packed_words = (size_t)hp.instances * (hp.n + 1) * hp.n * POLY;
@@ -436,6 +455,13 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
   B200_CUDA(cudaMemcpy(c->d_tw.p + POLY, i0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p + 2 * POLY, f1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p + 3 * POLY, i1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  {
+    std::vector<Twiddle> lo(2 * 2 * 64);
+    for (int i = 0; i < 64; i++) { lo[(0 * 2 + 0) * 64 + i] = f0[i]; lo[(0 * 2 + 1) * 64 + i] = i0[i];
+                                   lo[(1 * 2 + 0) * 64 + i] = f1[i]; lo[(1 * 2 + 1) * 64 + i] = i1[i]; }
+    upload_poly_constants(lo.data());
+    upload_mul_constants(lo.data());
+  }
   DevParams& dp = c->dp;
   dp.q[0] = (uint32_t)q0; dp.q[1] = (uint32_t)q1m;
   dp.cr1[0] = (uint64_t)(((u128)1 << 64) / q0);
@@ -705,19 +731,35 @@ int b200pir_fold_ciphertexts(b200pir_ctx* c, uint64_t* v_cts, size_t num, const 
   Guard gd(c);
   if (num == 0 || (num & (num - 1))) throw Error(B200PIR_E_SHAPE, "number of ciphertexts must be a power of two");
   if (num == 1) return 0;                                          // server.rs:394-396
-  if (!v_folding || !v_folding_neg) throw Error(B200PIR_E_BADARG, "null argument");
+  if (!v_folding) throw Error(B200PIR_E_BADARG, "null argument");
   int dims = 0;
   while (((size_t)1 << dims) < num) dims++;
   if (dims > (int)c->hp.nu_2) throw Error(B200PIR_E_SHAPE, "more ciphertexts than 2^nu_2");
   const size_t mat = (size_t)2 * 2 * c->hp.t_gsw * 2 * POLY;
   DevBuf<uint64_t> cts(num * 2 * POLY), wide(dims * mat);
-  DevBuf<uint32_t> vf(c->fold_words()), vfn(c->fold_words());
+  DevBuf<uint32_t> vf(c->fold_words());
   B200_CUDA(cudaMemcpyAsync(cts.p, v_cts, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
   B200_CUDA(cudaMemcpyAsync(wide.p, v_folding, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
   launch_narrow(vf.p, wide.p, wide.n, c->stream);
-  B200_CUDA(cudaMemcpyAsync(wide.p, v_folding_neg, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
-  launch_narrow(vfn.p, wide.p, wide.n, c->stream);
-  run_fold(c, cts.p, 1, num * 2 * POLY, num, dims - 1, vf.p, vfn.p, 1);
+  if (v_folding_neg) {
+    // general path: honours an arbitrary v_folding_neg exactly as server.rs:405-425 does
+    DevBuf<uint32_t> vfn(c->fold_words());
+    B200_CUDA(cudaMemcpyAsync(wide.p, v_folding_neg, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_narrow(vfn.p, wide.p, wide.n, c->stream);
+    run_fold(c, cts.p, 1, num * 2 * POLY, num, dims - 1, vf.p, vfn.p, 1);
+  } else {
+    // fast path (what process_query uses): v_folding_neg = get_v_folding_neg(v_folding) implied.
+    // Round results are copied back so every slot ends up as the reference's in-place loop leaves it.
+    DevBuf<uint32_t> a(num * 4 * POLY), b(num * 4 * POLY);
+    launch_raw_to_res(c->dp, a.p, cts.p, num * 2, c->stream);
+    int k = dims - 1;
+    for (size_t half = num / 2; half >= 1; half /= 2, k--) {
+      launch_fold_res(c->dp, a.p, b.p, 1, num * 4 * POLY, (int)half, vf.p + (size_t)k * mat, c->fold_words(), 1,
+                      (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+      B200_CUDA(cudaMemcpyAsync(a.p, b.p, half * 4 * POLY * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    launch_res_to_raw(c->dp, cts.p, a.p, num * 2, c->stream);
+  }
   B200_CUDA(cudaMemcpyAsync(v_cts, cts.p, cts.n * 8, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
@@ -819,9 +861,10 @@ int b200pir_pack(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* v_ct, uint64_t*
   const auto& hp = c->hp;
   const size_t nn = hp.n * hp.n, outp = (hp.n + 1) * hp.n;
   DevBuf<uint64_t> cts(nn * 2 * POLY), raw(outp * POLY), wide(outp * 2 * POLY);
-  DevBuf<uint32_t> o(outp * 2 * POLY);
+  DevBuf<uint32_t> o(outp * 2 * POLY), res(nn * 4 * POLY);
   B200_CUDA(cudaMemcpyAsync(cts.p, v_ct, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
-  launch_pack(c->dp, raw.p, cts.p, 2 * POLY, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+  launch_raw_to_res(c->dp, res.p, cts.p, nn * 2, c->stream);
+  launch_pack(c->dp, raw.p, res.p, 4 * POLY, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
   // the reference's pack returns the NTT-form matrix (server.rs:467); the kernel already applied .raw()
   launch_to_ntt(c->dp, o.p, raw.p, outp, c->stream);
   launch_widen(wide.p, o.p, o.n, c->stream);
@@ -853,7 +896,7 @@ static void run_query_batch_resident(b200pir_ctx* c, b200pir_db* db, b200pir_pp*
   // queries are already in c->w_query
   run_prepare(c, pp, count);
   run_first_dim_and_fold(c, db, count);
-  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, count, out_dev);
+  run_pack_encode(c, pp, c->folded, c->folded_stride, count, out_dev);
 }
 
 int b200pir_process_query_batch_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev,
@@ -923,7 +966,7 @@ int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const 
   }
   run_prepare(c, pp, 1);
   run_first_dim_and_fold(c, db, 1);
-  run_pack_encode(c, pp, c->w_cts.p, (size_t)db->rows * 2 * POLY, 1, c->w_resp.p);
+  run_pack_encode(c, pp, c->folded, c->folded_stride, 1, c->w_resp.p);
   B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
   if (c->profile == 1) c->prof_collect();
@@ -933,7 +976,7 @@ int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const 
 }
 
 int b200pir_query_stage_a_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count,
-                              uint64_t* partial_dev) {
+                              uint32_t* partial_dev) {
   API_BEGIN
   if (!c || !query_cts_dev || !partial_dev) throw Error(B200PIR_E_BADARG, "null argument");
   Guard gd(c);
@@ -945,14 +988,14 @@ int b200pir_query_stage_a_dev(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, co
   B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts_dev, count * 2 * POLY * 8, cudaMemcpyDeviceToDevice, c->stream));
   run_prepare(c, pp, count);
   run_first_dim_and_fold(c, db, count);
-  // gather the survivors [count][slices] (stride rows*2*2048) into a dense buffer
-  B200_CUDA(cudaMemcpy2DAsync(partial_dev, 2 * POLY * 8, c->w_cts.p, (size_t)db->rows * 2 * POLY * 8, 2 * POLY * 8,
-                              count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
+  // gather the survivors [count][slices] into a dense buffer of residue-form ciphertexts
+  B200_CUDA(cudaMemcpy2DAsync(partial_dev, 4 * POLY * 4, c->folded, c->folded_stride * 4, 4 * POLY * 4, count * c->slices,
+                              cudaMemcpyDeviceToDevice, c->stream));
   B200_CUDA(cudaGetLastError());
   API_END
 }
 
-int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* gathered_dev, size_t world, size_t count,
+int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world, size_t count,
                               uint8_t* out_dev) {
   API_BEGIN
   if (!c || !gathered_dev || !out_dev) throw Error(B200PIR_E_BADARG, "null argument");
@@ -960,19 +1003,22 @@ int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* ga
   check_pp(c, pp);
   if (world == 0 || (world & (world - 1)) || world > (size_t)c->num_per) throw Error(B200PIR_E_SHAPE, "bad world size");
   c->ensure_workspace(count, world);
-  // gathered: [world][count][slices][2][2048]  ->  w_cts as [count][slices][world][2][2048]
-  const size_t ct = 2 * POLY;
+  // gathered: [world][count][slices][ct]  ->  w_mult as [count][slices][world][ct]   (ct = 4*2048 u32)
+  const size_t ct = 4 * POLY;
   for (size_t w = 0; w < world; w++)
-    B200_CUDA(cudaMemcpy2DAsync(c->w_cts.p + w * ct, world * ct * 8, gathered_dev + w * count * c->slices * ct, ct * 8,
-                                ct * 8, count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
+    B200_CUDA(cudaMemcpy2DAsync(c->w_mult.p + w * ct, world * ct * 4, gathered_dev + w * count * c->slices * ct, ct * 4,
+                                ct * 4, count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
   int dims = 0;
   while (((size_t)1 << dims) < world) dims++;
   {
     b200pir_ctx::Scope sc(c, ST_FOLD);
+    c->folded = c->w_mult.p;
+    c->folded_stride = world * ct;
     if (world > 1)
-      run_fold(c, c->w_cts.p, count * c->slices, world * ct, world, dims - 1, c->w_vfold.p, c->w_vfold_neg.p, c->slices);
+      c->folded = run_fold_res(c, c->w_mult.p, c->w_cts.p, count * c->slices, world * ct, world, dims - 1, c->w_vfold.p,
+                               c->slices);
   }
-  run_pack_encode(c, pp, c->w_cts.p, world * ct, count, out_dev);
+  run_pack_encode(c, pp, c->folded, c->folded_stride, count, out_dev);
   B200_CUDA(cudaGetLastError());
   API_END
 }

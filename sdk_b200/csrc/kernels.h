@@ -25,6 +25,12 @@ void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool invers
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s);
 // poly.rs:646-663 from_ntt: ntt32 -> raw u64 (inverse NTT both moduli + CRT lift)
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s);
+// raw u64 coefficients <-> residue form u32 [poly][n][z] (coefficient domain; the CRT lift is poly.rs:658)
+void launch_raw_to_res(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t polys, cudaStream_t s);
+void launch_res_to_raw(const DevParams& P, uint64_t* out, const uint32_t* res, size_t polys, cudaStream_t s);
+// twiddle entries 0..63 of every (modulus, direction) -> constant bank of the poly kernels' module
+void upload_poly_constants(const Twiddle* lo /* [2][2][64] */);
+void upload_mul_constants(const Twiddle* lo /* [2][2][64] */);
 // format converters for the C ABI (u64 [n][z] words < 2^32  <->  ntt32)
 void launch_widen(uint64_t* out, const uint32_t* in, size_t words, cudaStream_t s);
 void launch_narrow(uint32_t* out, const uint64_t* in, size_t words, cudaStream_t s);
@@ -61,6 +67,11 @@ void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_d
 void launch_fold_round(const DevParams& P, uint64_t* cts, size_t batch, size_t batch_stride /*u64 words*/, int half,
                        const uint32_t* c_pos, const uint32_t* c_neg, size_t c_batch_stride /*u32 words, per query*/,
                        int slices_per_query, int t_gsw, int bits, cudaStream_t s);
+// Fast path on residue-form ciphertexts u32 [batch][num][row][n][z] (see k_fold_res): out[i] (i < half) from
+// in[i], in[half+i]; in != out.  Needs only v_folding (c_pos).
+void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size_t batch, size_t batch_stride /*u32*/,
+                     int half, const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
+                     cudaStream_t s);
 // server.rs:505-523 get_v_folding_neg, computed pointwise: neg = (q_n - C) + G  (NTT is linear and the
 // gadget matrix is constant-coefficient, so this is the same canonical value)
 void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_folding, int count, int t_gsw, int bits,
@@ -83,9 +94,9 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v,
                          int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv, cudaStream_t s);
 
 // ---- packing + encoding (server.rs:429-503; lib/server compute/pack.rs)
-// folded: raw ciphertexts, ct (inst, t) at folded + (inst*n*n + t)*ct_stride (u64 words);
+// folded: residue-form ciphertexts, ct (inst, t) at folded + (inst*n*n + t)*ct_stride (u32 words);
 // w: ntt32 packing matrices; out: raw [inst][n+1][n][2048]
-void launch_pack(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+void launch_pack(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
                  const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
                  cudaStream_t s);
 void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,

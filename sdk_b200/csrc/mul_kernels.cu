@@ -19,6 +19,19 @@ namespace b200pir {
 
 namespace {
 
+__constant__ Twiddle c_tw_lo_mul[2][2][64];
+struct TwConstM {
+  int n, dir;
+  __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_mul[n][dir][i]; }
+};
+struct TwGlobalM {
+  const Twiddle* p;
+  __device__ __forceinline__ Twiddle operator()(int i) const {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
+    return Twiddle{v.x, v.y};
+  }
+};
+
 template <int R, int NQ, int UNROLL>
 __global__ void __launch_bounds__(512)
 k_multiply(DevParams P, MulGeom G, const uint4* __restrict__ db, const uint4* __restrict__ qv, uint32_t* __restrict__ out,
@@ -157,7 +170,7 @@ k_db_synth(DevParams P, MulGeom G, Shard sh, uint4* db, uint64_t seed, uint64_t 
   const int jp = blockIdx.x % half;
   const int ii = (blockIdx.x / half) % G.num_per;                 // local row
   const int slice = slice_begin + blockIdx.x / (half * G.num_per);
-  const uint32_t q = P.q[n];
+  const uint32_t q = n ? P.q[1] : P.q[0];
   const uint64_t num_per_global = (uint64_t)G.num_per * sh.count;
   const uint64_t num_items = (uint64_t)G.dim0 * num_per_global;
   struct S { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
@@ -171,7 +184,7 @@ k_db_synth(DevParams P, MulGeom G, Shard sh, uint4* db, uint64_t seed, uint64_t 
       uint64_t v = splitmix64_at(seed, base + a * 256 + tid) % pt;
       x[a] = (v > pt / 2) ? (uint32_t)(q - (uint32_t)(pt - v)) : (uint32_t)v;     // recenter_mod, then mod q_n
     }
-    ntt_forward_group(tid, x, ntt_smem + n * NTT_SMEM_WORDS, P.fwd[n], q, S());
+    ntt_forward_group(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());
 #pragma unroll
     for (int k = 0; k < 8; k++) cell[(tid * 8 + k) * 4 + jb * 2 + n] = x[k];
   }
@@ -244,6 +257,9 @@ inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + blo
 
 }  // namespace
 
+void upload_mul_constants(const Twiddle* lo) {
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_mul, lo, sizeof(Twiddle) * 2 * 2 * 64));
+}
 void launch_multiply(const DevParams& P, const MulGeom& G, const uint4* db_dev, const uint4* q_dev, uint32_t* out,
                      int slice_begin, int slice_count, int nq, size_t q_stride, size_t out_stride, int variant,
                      cudaStream_t s) {

@@ -72,52 +72,61 @@ NTT_HD uint32_t ntt_canon(uint32_t v, uint32_t q, uint32_t two_q) {
 // Three butterfly stages over the 3 index bits held in registers (a = 0..7, bit2 = first stage).
 // tw_base[s] is the table offset 2^mm of stage s; grp[s] the group index of the thread's a=0
 // element at that stage (group of element a is grp[s] + (a >> (3 - s))).
-NTT_HD void radix8_fwd(uint32_t (&x)[8], const Twiddle* tab, int m0, int g0, uint32_t q, uint32_t two_q) {
+// `tab` is any callable idx -> Twiddle (plain array, __constant__ bank, shared-memory copy ...).
+struct TwArray {
+  const Twiddle* p;
+  NTT_HD Twiddle operator()(int i) const { return p[i]; }
+};
+template <typename Tab>
+NTT_HD void radix8_fwd(uint32_t (&x)[8], Tab tab, int m0, int g0, uint32_t q, uint32_t two_q) {
   // stage s=0: pairs (a, a+4); group = g0                    table idx m0 + g0
   // stage s=1: pairs (a, a+2); group = 2*g0 + (a>>2)         table idx 2*m0 + ...
   // stage s=2: pairs (a, a+1); group = 4*g0 + (a>>1)
-  Twiddle t0 = tab[m0 + g0];
+  Twiddle t0 = tab(m0 + g0);
 #pragma unroll
   for (int a = 0; a < 4; a++) bfly_fwd(x[a], x[a + 4], t0, q, two_q);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    Twiddle t1 = tab[2 * m0 + 2 * g0 + h];
+    Twiddle t1 = tab(2 * m0 + 2 * g0 + h);
 #pragma unroll
     for (int a = 0; a < 2; a++) bfly_fwd(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
   }
 #pragma unroll
   for (int h = 0; h < 4; h++) {
-    Twiddle t2 = tab[4 * m0 + 4 * g0 + h];
+    Twiddle t2 = tab(4 * m0 + 4 * g0 + h);
     bfly_fwd(x[2 * h], x[2 * h + 1], t2, q, two_q);
   }
 }
-NTT_HD void radix8_inv(uint32_t (&x)[8], const Twiddle* tab, int m0, int g0, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void radix8_inv(uint32_t (&x)[8], Tab tab, int m0, int g0, uint32_t q, uint32_t two_q) {
   // exact reverse order of radix8_fwd
 #pragma unroll
   for (int h = 0; h < 4; h++) {
-    Twiddle t2 = tab[4 * m0 + 4 * g0 + h];
+    Twiddle t2 = tab(4 * m0 + 4 * g0 + h);
     bfly_inv(x[2 * h], x[2 * h + 1], t2, q, two_q);
   }
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    Twiddle t1 = tab[2 * m0 + 2 * g0 + h];
+    Twiddle t1 = tab(2 * m0 + 2 * g0 + h);
 #pragma unroll
     for (int a = 0; a < 2; a++) bfly_inv(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
   }
-  Twiddle t0 = tab[m0 + g0];
+  Twiddle t0 = tab(m0 + g0);
 #pragma unroll
   for (int a = 0; a < 4; a++) bfly_inv(x[a], x[a + 4], t0, q, two_q);
 }
 
 // ---- per-pass thread-local steps.  `tid` in [0,256).  smem = this transform's 2304-word buffer.
 // Pass A (stages 0..2) on the strided layout; then store.
-NTT_HD void fwd_pass_a(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void fwd_pass_a(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   radix8_fwd(x, tab, 1, 0, q, two_q);                                  // m = 1,2,4 ; group base 0
 #pragma unroll
   for (int a = 0; a < 8; a++) smem[ntt_phys(a * 256 + tid)] = x[a];
 }
 // Pass B (stages 3..5): e = hi*256 + a*32 + lo
-NTT_HD void fwd_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void fwd_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int hi = tid >> 5, lo = tid & 31;
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(hi * 256 + a * 32 + lo)];
@@ -126,7 +135,8 @@ NTT_HD void fwd_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle*
   for (int a = 0; a < 8; a++) smem[ntt_phys(hi * 256 + a * 32 + lo)] = x[a];
 }
 // Pass C (stages 6..8): e = H*32 + a*4 + l2
-NTT_HD void fwd_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void fwd_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int H = tid >> 2, l2 = tid & 3;
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(H * 32 + a * 4 + l2)];
@@ -135,19 +145,20 @@ NTT_HD void fwd_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle*
   for (int a = 0; a < 8; a++) smem[ntt_phys(H * 32 + a * 4 + l2)] = x[a];
 }
 // Pass D (stages 9,10) on the contiguous layout e = tid*8 + k, then canonicalise.
-NTT_HD void fwd_pass_d(int tid, uint32_t (&x)[8], const uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void fwd_pass_d(int tid, uint32_t (&x)[8], const uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int base = ntt_phys(tid * 8);                                         // 8 contiguous words (two 16-byte chunks)
 #pragma unroll
   for (int k = 0; k < 8; k++) x[k] = smem[base + k];
 #pragma unroll
   for (int h = 0; h < 2; h++) {                                         // stage 9: m=512, group = 2*tid + h, pairs (k, k+2)
-    Twiddle t = tab[512 + 2 * tid + h];
+    Twiddle t = tab(512 + 2 * tid + h);
     bfly_fwd(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
     bfly_fwd(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
   }
 #pragma unroll
   for (int h = 0; h < 4; h++) {                                         // stage 10: m=1024, group = 4*tid + h
-    Twiddle t = tab[1024 + 4 * tid + h];
+    Twiddle t = tab(1024 + 4 * tid + h);
     bfly_fwd(x[2 * h], x[2 * h + 1], t, q, two_q);
   }
 #pragma unroll
@@ -155,15 +166,16 @@ NTT_HD void fwd_pass_d(int tid, uint32_t (&x)[8], const uint32_t* smem, const Tw
 }
 
 // Inverse: contiguous layout in (values in [0,2q)), strided layout out (canonical).
-NTT_HD void inv_pass_d(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void inv_pass_d(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
 #pragma unroll
   for (int h = 0; h < 4; h++) {                                         // stage mm=10
-    Twiddle t = tab[1024 + 4 * tid + h];
+    Twiddle t = tab(1024 + 4 * tid + h);
     bfly_inv(x[2 * h], x[2 * h + 1], t, q, two_q);
   }
 #pragma unroll
   for (int h = 0; h < 2; h++) {                                         // stage mm=9
-    Twiddle t = tab[512 + 2 * tid + h];
+    Twiddle t = tab(512 + 2 * tid + h);
     bfly_inv(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
     bfly_inv(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
   }
@@ -171,7 +183,8 @@ NTT_HD void inv_pass_d(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle*
 #pragma unroll
   for (int k = 0; k < 8; k++) smem[base + k] = x[k];
 }
-NTT_HD void inv_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void inv_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int H = tid >> 2, l2 = tid & 3;
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(H * 32 + a * 4 + l2)];
@@ -179,7 +192,8 @@ NTT_HD void inv_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle*
 #pragma unroll
   for (int a = 0; a < 8; a++) smem[ntt_phys(H * 32 + a * 4 + l2)] = x[a];
 }
-NTT_HD void inv_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void inv_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int hi = tid >> 5, lo = tid & 31;
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(hi * 256 + a * 32 + lo)];
@@ -187,7 +201,8 @@ NTT_HD void inv_pass_b(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle*
 #pragma unroll
   for (int a = 0; a < 8; a++) smem[ntt_phys(hi * 256 + a * 32 + lo)] = x[a];
 }
-NTT_HD void inv_pass_a(int tid, uint32_t (&x)[8], const uint32_t* smem, const Twiddle* tab, uint32_t q, uint32_t two_q) {
+template <typename Tab>
+NTT_HD void inv_pass_a(int tid, uint32_t (&x)[8], const uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = smem[ntt_phys(a * 256 + tid)];
   radix8_inv(x, tab, 1, 0, q, two_q);
@@ -200,31 +215,69 @@ NTT_HD void inv_pass_a(int tid, uint32_t (&x)[8], const uint32_t* smem, const Tw
 // order their shared-memory accesses).  On entry to either function the group's smem buffer must
 // not be in use; on return it may still be read by slower threads, so callers issue gsync()
 // before the next transform reuses it (both functions start with that barrier themselves).
-template <typename Sync>
-__device__ __forceinline__ void ntt_forward_group(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab,
+// `lo` serves table indices 1..63 (passes A, B: thread-uniform / warp-uniform -> constant bank),
+// `hi` serves indices 64..2047 (passes C, D: per-thread -> shared memory or L1).
+template <typename Sync, typename TabLo, typename TabHi>
+__device__ __forceinline__ void ntt_forward_group(int tid, uint32_t (&x)[8], uint32_t* smem, TabLo lo, TabHi hi,
                                                   uint32_t q, Sync gsync) {
   const uint32_t two_q = 2 * q;
   gsync();
-  fwd_pass_a(tid, x, smem, tab, q, two_q);
+  fwd_pass_a(tid, x, smem, lo, q, two_q);
   gsync();
-  fwd_pass_b(tid, x, smem, tab, q, two_q);
+  fwd_pass_b(tid, x, smem, lo, q, two_q);
   gsync();
-  fwd_pass_c(tid, x, smem, tab, q, two_q);
+  fwd_pass_c(tid, x, smem, hi, q, two_q);
   gsync();
-  fwd_pass_d(tid, x, smem, tab, q, two_q);
+  fwd_pass_d(tid, x, smem, hi, q, two_q);
 }
-template <typename Sync>
-__device__ __forceinline__ void ntt_inverse_group(int tid, uint32_t (&x)[8], uint32_t* smem, const Twiddle* tab,
+// two independent transforms between the same barriers (instruction-level parallelism x2, half the
+// barriers per transform)
+template <typename Sync, typename TabLo, typename TabHi>
+__device__ __forceinline__ void ntt_forward_group2(int tid, uint32_t (&x0)[8], uint32_t (&x1)[8], uint32_t* smem0,
+                                                   uint32_t* smem1, TabLo lo, TabHi hi, uint32_t q, Sync gsync) {
+  const uint32_t two_q = 2 * q;
+  gsync();
+  fwd_pass_a(tid, x0, smem0, lo, q, two_q);
+  fwd_pass_a(tid, x1, smem1, lo, q, two_q);
+  gsync();
+  fwd_pass_b(tid, x0, smem0, lo, q, two_q);
+  fwd_pass_b(tid, x1, smem1, lo, q, two_q);
+  gsync();
+  fwd_pass_c(tid, x0, smem0, hi, q, two_q);
+  fwd_pass_c(tid, x1, smem1, hi, q, two_q);
+  gsync();
+  fwd_pass_d(tid, x0, smem0, hi, q, two_q);
+  fwd_pass_d(tid, x1, smem1, hi, q, two_q);
+}
+template <typename Sync, typename TabLo, typename TabHi>
+__device__ __forceinline__ void ntt_inverse_group(int tid, uint32_t (&x)[8], uint32_t* smem, TabLo lo, TabHi hi,
                                                   uint32_t q, Sync gsync) {
   const uint32_t two_q = 2 * q;
   gsync();
-  inv_pass_d(tid, x, smem, tab, q, two_q);
+  inv_pass_d(tid, x, smem, hi, q, two_q);
   gsync();
-  inv_pass_c(tid, x, smem, tab, q, two_q);
+  inv_pass_c(tid, x, smem, hi, q, two_q);
   gsync();
-  inv_pass_b(tid, x, smem, tab, q, two_q);
+  inv_pass_b(tid, x, smem, lo, q, two_q);
   gsync();
-  inv_pass_a(tid, x, smem, tab, q, two_q);
+  inv_pass_a(tid, x, smem, lo, q, two_q);
+}
+template <typename Sync, typename TabLo, typename TabHi>
+__device__ __forceinline__ void ntt_inverse_group2(int tid, uint32_t (&x0)[8], uint32_t (&x1)[8], uint32_t* smem0,
+                                                   uint32_t* smem1, TabLo lo, TabHi hi, uint32_t q, Sync gsync) {
+  const uint32_t two_q = 2 * q;
+  gsync();
+  inv_pass_d(tid, x0, smem0, hi, q, two_q);
+  inv_pass_d(tid, x1, smem1, hi, q, two_q);
+  gsync();
+  inv_pass_c(tid, x0, smem0, hi, q, two_q);
+  inv_pass_c(tid, x1, smem1, hi, q, two_q);
+  gsync();
+  inv_pass_b(tid, x0, smem0, lo, q, two_q);
+  inv_pass_b(tid, x1, smem1, lo, q, two_q);
+  gsync();
+  inv_pass_a(tid, x0, smem0, lo, q, two_q);
+  inv_pass_a(tid, x1, smem1, lo, q, two_q);
 }
 #endif
 

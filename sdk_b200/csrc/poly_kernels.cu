@@ -14,30 +14,84 @@ namespace b200pir {
 namespace {
 
 constexpr int CTA = 512;
+constexpr int HI_TW = NTT_N - 64;       // twiddle table entries 64..2047 (passes C, D)
+
+// Table entries 0..63 (passes A and B) of every (modulus, direction) live in the constant bank: the
+// index is thread-uniform (pass A) or warp-uniform (pass B), so they cost no load/store-unit traffic.
+__constant__ Twiddle c_tw_lo[2][2][64];     // [n][0 = forward, 1 = inverse][index]
+
+struct TwConst {
+  int n, dir;
+  __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo[n][dir][i]; }
+};
+struct TwShared {            // shared-memory copy of entries 64..2047
+  const Twiddle* p;
+  __device__ __forceinline__ Twiddle operator()(int i) const { return p[i - 64]; }
+};
+struct TwGlobal {            // straight from global memory through L1 (rarely used transforms)
+  const Twiddle* p;
+  __device__ __forceinline__ Twiddle operator()(int i) const {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
+    return Twiddle{v.x, v.y};
+  }
+};
 
 struct Grp {
   int tid;              // 0..255 inside the group
   int n;                // modulus index handled by this group
   uint32_t q;
   uint64_t cr1;
-  const Twiddle* fwd;
+  const Twiddle* fwd;   // global tables
   const Twiddle* inv;
   uint32_t* smem;       // this group's NTT exchange buffer (NTT_SMEM_WORDS)
+  const Twiddle* fwd_hi_sm;   // shared copy of fwd[64..], or null
 };
 struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
+// group g of a 512-thread CTA (threads 256g..256g+255) works modulo q_g
 __device__ __forceinline__ Grp make_grp(const DevParams& P, uint32_t* ntt_smem) {
   Grp g;
   g.n = threadIdx.x >> 8;
   g.tid = threadIdx.x & 255;
-  g.q = P.q[g.n];
-  g.cr1 = P.cr1[g.n];
-  g.fwd = P.fwd[g.n];
-  g.inv = P.inv[g.n];
+  g.q = g.n ? P.q[1] : P.q[0];
+  g.cr1 = g.n ? P.cr1[1] : P.cr1[0];
+  g.fwd = g.n ? P.fwd[1] : P.fwd[0];
+  g.inv = g.n ? P.inv[1] : P.inv[0];
   g.smem = ntt_smem + g.n * NTT_SMEM_WORDS;
+  g.fwd_hi_sm = nullptr;
   return g;
+}
+// one 256-thread CTA per modulus (blockIdx.y = n)
+__device__ __forceinline__ Grp make_grp_single(const DevParams& P, uint32_t* ntt_smem, int n) {
+  Grp g;
+  g.n = n;
+  g.tid = threadIdx.x;
+  g.q = n ? P.q[1] : P.q[0];
+  g.cr1 = n ? P.cr1[1] : P.cr1[0];
+  g.fwd = n ? P.fwd[1] : P.fwd[0];
+  g.inv = n ? P.inv[1] : P.inv[0];
+  g.smem = ntt_smem;
+  g.fwd_hi_sm = nullptr;
+  return g;
+}
+// copy this group's forward table entries 64..2047 into shared memory (visible after the next barrier)
+__device__ __forceinline__ void stage_fwd_twiddles(Grp& g, Twiddle* dst) {
+  for (int i = g.tid; i < HI_TW; i += 256) {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(g.fwd + 64 + i));
+    dst[i] = Twiddle{v.x, v.y};
+  }
+  g.fwd_hi_sm = dst;
+}
+// SM = true: the kernel staged the forward hi-table with stage_fwd_twiddles()
+template <bool SM>
+__device__ __forceinline__ void grp_ntt_fwd(const Grp& g, uint32_t (&x)[8]) {
+  if (SM) ntt_forward_group(g.tid, x, g.smem, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+  else ntt_forward_group(g.tid, x, g.smem, TwConst{g.n, 0}, TwGlobal{g.fwd}, g.q, CtaSync());
+}
+__device__ __forceinline__ void grp_ntt_inv(const Grp& g, uint32_t (&x)[8]) {
+  ntt_inverse_group(g.tid, x, g.smem, TwConst{g.n, 1}, TwGlobal{g.inv}, g.q, CtaSync());
 }
 
 // contiguous-layout load/store of 8 ntt32 words (two 16-byte accesses)
@@ -65,7 +119,7 @@ __device__ __forceinline__ void acc_reduce(uint64_t (&acc)[ROWS][8], const Grp& 
 // acc[r][.] += sum_k  C[r][col0 + k*col_step] (.) NTT(digit_k(v))     (pointwise, this group's modulus)
 // v[a] = raw coefficient at index a*256 + tid (strided layout).  c0 points at element (row 0, first
 // column) of this group's modulus, offset by tid*8.  `cnt` counts products held per accumulator.
-template <int ROWS>
+template <int ROWS, bool SM>
 __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
                                            int bits, const uint32_t* c0, size_t col_step, size_t row_step,
                                            const Grp& g) {
@@ -74,7 +128,7 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
     uint32_t x[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) x[a] = gadget_digit(v[a], k, bits, mask);
-    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+    grp_ntt_fwd<SM>(g, x);
     const uint32_t* c = c0 + (size_t)k * col_step;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
@@ -105,53 +159,71 @@ __device__ __forceinline__ void crt_lift(const uint32_t (&x)[8], uint32_t* res, 
 }
 
 // ------------------------------------------------------------------ plain transforms
-__global__ void __launch_bounds__(CTA) k_ntt32(DevParams P, uint32_t* polys, int inverse) {
-  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
-  Grp g = make_grp(P, ntt_smem);
+// grid = (polys, 2 moduli), 256 threads: one CTA per single-modulus transform.
+__global__ void __launch_bounds__(256) k_ntt32(DevParams P, uint32_t* polys, int inverse) {
+  __shared__ __align__(16) uint32_t ntt_smem[NTT_SMEM_WORDS];
+  Grp g = make_grp_single(P, ntt_smem, blockIdx.y);
   uint32_t* p = polys + ((size_t)blockIdx.x * 2 + g.n) * POLY;
   uint32_t x[8];
   if (!inverse) {
 #pragma unroll
     for (int a = 0; a < 8; a++) x[a] = p[a * 256 + g.tid];
-    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+    grp_ntt_fwd<false>(g, x);
     st8(p + g.tid * 8, x);
   } else {
     ld8(x, p + g.tid * 8);
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
 #pragma unroll
     for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
   }
 }
 // u64 ABI words (ntt.rs:68 / :213 operate on &mut [u64]); values are truncated to 32 bits exactly as
 // the reference's forward butterfly does (`as u32`, ntt.rs:93-94).
-__global__ void __launch_bounds__(CTA) k_ntt_u64(DevParams P, uint64_t* polys, int inverse) {
-  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
-  Grp g = make_grp(P, ntt_smem);
+__global__ void __launch_bounds__(256) k_ntt_u64(DevParams P, uint64_t* polys, int inverse) {
+  __shared__ __align__(16) uint32_t ntt_smem[NTT_SMEM_WORDS];
+  Grp g = make_grp_single(P, ntt_smem, blockIdx.y);
   uint64_t* p = polys + ((size_t)blockIdx.x * 2 + g.n) * POLY;
   uint32_t x[8];
   if (!inverse) {
 #pragma unroll
     for (int a = 0; a < 8; a++) x[a] = (uint32_t)p[a * 256 + g.tid];
-    ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+    grp_ntt_fwd<false>(g, x);
 #pragma unroll
     for (int k = 0; k < 8; k++) p[g.tid * 8 + k] = x[k];
   } else {
 #pragma unroll
     for (int k = 0; k < 8; k++) x[k] = (uint32_t)p[g.tid * 8 + k];
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
 #pragma unroll
     for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
   }
 }
-__global__ void __launch_bounds__(CTA) k_to_ntt(DevParams P, uint32_t* out, const uint64_t* raw) {
-  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
-  Grp g = make_grp(P, ntt_smem);
+__global__ void __launch_bounds__(256) k_to_ntt(DevParams P, uint32_t* out, const uint64_t* raw) {
+  __shared__ __align__(16) uint32_t ntt_smem[NTT_SMEM_WORDS];
+  Grp g = make_grp_single(P, ntt_smem, blockIdx.y);
   const uint64_t* src = raw + (size_t)blockIdx.x * POLY;
   uint32_t x[8];
 #pragma unroll
   for (int a = 0; a < 8; a++) x[a] = barrett64(src[a * 256 + g.tid], g.cr1, g.q);
-  ntt_forward_group(g.tid, x, g.smem, g.fwd, g.q, CtaSync());
+  grp_ntt_fwd<false>(g, x);
   st8(out + ((size_t)blockIdx.x * 2 + g.n) * POLY + g.tid * 8, x);
+}
+// raw u64 coefficients -> residue form u32 [poly][n][z] (coefficient domain), and back (CRT lift)
+__global__ void k_raw_to_res(DevParams P, uint32_t* out, const uint64_t* raw, size_t polys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // over polys * 2048
+  if (idx >= polys * POLY) return;
+  size_t poly = idx / POLY;
+  int z = (int)(idx % POLY);
+  uint64_t v = raw[idx];
+  out[(poly * 2 + 0) * POLY + z] = barrett64(v, P.cr1[0], P.q[0]);
+  out[(poly * 2 + 1) * POLY + z] = barrett64(v, P.cr1[1], P.q[1]);
+}
+__global__ void k_res_to_raw(DevParams P, uint64_t* out, const uint32_t* res, size_t polys) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= polys * POLY) return;
+  size_t poly = idx / POLY;
+  int z = (int)(idx % POLY);
+  out[idx] = crt_compose(res[(poly * 2 + 0) * POLY + z], res[(poly * 2 + 1) * POLY + z], P);
 }
 __global__ void __launch_bounds__(CTA) k_from_ntt(DevParams P, uint64_t* out, const uint32_t* in) {
   __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
@@ -159,7 +231,7 @@ __global__ void __launch_bounds__(CTA) k_from_ntt(DevParams P, uint64_t* out, co
   Grp g = make_grp(P, ntt_smem);
   uint32_t x[8];
   ld8(x, in + ((size_t)blockIdx.x * 2 + g.n) * POLY + g.tid * 8);
-  ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+  grp_ntt_inv(g, x);
   uint64_t* dst = out + (size_t)blockIdx.x * POLY;
   crt_lift(x, res, g, P, [&](int z, uint64_t v) { dst[z] = v; });
 }
@@ -204,7 +276,7 @@ k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const ui
       for (int a = 0; a < 8; a++) v[a] = ct[rho * POLY + a * 256 + g.tid];
       // G^-1 row index = rho + 2k  -> key-matrix column rho + 2k
       const uint32_t* c0 = C + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
-      digits_mac<2>(acc, cnt, v, t_gsw, bits, c0, col_step, row_step, g);
+      digits_mac<2, false>(acc, cnt, v, t_gsw, bits, c0, col_step, row_step, g);
     }
   }
   uint64_t* dst = base + (size_t)i * 2 * POLY;
@@ -213,9 +285,113 @@ k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const ui
     uint32_t x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = barrett64(acc[r][e], g.cr1, g.q);
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
     uint64_t* d = dst + r * POLY;
     crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
+  }
+}
+
+// ------------------------------------------------------------------ fold, fast path (residue form)
+// Ciphertexts are kept in "residue form": u32 [ct][row][n][z] = coefficient z of the row modulo q_n
+// (what the inverse NTT of each CRT half produces, before the CRT lift).  One step computes
+//     out[i] = ct[i] + INTT( C_k . NTT( G^-1(ct[half+i]) - G^-1(ct[i]) ) )            (mod q_n, per modulus)
+// which is the same canonical value as server.rs:405-425's
+//     from_ntt( (G - C_k) . NTT(G^-1(ct[i])) + C_k . NTT(G^-1(ct[half+i])) )
+// because v_folding_neg[k] = G - C_k (server.rs:505-523), G . G^-1(x) = x and the NTT is linear over
+// Z_{q_n}; canonical representatives are unique, so the bytes agree.  It needs half the forward
+// transforms, no CRT lift on the way out, and no v_folding_neg at all.
+// grid = (batch*half, 2 moduli), 256 threads.  in/out are distinct buffers (ping-pong): the CTA of
+// modulus n reads BOTH residues of its inputs (for the gadget digits) while the other CTA writes.
+__global__ void __launch_bounds__(256, 2)
+k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
+           const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* sm0 = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
+  Twiddle* tw = reinterpret_cast<Twiddle*>(sm1 + NTT_SMEM_WORDS);
+  Grp g = make_grp_single(P, sm0, blockIdx.y);
+  stage_fwd_twiddles(g, tw);
+  const TwConst lo{g.n, 0};
+  const TwShared hi{tw};
+  const int b = blockIdx.x / half, i = blockIdx.x % half;
+  const uint32_t* ci = in + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
+  const uint32_t* ch = in + (size_t)b * batch_stride + (size_t)(half + i) * 4 * POLY;
+  const uint32_t* C = c_pos + (size_t)(b / slices_per_query) * c_batch_stride;
+  const int cols = 2 * t_gsw;
+  const size_t row_step = (size_t)cols * 2 * POLY;
+  const uint64_t mask = (1ull << bits) - 1;
+  const uint32_t q = g.q;
+
+  uint64_t acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[r][e] = 0;
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    uint64_t vi[8], vh[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int z = a * 256 + g.tid;
+      vi[a] = crt_compose(__ldg(ci + (rho * 2 + 0) * POLY + z), __ldg(ci + (rho * 2 + 1) * POLY + z), P);
+      vh[a] = crt_compose(__ldg(ch + (rho * 2 + 0) * POLY + z), __ldg(ch + (rho * 2 + 1) * POLY + z), P);
+    }
+    // key-matrix column of digit k: rho + 2k
+    const uint32_t* c0 = C + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < t_gsw; k += 2) {
+      uint32_t x0[8], x1[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        uint32_t d0 = gadget_digit(vh[a], k, bits, mask) - gadget_digit(vi[a], k, bits, mask);
+        uint32_t d1 = gadget_digit(vh[a], k + 1, bits, mask) - gadget_digit(vi[a], k + 1, bits, mask);
+        x0[a] = ntt_min(d0, d0 + q);           // negative differences wrap: add q
+        x1[a] = ntt_min(d1, d1 + q);
+      }
+      ntt_forward_group2(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        uint32_t cv[8];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)(k + 1) * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
+      }
+    }
+    if (k < t_gsw) {                            // odd t_gsw: last digit alone
+      uint32_t x0[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        uint32_t d0 = gadget_digit(vh[a], k, bits, mask) - gadget_digit(vi[a], k, bits, mask);
+        x0[a] = ntt_min(d0, d0 + q);
+      }
+      ntt_forward_group(g.tid, x0, sm0, lo, hi, q, CtaSync());
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        uint32_t cv[8];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
+      }
+    }
+    // 2 * t_gsw <= 112 products of < 2^56 per accumulator in total: no overflow before the final reduction
+  }
+  uint32_t y0[8], y1[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    y0[e] = barrett64(acc[0][e], g.cr1, q);
+    y1[e] = barrett64(acc[1][e], g.cr1, q);
+  }
+  ntt_inverse_group2(g.tid, y0, y1, sm0, sm1, TwConst{g.n, 1}, TwGlobal{g.inv}, q, CtaSync());
+  uint32_t* co = out + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int z = a * 256 + g.tid;
+    co[(0 * 2 + g.n) * POLY + z] = addmod(y0[a], __ldg(ci + (0 * 2 + g.n) * POLY + z), q);
+    co[(1 * 2 + g.n) * POLY + z] = addmod(y1[a], __ldg(ci + (1 * 2 + g.n) * POLY + z), q);
   }
 }
 
@@ -257,6 +433,7 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
   uint64_t* autom = reinterpret_cast<uint64_t*>(res + 2 * POLY);      // [2][2048]
+  Twiddle* tw = reinterpret_cast<Twiddle*>(autom + 2 * POLY);         // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
 
   const int i = blockIdx.x;
@@ -269,6 +446,7 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
   const int t_exp = left ? R.t_left : R.t_right;
   const int bits = left ? R.bits_left : R.bits_right;
 
+  stage_fwd_twiddles(g, tw + g.n * HI_TW);
   uint32_t* vi = v + (size_t)i * 4 * POLY;
   uint32_t keep[2][8];
   // from_ntt + automorph (poly.rs:393-405), scattered into shared memory
@@ -278,7 +456,7 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
     ld8(x, vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
 #pragma unroll
     for (int e = 0; e < 8; e++) keep[rho][e] = x[e];
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
     uint64_t* au = autom + rho * POLY;
     const int t_auto = R.t_auto;
     const uint64_t Q = P.modulus;
@@ -301,12 +479,12 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
     for (int a = 0; a < 8; a++) vv[a] = autom[a * 256 + g.tid];
     // gadget_invert_rdim(.., rdim = 1): digit k -> key column k  (server.rs:82-89)
     const uint32_t* c0 = W + (size_t)g.n * POLY + g.tid * 8;
-    digits_mac<2>(acc, cnt, vv, t_exp, bits, c0, (size_t)2 * POLY, (size_t)t_exp * 2 * POLY, g);
+    digits_mac<2, true>(acc, cnt, vv, t_exp, bits, c0, (size_t)2 * POLY, (size_t)t_exp * 2 * POLY, g);
   }
   uint32_t y[8];
 #pragma unroll
   for (int a = 0; a < 8; a++) y[a] = barrett64(autom[POLY + a * 256 + g.tid], g.cr1, g.q);
-  ntt_forward_group(g.tid, y, g.smem, g.fwd, g.q, CtaSync());
+  grp_ntt_fwd<true>(g, y);
 #pragma unroll
   for (int rho = 0; rho < 2; rho++) {
     uint32_t o[8];
@@ -337,7 +515,9 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, 
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
   uint64_t* raw = reinterpret_cast<uint64_t*>(res + 2 * POLY);        // [2][2048]
+  Twiddle* tw = reinterpret_cast<Twiddle*>(raw + 2 * POLY);           // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
+  stage_fwd_twiddles(g, tw + g.n * HI_TW);
   const int i = blockIdx.x / t_gsw, j = blockIdx.x % t_gsw;
   const int idx_inp = idx_factor * (i * t_gsw + j) + idx_offset;
   const uint32_t* inp = v + (size_t)idx_inp * 4 * POLY;
@@ -348,7 +528,7 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, 
     uint32_t x[8];
     ld8(x, inp + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
     st8(out + (((size_t)rho * cols + 2 * j + 1) * 2 + g.n) * POLY + g.tid * 8, x);      // ct.copy_into(.., 0, 2j+1)
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
     uint64_t* d = raw + rho * POLY;
     crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
   }
@@ -366,7 +546,7 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, 
 #pragma unroll
     for (int a = 0; a < 8; a++) vv[a] = raw[rho * POLY + a * 256 + g.tid];
     const uint32_t* c0 = v_conv + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
-    digits_mac<2>(acc, cnt, vv, t_conv, bits_conv, c0, (size_t)2 * 2 * POLY, (size_t)ccols * 2 * POLY, g);
+    digits_mac<2, true>(acc, cnt, vv, t_conv, bits_conv, c0, (size_t)2 * 2 * POLY, (size_t)ccols * 2 * POLY, g);
   }
 #pragma unroll
   for (int r = 0; r < 2; r++) {
@@ -380,13 +560,15 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, 
 // ------------------------------------------------------------------ pack (v0: server.rs:429-468; v1: lib/server pack.rs:45-98)
 template <int ROWS>
 __global__ void __launch_bounds__(CTA, 1)
-k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride, const uint32_t* v_packing, int t_conv,
+k_pack(DevParams P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride, const uint32_t* v_packing, int t_conv,
        int bits, int version) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
-  uint64_t* rawbuf = reinterpret_cast<uint64_t*>(res + 2 * POLY);     // [2048]
+  uint64_t* rawbuf = reinterpret_cast<uint64_t*>(res + 2 * POLY);     // [2048] (+ [2048] unused)
+  Twiddle* tw = reinterpret_cast<Twiddle*>(rawbuf + 2 * POLY);        // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
+  stage_fwd_twiddles(g, tw + g.n * HI_TW);
   constexpr int n = ROWS - 1;
   const int inst = blockIdx.x / n, c = blockIdx.x % n;
   const size_t mat_words = (size_t)ROWS * t_conv * 2 * POLY;
@@ -400,7 +582,8 @@ k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
 
 #pragma unroll 1
   for (int r = 0; r < n; r++) {
-    const uint64_t* ct = folded + ((size_t)inst * n * n + (size_t)r * n + c) * ct_stride;
+    // residue form: u32 [row][n][z]
+    const uint32_t* ct = folded + ((size_t)inst * n * n + (size_t)r * n + c) * ct_stride;
     const uint32_t* W = v_packing + (version == 0 ? (size_t)r * mat_words : 0);
     uint64_t acc[ROWS][8];
 #pragma unroll
@@ -411,13 +594,13 @@ k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
     {
       uint64_t vv[8];
 #pragma unroll
-      for (int a = 0; a < 8; a++) vv[a] = ct[a * 256 + g.tid];
-      digits_mac<ROWS>(acc, cnt, vv, t_conv, bits, W + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
+      for (int a = 0; a < 8; a++) vv[a] = crt_compose(__ldg(ct + a * 256 + g.tid), __ldg(ct + POLY + a * 256 + g.tid), P);
+      digits_mac<ROWS, true>(acc, cnt, vv, t_conv, bits, W + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
     }
     uint32_t y[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) y[a] = barrett64(ct[POLY + a * 256 + g.tid], g.cr1, g.q);
-    ntt_forward_group(g.tid, y, g.smem, g.fwd, g.q, CtaSync());
+    for (int a = 0; a < 8; a++) y[a] = __ldg(ct + (2 + g.n) * POLY + a * 256 + g.tid);   // row 1 mod q_n
+    grp_ntt_fwd<true>(g, y);
     uint32_t prod[ROWS][8];
 #pragma unroll
     for (int m = 0; m < ROWS; m++)
@@ -442,7 +625,7 @@ k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
         uint32_t x[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = prod[0][e];
-        ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+        grp_ntt_inv(g, x);
         crt_lift(x, res, g, P, [&](int z, uint64_t val) { rawbuf[z] = val; });
         __syncthreads();
         uint64_t vv[8];
@@ -453,7 +636,7 @@ k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
 #pragma unroll
           for (int e = 0; e < 8; e++) acc[m][e] = 0;
         cnt = 0;
-        digits_mac<ROWS>(acc, cnt, vv, t_conv, bits, Wshift + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
+        digits_mac<ROWS, true>(acc, cnt, vv, t_conv, bits, Wshift + (size_t)g.n * POLY + g.tid * 8, col_step, row_step, g);
         uint32_t np[ROWS][8];
 #pragma unroll
         for (int m = 0; m < ROWS; m++)
@@ -481,7 +664,7 @@ k_pack(DevParams P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
     uint32_t x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = vint[m][e];
-    ntt_inverse_group(g.tid, x, g.smem, g.inv, g.q, CtaSync());
+    grp_ntt_inv(g, x);
     uint64_t* d = out_raw + (((size_t)inst * ROWS + m) * n + c) * POLY;
     crt_lift(x, res, g, P, [&](int z, uint64_t val) { d[z] = val; });
   }
@@ -541,18 +724,41 @@ __global__ void k_encode(DevParams P, uint64_t* out, size_t out_words, const uin
 }
 
 inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
-const size_t kDynSmemBig = (size_t)(2 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t)2 * POLY * 8;
+const size_t kDynSmemBig = (size_t)(2 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t)2 * POLY * 8 + (size_t)2 * HI_TW * 8;
+const size_t kDynSmemFold = (size_t)(2 * NTT_SMEM_WORDS) * 4 + (size_t)HI_TW * 8;
 
 }  // namespace
 
+void upload_poly_constants(const Twiddle* lo /* [2][2][64] */) {
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo, lo, sizeof(Twiddle) * 2 * 2 * 64));
+}
 void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s) {
-  if (count) ++g_kernel_launches, k_ntt_u64<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+  if (count) ++g_kernel_launches, k_ntt_u64<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, polys, inverse ? 1 : 0);
 }
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s) {
-  if (count) ++g_kernel_launches, k_ntt32<<<(unsigned)count, CTA, 0, s>>>(P, polys, inverse ? 1 : 0);
+  if (count) ++g_kernel_launches, k_ntt32<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, polys, inverse ? 1 : 0);
 }
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s) {
-  if (count) ++g_kernel_launches, k_to_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out, raw);
+  if (count) ++g_kernel_launches, k_to_ntt<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, out, raw);
+}
+void launch_raw_to_res(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t polys, cudaStream_t s) {
+  if (polys) ++g_kernel_launches, k_raw_to_res<<<grid1d(polys * POLY, 256), 256, 0, s>>>(P, out, raw, polys);
+}
+void launch_res_to_raw(const DevParams& P, uint64_t* out, const uint32_t* res, size_t polys, cudaStream_t s) {
+  if (polys) ++g_kernel_launches, k_res_to_raw<<<grid1d(polys * POLY, 256), 256, 0, s>>>(P, out, res, polys);
+}
+void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size_t batch, size_t batch_stride, int half,
+                     const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
+                     cudaStream_t s) {
+  if (batch == 0 || half == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_fold_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
+    attr_set = true;
+  }
+  ++g_kernel_launches;
+  k_fold_res<<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
+                                                                         c_batch_stride, slices_per_query, t_gsw, bits);
 }
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);
@@ -608,7 +814,7 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v,
                                                                      t_conv, bits_conv);
 }
 template <int ROWS>
-static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
                           const uint32_t* v_packing, int instances, int t_conv, int bits_conv, int version,
                           cudaStream_t s) {
   static bool attr_set = false;
@@ -620,7 +826,7 @@ static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint64_t*
   k_pack<ROWS><<<(unsigned)(instances * (ROWS - 1)), CTA, kDynSmemBig, s>>>(P, out_raw, folded, ct_stride, v_packing,
                                                                            t_conv, bits_conv, version);
 }
-void launch_pack(const DevParams& P, uint64_t* out_raw, const uint64_t* folded, size_t ct_stride,
+void launch_pack(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
                  const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
                  cudaStream_t s) {
   switch (n) {

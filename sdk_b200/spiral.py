@@ -199,8 +199,10 @@ def multiply_reg_by_database(params, db, slice_idx, v_firstdim):
     return out
 
 
-def fold_ciphertexts(params, v_cts, v_folding, v_folding_neg):
-    """server.rs:388-427.  v_cts (num x 2 x 2048) is folded in place; result in v_cts[0]."""
+def fold_ciphertexts(params, v_cts, v_folding, v_folding_neg=None):
+    """server.rs:388-427.  v_cts (num x 2 x 2048) is folded in place; result in v_cts[0].
+    v_folding_neg=None means get_v_folding_neg(v_folding) (what process_query passes) and selects the
+    library's fast path."""
     num = v_cts.size // (2 * POLY_LEN)
     check(LIB.b200pir_fold_ciphertexts(params._h, _ptr(v_cts), num, _ptr(v_folding), _ptr(v_folding_neg)))
 

@@ -37,20 +37,20 @@ int main() {
       static uint32_t regs[256][8];
       std::vector<uint32_t> smem(NTT_SMEM_WORDS, 0xDEADBEEF);
       for (int t = 0; t < 256; t++) for (int a = 0; a < 8; a++) regs[t][a] = in[a * 256 + t];
-      for (int t = 0; t < 256; t++) fwd_pass_a(t, regs[t], smem.data(), fwd.data(), q, two_q);
-      for (int t = 0; t < 256; t++) fwd_pass_b(t, regs[t], smem.data(), fwd.data(), q, two_q);
-      for (int t = 0; t < 256; t++) fwd_pass_c(t, regs[t], smem.data(), fwd.data(), q, two_q);
-      for (int t = 0; t < 256; t++) fwd_pass_d(t, regs[t], smem.data(), fwd.data(), q, two_q);
+      for (int t = 0; t < 256; t++) fwd_pass_a(t, regs[t], smem.data(), TwArray{fwd.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) fwd_pass_b(t, regs[t], smem.data(), TwArray{fwd.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) fwd_pass_c(t, regs[t], smem.data(), TwArray{fwd.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) fwd_pass_d(t, regs[t], smem.data(), TwArray{fwd.data()}, q, two_q);
       for (int t = 0; t < 256; t++) for (int k = 0; k < 8; k++)
         if (regs[t][k] != ref[mod * 2048 + t * 8 + k]) { if (bad < 5) printf("fwd mismatch mod %d trial %d at %d\n", mod, trial, t * 8 + k); bad++; }
       // ---- inverse emulation (input: canonical forward output, contiguous layout)
       std::vector<uint64_t> ref2 = ref;
       orc::ntt_inverse(p, ref2.data());
       std::fill(smem.begin(), smem.end(), 0xDEADBEEF);
-      for (int t = 0; t < 256; t++) inv_pass_d(t, regs[t], smem.data(), inv.data(), q, two_q);
-      for (int t = 0; t < 256; t++) inv_pass_c(t, regs[t], smem.data(), inv.data(), q, two_q);
-      for (int t = 0; t < 256; t++) inv_pass_b(t, regs[t], smem.data(), inv.data(), q, two_q);
-      for (int t = 0; t < 256; t++) inv_pass_a(t, regs[t], smem.data(), inv.data(), q, two_q);
+      for (int t = 0; t < 256; t++) inv_pass_d(t, regs[t], smem.data(), TwArray{inv.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) inv_pass_c(t, regs[t], smem.data(), TwArray{inv.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) inv_pass_b(t, regs[t], smem.data(), TwArray{inv.data()}, q, two_q);
+      for (int t = 0; t < 256; t++) inv_pass_a(t, regs[t], smem.data(), TwArray{inv.data()}, q, two_q);
       for (int t = 0; t < 256; t++) for (int a = 0; a < 8; a++)
         if (regs[t][a] != ref2[mod * 2048 + a * 256 + t]) { if (bad < 5) printf("inv mismatch mod %d trial %d at %d\n", mod, trial, a * 256 + t); bad++; }
     }

@@ -192,6 +192,10 @@ def test_fold_and_folding_neg_match_oracle(name):
     S.fold_ciphertexts(G, got, d["v_folding"], d["v_folding_neg"])
     # the reference leaves partially folded values in slots >= 1; every slot must agree
     assert np.array_equal(got, ref)
+    # fast path (v_folding_neg implied, as in process_query): same bytes in every slot
+    fast = inter.copy()
+    S.fold_ciphertexts(G, fast, d["v_folding"])
+    assert np.array_equal(fast, ref)
     # a sub-fold (len 2) uses only v_folding[0]  (server.rs:398-420)
     two = inter[: 2 * 2 * P.N].copy()
     ref2 = P.fold_ciphertexts(two, d["v_folding"], d["v_folding_neg"])
