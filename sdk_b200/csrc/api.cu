@@ -250,19 +250,16 @@ void upload_ntt32(b200pir_ctx* c, DevBuf<uint32_t>& dst, const uint64_t* host, s
 
 // ---- pipeline pieces (all stream-ordered, device pointers)
 
-// server.rs:525-591 for one query.  v: [2^g][4][2048]; writes q_dev and v_fold.
-void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw, uint32_t* v, uint4* q_dev,
-                      uint32_t* v_fold) {
+// server.rs:19-121 over `nq` queries at once (v: [nq][2^g][4][2048], v_stride words apart)
+void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size_t v_stride, int nq) {
   const auto& hp = c->hp;
   cudaStream_t s = c->stream;
-  B200_CUDA(cudaMemsetAsync(v, 0, c->v_words() * 4, s));
-  launch_to_ntt(c->dp, v, query_raw, 2, s);                       // v[0] = query.ct.ntt()
   const int g = c->g;
   const int stop_round = hp.nu_2 > 0 ? c->stop_round : 0;
   const int max_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
   for (int r = 0; r < g; r++) {
     const int num_in = 1 << r;
-    launch_expand_scalar(c->dp, v, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    launch_expand_scalar(c->dp, v, v_stride, nq, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
     ExpandRound R;
     R.r = r; R.num_in = num_in; R.stop_round = stop_round; R.max_bits_to_gen_right = max_right;
     R.t_auto = (POLY >> r) + 1;
@@ -277,12 +274,24 @@ void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw,
     } else {
       R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;   // unwrap_or(v_w_left), server.rs:549
     }
-    launch_expand_round(c->dp, v, R, s);
+    launch_expand_round(c->dp, v, v_stride, nq, R, s);
   }
+}
+
+// server.rs:525-591 for `nq` queries.  v: [nq][2^g][4][2048]; writes q_dev and v_fold of every query.
+void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw, uint32_t* v, uint4* q_dev,
+                      uint32_t* v_fold, int nq) {
+  const auto& hp = c->hp;
+  cudaStream_t s = c->stream;
+  B200_CUDA(cudaMemsetAsync(v, 0, (size_t)nq * c->v_words() * 4, s));
+  for (int qi = 0; qi < nq; qi++)
+    launch_to_ntt(c->dp, v + (size_t)qi * c->v_words(), query_raw + (size_t)qi * 2 * POLY, 2, s);   // v[0] = query.ct.ntt()
+  run_coefficient_expansion(c, pp, v, c->v_words(), nq);
   const int factor = hp.nu_2 > 0 ? 2 : 1;
-  launch_reorient(c->geom(c->num_per), q_dev, v, factor, s);
+  launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
   if (hp.nu_2 > 0)
-    launch_regev_to_gsw(c->dp, v_fold, v, (int)hp.nu_2, 2, 1, pp->conv.p, (int)hp.t_gsw, (int)hp.t_conv, c->bits_conv, s);
+    launch_regev_to_gsw(c->dp, v_fold, c->fold_words(), v, c->v_words(), nq, (int)hp.nu_2, 2, 1, pp->conv.p,
+                        (int)hp.t_gsw, (int)hp.t_conv, c->bits_conv, s);
 }
 
 // fold `num` ciphertexts per batch entry with matrices k = k0, k0-1, ...
@@ -315,11 +324,7 @@ const uint32_t* run_fold_res(b200pir_ctx* c, uint32_t* a, uint32_t* b, size_t ba
 // expansion (or direct upload) for `count` queries already in w_query / w_qdev,w_vfold
 void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
   b200pir_ctx::Scope sc(c, ST_EXPAND);
-  if (c->hp.expand_queries) {
-    for (size_t qi = 0; qi < count; qi++)
-      run_expand_query(c, pp, c->w_query.p + qi * 2 * POLY, c->w_v.p + qi * c->v_words(),
-                       c->w_qdev.p + qi * (size_t)c->dim0 * POLY, c->w_vfold.p + qi * c->fold_words());
-  }
+  if (c->hp.expand_queries) run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p, (int)count);
   // v_folding_neg (server.rs:680) is not materialised: the fold fast path uses G - C_k implicitly.
 }
 
@@ -796,25 +801,7 @@ int b200pir_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint64_t* v) {
   DevBuf<uint32_t> dv(words);
   B200_CUDA(cudaMemcpyAsync(wide.p, v, words * 8, cudaMemcpyHostToDevice, c->stream));
   launch_narrow(dv.p, wide.p, words, c->stream);
-  const int stop_round = hp.nu_2 > 0 ? c->stop_round : 0;
-  for (int r = 0; r < c->g; r++) {
-    const int num_in = 1 << r;
-    launch_expand_scalar(c->dp, dv.p, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, c->stream);
-    ExpandRound R;
-    R.r = r; R.num_in = num_in; R.stop_round = stop_round;
-    R.max_bits_to_gen_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
-    R.t_auto = (POLY >> r) + 1;
-    R.t_left = (int)hp.t_exp_left; R.bits_left = c->bits_left;
-    R.w_left = pp->left.p + (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
-    if (hp.nu_2 > 0 && c->has_right) {
-      int rr = r <= c->stop_round ? r : c->stop_round;
-      R.t_right = (int)hp.t_exp_right; R.bits_right = c->bits_right;
-      R.w_right = pp->right.p + (size_t)rr * 2 * hp.t_exp_right * 2 * POLY;
-    } else {
-      R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;
-    }
-    launch_expand_round(c->dp, dv.p, R, c->stream);
-  }
+  run_coefficient_expansion(c, pp, dv.p, words, 1);
   launch_widen(wide.p, dv.p, words, c->stream);
   B200_CUDA(cudaMemcpyAsync(v, wide.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -831,7 +818,7 @@ int b200pir_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_c
   if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "context was created with expand_queries = 0");
   c->ensure_workspace(1, 1);
   B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_ct, 2 * POLY * 8, cudaMemcpyHostToDevice, c->stream));
-  run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p);
+  run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p, 1);
   // q_dev -> reference layout [z][j][r]
   const size_t qwords = (size_t)c->dim0 * 2 * POLY;
   std::vector<uint32_t> hq(qwords * 2);

@@ -78,20 +78,24 @@ void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_fol
                         cudaStream_t s);
 
 // ---- query expansion (server.rs:19-151, 525-591)
-// v: ntt32 [2^g][2][n][z].  One round = scalar-multiply launch + expand launch.
-void launch_expand_scalar(const DevParams& P, uint32_t* v, int num_in, const uint32_t* neg1_r, cudaStream_t s);
+// v: ntt32 [nq][2^g][2][n][z] (queries v_stride words apart).  One round = scalar-multiply launch + expand
+// launch, each covering all nq queries (grid.y).
+void launch_expand_scalar(const DevParams& P, uint32_t* v, size_t v_stride, int nq, int num_in, const uint32_t* neg1_r,
+                          cudaStream_t s);
 struct ExpandRound {
   int r, num_in, stop_round, max_bits_to_gen_right, t_auto;
   const uint32_t* w_left;   // ntt32 [2][t_exp_left]  for this round (or null when r == 0 / unused)
   const uint32_t* w_right;  // ntt32 [2][t_exp_right]
   int t_left, t_right, bits_left, bits_right;
 };
-void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, cudaStream_t s);
-// util.rs:323-355 reorient: v[idx_factor*j] -> q_dev
-void launch_reorient(const MulGeom& G, uint4* q_dev, const uint32_t* v, int idx_factor, cudaStream_t s);
+void launch_expand_round(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R, cudaStream_t s);
+// util.rs:323-355 reorient: v[idx_factor*j] -> q_dev   (per query: q_stride uint4 apart)
+void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int nq,
+                     int idx_factor, cudaStream_t s);
 // server.rs:123-151: v_gsw[i] (ntt32 [2][2 t_gsw]) from v_inp[idx_factor*(i t_gsw + j) + idx_offset]
-void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v, int count, int idx_factor,
-                         int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv, cudaStream_t s);
+void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride,
+                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* v_conv, int t_gsw,
+                         int t_conv, int bits_conv, cudaStream_t s);
 
 // ---- packing + encoding (server.rs:429-503; lib/server compute/pack.rs)
 // folded: residue-form ciphertexts, ct (inst, t) at folded + (inst*n*n + t)*ct_stride (u32 words);

@@ -44,6 +44,7 @@ struct Grp {
   const Twiddle* fwd;   // global tables
   const Twiddle* inv;
   uint32_t* smem;       // this group's NTT exchange buffer (NTT_SMEM_WORDS)
+  uint32_t* smem2;      // second buffer for paired transforms (null when the kernel has none)
   const Twiddle* fwd_hi_sm;   // shared copy of fwd[64..], or null
 };
 struct CtaSync {
@@ -60,6 +61,7 @@ __device__ __forceinline__ Grp make_grp(const DevParams& P, uint32_t* ntt_smem) 
   g.fwd = g.n ? P.fwd[1] : P.fwd[0];
   g.inv = g.n ? P.inv[1] : P.inv[0];
   g.smem = ntt_smem + g.n * NTT_SMEM_WORDS;
+  g.smem2 = nullptr;
   g.fwd_hi_sm = nullptr;
   return g;
 }
@@ -73,6 +75,7 @@ __device__ __forceinline__ Grp make_grp_single(const DevParams& P, uint32_t* ntt
   g.fwd = n ? P.fwd[1] : P.fwd[0];
   g.inv = n ? P.inv[1] : P.inv[0];
   g.smem = ntt_smem;
+  g.smem2 = nullptr;
   g.fwd_hi_sm = nullptr;
   return g;
 }
@@ -124,7 +127,36 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
                                            int bits, const uint32_t* c0, size_t col_step, size_t row_step,
                                            const Grp& g) {
   const uint64_t mask = (1ull << bits) - 1;
-  for (int k = 0; k < ndig; k++) {
+  int k = 0;
+  if (SM) {
+    // two digit polynomials per trip: twice the instruction-level parallelism, half the barriers
+    // (kernels that stage twiddles also provide the second exchange buffer g.smem2)
+#pragma unroll 1
+    for (; k + 1 < ndig; k += 2) {
+      uint32_t x0[8], x1[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        x0[a] = gadget_digit(v[a], k, bits, mask);
+        x1[a] = gadget_digit(v[a], k + 1, bits, mask);
+      }
+      ntt_forward_group2(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+      const uint32_t* c = c0 + (size_t)k * col_step;
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        uint32_t cv[8];
+        ld8_ro(cv, c + (size_t)r * row_step);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
+        ld8_ro(cv, c + col_step + (size_t)r * row_step);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
+      }
+      cnt += 2;
+      if (cnt >= 200) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+    }
+  }
+#pragma unroll 1
+  for (; k < ndig; k++) {
     uint32_t x[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) x[a] = gadget_digit(v[a], k, bits, mask);
@@ -417,7 +449,8 @@ __global__ void k_folding_neg(DevParams P, uint32_t* out, const uint32_t* vf, si
 
 // ------------------------------------------------------------------ query expansion
 // server.rs:105-110: v[num_in + i] = v[i] (.) neg1
-__global__ void k_expand_scalar(DevParams P, uint32_t* v, int num_in, const uint32_t* neg1) {
+__global__ void k_expand_scalar(DevParams P, uint32_t* v, size_t v_stride, int num_in, const uint32_t* neg1) {
+  v += (size_t)blockIdx.y * v_stride;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // over num_in * 2 rows * 2 mod * 2048
   size_t total = (size_t)num_in * 4 * POLY;
   if (idx >= total) return;
@@ -428,13 +461,15 @@ __global__ void k_expand_scalar(DevParams P, uint32_t* v, int num_in, const uint
 }
 
 // server.rs:39-103 action_expand for ciphertext index blockIdx.x of round R.r (in place on v).
-__global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* v, ExpandRound R) {
+__global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* v, size_t v_stride, ExpandRound R) {
+  v += (size_t)blockIdx.y * v_stride;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
-  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint32_t* res = ntt_smem + 4 * NTT_SMEM_WORDS;
   uint64_t* autom = reinterpret_cast<uint64_t*>(res + 2 * POLY);      // [2][2048]
   Twiddle* tw = reinterpret_cast<Twiddle*>(autom + 2 * POLY);         // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
+  g.smem2 = ntt_smem + (2 + g.n) * NTT_SMEM_WORDS;
 
   const int i = blockIdx.x;
   const int ih = i < R.num_in ? i : i - R.num_in;       // index within its half (server.rs:112-119)
@@ -498,7 +533,9 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
 }
 
 // util.rs:323-355
-__global__ void k_reorient(MulGeom G, uint4* q_dev, const uint32_t* v, int idx_factor) {
+__global__ void k_reorient(MulGeom G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int idx_factor) {
+  q_dev += (size_t)blockIdx.y * q_stride;
+  v += (size_t)blockIdx.y * v_stride;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // over dim0 * 2048
   if (idx >= (size_t)G.dim0 * POLY) return;
   int z = (int)(idx % POLY), j = (int)(idx / POLY);
@@ -509,14 +546,17 @@ __global__ void k_reorient(MulGeom G, uint4* q_dev, const uint32_t* v, int idx_f
 
 // server.rs:134-150.  CTA = (gsw index i, digit j).
 __global__ void __launch_bounds__(CTA, 1)
-k_regev_to_gsw(DevParams P, uint32_t* v_gsw, const uint32_t* v, int idx_factor, int idx_offset, const uint32_t* v_conv,
-               int t_gsw, int t_conv, int bits_conv) {
+k_regev_to_gsw(DevParams P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride, int idx_factor,
+               int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv) {
+  v_gsw += (size_t)blockIdx.y * gsw_stride;
+  v += (size_t)blockIdx.y * v_stride;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
-  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint32_t* res = ntt_smem + 4 * NTT_SMEM_WORDS;
   uint64_t* raw = reinterpret_cast<uint64_t*>(res + 2 * POLY);        // [2][2048]
   Twiddle* tw = reinterpret_cast<Twiddle*>(raw + 2 * POLY);           // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
+  g.smem2 = ntt_smem + (2 + g.n) * NTT_SMEM_WORDS;
   stage_fwd_twiddles(g, tw + g.n * HI_TW);
   const int i = blockIdx.x / t_gsw, j = blockIdx.x % t_gsw;
   const int idx_inp = idx_factor * (i * t_gsw + j) + idx_offset;
@@ -564,10 +604,11 @@ k_pack(DevParams P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
        int bits, int version) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
-  uint32_t* res = ntt_smem + 2 * NTT_SMEM_WORDS;
+  uint32_t* res = ntt_smem + 4 * NTT_SMEM_WORDS;
   uint64_t* rawbuf = reinterpret_cast<uint64_t*>(res + 2 * POLY);     // [2048] (+ [2048] unused)
   Twiddle* tw = reinterpret_cast<Twiddle*>(rawbuf + 2 * POLY);        // [2][HI_TW]
   Grp g = make_grp(P, ntt_smem);
+  g.smem2 = ntt_smem + (2 + g.n) * NTT_SMEM_WORDS;
   stage_fwd_twiddles(g, tw + g.n * HI_TW);
   constexpr int n = ROWS - 1;
   const int inst = blockIdx.x / n, c = blockIdx.x % n;
@@ -724,7 +765,7 @@ __global__ void k_encode(DevParams P, uint64_t* out, size_t out_words, const uin
 }
 
 inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
-const size_t kDynSmemBig = (size_t)(2 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t)2 * POLY * 8 + (size_t)2 * HI_TW * 8;
+const size_t kDynSmemBig = (size_t)(4 * NTT_SMEM_WORDS + 2 * POLY) * 4 + (size_t)2 * POLY * 8 + (size_t)2 * HI_TW * 8;
 const size_t kDynSmemFold = (size_t)(2 * NTT_SMEM_WORDS) * 4 + (size_t)HI_TW * 8;
 
 }  // namespace
@@ -782,27 +823,30 @@ void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_fol
   size_t total = (size_t)count * 2 * 2 * t_gsw * 2 * POLY;
   if (total) ++g_kernel_launches, k_folding_neg<<<grid1d(total, 256), 256, 0, s>>>(P, out, v_folding, total, t_gsw, bits);
 }
-void launch_expand_scalar(const DevParams& P, uint32_t* v, int num_in, const uint32_t* neg1_r, cudaStream_t s) {
+void launch_expand_scalar(const DevParams& P, uint32_t* v, size_t v_stride, int nq, int num_in, const uint32_t* neg1_r,
+                          cudaStream_t s) {
   size_t total = (size_t)num_in * 4 * POLY;
   ++g_kernel_launches;
-  k_expand_scalar<<<grid1d(total, 256), 256, 0, s>>>(P, v, num_in, neg1_r);
+  k_expand_scalar<<<dim3(grid1d(total, 256), nq), 256, 0, s>>>(P, v, v_stride, num_in, neg1_r);
 }
-void launch_expand_round(const DevParams& P, uint32_t* v, const ExpandRound& R, cudaStream_t s) {
+void launch_expand_round(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
     attr_set = true;
   }
   ++g_kernel_launches;
-  k_expand_round<<<(unsigned)(2 * R.num_in), CTA, kDynSmemBig, s>>>(P, v, R);
+  k_expand_round<<<dim3((unsigned)(2 * R.num_in), nq), CTA, kDynSmemBig, s>>>(P, v, v_stride, R);
 }
-void launch_reorient(const MulGeom& G, uint4* q_dev, const uint32_t* v, int idx_factor, cudaStream_t s) {
+void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int nq,
+                     int idx_factor, cudaStream_t s) {
   size_t total = (size_t)G.dim0 * POLY;
   ++g_kernel_launches;
-  k_reorient<<<grid1d(total, 256), 256, 0, s>>>(G, q_dev, v, idx_factor);
+  k_reorient<<<dim3(grid1d(total, 256), nq), 256, 0, s>>>(G, q_dev, q_stride, v, v_stride, idx_factor);
 }
-void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v, int count, int idx_factor,
-                         int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv, cudaStream_t s) {
+void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride,
+                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* v_conv, int t_gsw,
+                         int t_conv, int bits_conv, cudaStream_t s) {
   if (count == 0) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -810,8 +854,9 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, const uint32_t* v,
     attr_set = true;
   }
   ++g_kernel_launches;
-  k_regev_to_gsw<<<(unsigned)(count * t_gsw), CTA, kDynSmemBig, s>>>(P, v_gsw, v, idx_factor, idx_offset, v_conv, t_gsw,
-                                                                     t_conv, bits_conv);
+  k_regev_to_gsw<<<dim3((unsigned)(count * t_gsw), nq), CTA, kDynSmemBig, s>>>(P, v_gsw, gsw_stride, v, v_stride,
+                                                                               idx_factor, idx_offset, v_conv, t_gsw,
+                                                                               t_conv, bits_conv);
 }
 template <int ROWS>
 static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
