@@ -303,3 +303,51 @@ def test_dpir_matvec_matches_oracle(rows, cols):
     m = D.PackedMatrix(a, rows, cols)
     assert np.array_equal(D.matrix_mul_vec_packed(m, b), O.dpir_matvec_packed(a, b, rows, cols))
     m.close()
+
+
+# ------------------------------------------------------------------ C++ host mirror (include/b200pir.hpp)
+def test_cpp_host_mirror_matches_python_path(tmp_path):
+    import os
+    import subprocess
+    S = _gpu()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_smoke")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O2", "-o", exe,
+                           os.path.join(root, "tests", "cpp", "host_mirror_smoke.cpp"), "-L" + os.path.join(root, "sdk_b200"),
+                           "-lb200pir", "-Wl,-rpath," + os.path.join(root, "sdk_b200")])
+    size, h_cpp = subprocess.check_output([exe], text=True).split()
+    # same xorshift64 stream on the Python side
+    state = [88172645463325252]
+    M = (1 << 64) - 1
+
+    def nxt():
+        s = state[0]
+        s ^= (s << 13) & M
+        s ^= s >> 7
+        s ^= (s << 17) & M
+        state[0] = s
+        return s
+
+    def ntt_mat(polys):
+        v = np.empty(polys * 4096, dtype=np.uint64)
+        for i in range(polys):
+            v[i * 4096:i * 4096 + 2048] = [nxt() % Q0 for _ in range(2048)]
+            v[i * 4096 + 2048:(i + 1) * 4096] = [nxt() % Q1 for _ in range(2048)]
+        return v
+
+    kw = dict(O.PARAM_SETS["T"])
+    G = S.Params(**kw)
+    pack, left, right, conv = ntt_mat(2 * 3 * 4), ntt_mat(7 * 2 * 8), ntt_mat(5 * 2 * 8), ntt_mat(2 * 8)
+    gpp = S.PublicParameters(G, pack, left, right, conv)
+    gdb = S.Database(G)
+    gdb.fill_synthetic(SEED_DB)
+    ct = np.array([nxt() % (Q0 * Q1) for _ in range(4096)], dtype=np.uint64)
+    resp = S.process_query(G, gpp, S.Query(ct=ct), gdb)
+    h = 1469598103934665603
+    for b in resp.tobytes():
+        h = ((h ^ b) * 1099511628211) & M
+    assert int(size) == resp.size and int(h_cpp) == h
+    # and the oracle agrees on the same synthetic inputs
+    P = O.Params(**kw)
+    ref = P.process_query(dict(pack=pack, left=left, right=right, conv=conv), dict(ct=ct), P.generate_db(SEED_DB))
+    assert np.array_equal(resp, ref)
