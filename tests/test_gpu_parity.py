@@ -351,3 +351,46 @@ def test_cpp_host_mirror_matches_python_path(tmp_path):
     P = O.Params(**kw)
     ref = P.process_query(dict(pack=pack, left=left, right=right, conv=conv), dict(ct=ct), P.generate_db(SEED_DB))
     assert np.array_equal(resp, ref)
+
+
+# ------------------------------------------------------------------ multi-GPU composition, emulated on one GPU
+@pytest.mark.parametrize("name,world", [("T0", 2), ("T0", 4), ("T", 4), ("T1", 2)])
+def test_sharded_stages_equal_single_gpu(name, world):
+    """stage A on every row shard (ii = s mod G) + concatenation (what the NCCL all-gather produces) + stage B
+    == single-GPU process_query == oracle, byte for byte."""
+    import ctypes as C
+    import torch
+    from sdk_b200._lib import LIB, check
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    idxs = [5, P.dim0 * P.num_per - 3]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    count = len(idxs)
+    d_q = torch.from_numpy(qs.view(np.int64)).cuda()
+    ct_words = 4 * P.N                                    # residue-form ciphertext, u32 words
+    gathered = torch.zeros(world * count * P.slices * ct_words, dtype=torch.int32, device="cuda")
+    slice_words = P.dim0 * P.num_per * P.N
+    shards = []
+    for s in range(world):
+        sh = S.Database(G, shard_index=s, shard_count=world)
+        for sl in range(P.slices):
+            sh.upload_slice(sl, db[sl * slice_words:(sl + 1) * slice_words])
+        shards.append(sh)
+        part = gathered[s * count * P.slices * ct_words:(s + 1) * count * P.slices * ct_words]
+        check(LIB.b200pir_query_stage_a_dev(G._h, sh._h, gpp._h, d_q.data_ptr(), count, part.data_ptr()))
+    out = torch.zeros(count * G.response_bytes, dtype=torch.uint8, device="cuda")
+    check(LIB.b200pir_query_stage_b_dev(G._h, gpp._h, gathered.data_ptr(), world, count, out.data_ptr()))
+    G.synchronize()
+    got = out.cpu().numpy().reshape(count, G.response_bytes)
+    for k, i in enumerate(idxs):
+        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
+        assert np.array_equal(got[k], ref), (name, world, k)
+        assert np.array_equal(cl.decode_response(got[k]), P.db_plain_item(SEED_DB, i))
+    # the synthetic generator honours the shard mapping too
+    sh2 = S.Database(G, shard_index=world - 1, shard_count=world)
+    sh2.fill_synthetic(SEED_DB)
+    rng = np.random.default_rng(8)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    assert np.array_equal(S.multiply_reg_by_database(G, sh2, 0, v), S.multiply_reg_by_database(G, shards[-1], 0, v))
+    for sh in shards + [sh2]:
+        sh.close()
