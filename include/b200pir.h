@@ -87,6 +87,8 @@ void b200pir_pp_destroy(b200pir_pp* pp);
 /* ntt.rs:67-113 ntt_forward / :212-258 ntt_inverse over `count` polys of [2][2048] u64, in place. */
 int b200pir_ntt_forward(b200pir_ctx* ctx, uint64_t* polys, size_t count);
 int b200pir_ntt_inverse(b200pir_ctx* ctx, uint64_t* polys, size_t count);
+/* Device-resident batch (BASELINE config #5): `count` polys of u32 [2][2048] residues, in place, stream-ordered. */
+int b200pir_ntt32_dev(b200pir_ctx* ctx, uint32_t* polys_dev, size_t count, int inverse);
 /* poly.rs:613-623 to_ntt / :646-663 from_ntt over `count` polys. */
 int b200pir_to_ntt(b200pir_ctx* ctx, uint64_t* out_ntt, const uint64_t* raw, size_t count);
 int b200pir_from_ntt(b200pir_ctx* ctx, uint64_t* out_raw, const uint64_t* ntt, size_t count);

@@ -677,6 +677,15 @@ static int ntt_host(b200pir_ctx* c, uint64_t* polys, size_t count, bool inverse)
 int b200pir_ntt_forward(b200pir_ctx* c, uint64_t* polys, size_t count) { return ntt_host(c, polys, count, false); }
 int b200pir_ntt_inverse(b200pir_ctx* c, uint64_t* polys, size_t count) { return ntt_host(c, polys, count, true); }
 
+int b200pir_ntt32_dev(b200pir_ctx* c, uint32_t* polys_dev, size_t count, int inverse) {
+  API_BEGIN
+  if (!c || !polys_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  launch_ntt32(c->dp, polys_dev, count, inverse != 0, c->stream);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
 int b200pir_to_ntt(b200pir_ctx* c, uint64_t* out_ntt, const uint64_t* raw, size_t count) {
   API_BEGIN
   if (!c || !out_ntt || !raw) throw Error(B200PIR_E_BADARG, "null argument");

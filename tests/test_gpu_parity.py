@@ -394,3 +394,37 @@ def test_sharded_stages_equal_single_gpu(name, world):
     assert np.array_equal(S.multiply_reg_by_database(G, sh2, 0, v), S.multiply_reg_by_database(G, shards[-1], 0, v))
     for sh in shards + [sh2]:
         sh.close()
+
+
+# ------------------------------------------------------------------ BASELINE configs[0]: the e2e parameter files, full size
+@pytest.mark.parametrize("name", ["E1", "E0"])
+def test_e2e_params_full_size_bytes_and_decode(name):
+    """e2e-tests/params/v1.json / v0.json with every one of the 2^14 rows populated (4 GiB packed database):
+    first-dimension words, folded ciphertexts and response bytes equal the oracle's; the decoded item equals the
+    planted one (SURVEY 8d, config #1)."""
+    S = _gpu()
+    P = O.Params.named(name)
+    cl = O.Client(P, 2024)
+    pp = cl.generate_keys()
+    db = P.generate_db(SEED_DB)
+    G = S.Params(**P.kw)
+    gdb = S.Database.from_words(G, db)
+    gpp = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
+    idx = 12345
+    q = cl.generate_query(idx)
+    ref, d = P.process_query(pp, q, db, dump=True)
+    got = S.process_query(G, gpp, S.Query(ct=q["ct"]), gdb)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(cl.decode_response(got), P.db_plain_item(SEED_DB, idx))
+    slice_words = P.dim0 * P.num_per * P.N
+    assert np.array_equal(S.multiply_reg_by_database(G, gdb, 0, d["v_firstdim"]), d["first_mult"])
+    inter = P.from_ntt(d["first_mult"])
+    S.fold_ciphertexts(G, inter, d["v_folding"])
+    assert np.array_equal(inter[: 2 * P.N], d["folded"][: 2 * P.N])
+    # the GPU-side generator builds the same 4 GiB database
+    g2 = S.Database(G)
+    g2.fill_synthetic(SEED_DB)
+    assert np.array_equal(S.multiply_reg_by_database(G, g2, P.slices - 1, d["v_firstdim"]),
+                          P.multiply_reg_by_database(db[(P.slices - 1) * slice_words:], d["v_firstdim"]))
+    for h in (g2, gdb, gpp, G):
+        h.close()
