@@ -127,6 +127,8 @@ struct b200pir_ctx {
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 4, profile = 0;
+  int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
+  DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
   size_t ws_queries = 0, ws_rows = 0;
   DevBuf<uint64_t> w_query;      // [Q][2][2048] raw
@@ -204,7 +206,11 @@ struct b200pir_db {
   b200pir_ctx* ctx;
   Shard shard;
   int rows;                 // local second-dimension rows
+  int format = 0;           // 0: d (IMAD layout)  1: f (INT8 MMA fragment order)
   DevBuf<uint4> d;          // [slice][row][dim0/2][2048]
+  DevBuf<uint4> f;          // [slice][n][z][mt][ks][limb][lane]
+  ImmaGeom F;
+  size_t slice_cells() const { return (size_t)rows * (ctx->dim0 / 2) * POLY; }
 };
 
 struct b200pir_pp {
@@ -334,23 +340,42 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
   MulGeom G = c->geom(rows);
   const size_t q_stride = (size_t)c->dim0 * POLY;
   const size_t out_stride = (size_t)c->slices * rows * 4 * POLY;
-  {
-    b200pir_ctx::Scope sc(c, ST_MUL);
-    size_t qi = 0;
-    while (qi < count) {
-      int nq = 1;
-      if (count - qi >= 4 && c->max_group >= 4) nq = 4;
-      else if (count - qi >= 2 && c->max_group >= 2) nq = 2;
-      launch_multiply(c->dp, G, db->d.p, c->w_qdev.p + qi * q_stride, c->w_mult.p + qi * out_stride, 0, c->slices, nq,
-                      q_stride, out_stride, c->mul_variant, c->stream);
-      c->mul_launches++;
-      qi += nq;
+  if (db->format == 0) {
+    {
+      b200pir_ctx::Scope sc(c, ST_MUL);
+      size_t qi = 0;
+      while (qi < count) {
+        int nq = 1;
+        if (count - qi >= 4 && c->max_group >= 4) nq = 4;
+        else if (count - qi >= 2 && c->max_group >= 2) nq = 2;
+        launch_multiply(c->dp, G, db->d.p, c->w_qdev.p + qi * q_stride, c->w_mult.p + qi * out_stride, 0, c->slices, nq,
+                        q_stride, out_stride, c->mul_variant, c->stream);
+        c->mul_launches++;
+        qi += nq;
+      }
     }
-  }
-  {
-    // server.rs:707-709 from_ntt, minus the CRT lift: inverse NTT of every CRT half in place -> residue form
-    b200pir_ctx::Scope sc(c, ST_FROMNTT);
-    launch_ntt32(c->dp, c->w_mult.p, count * c->slices * rows * 2, true, c->stream);
+    {
+      // server.rs:707-709 from_ntt, minus the CRT lift: inverse NTT of every CRT half in place -> residue form
+      b200pir_ctx::Scope sc(c, ST_FROMNTT);
+      launch_ntt32(c->dp, c->w_mult.p, count * c->slices * rows * 2, true, c->stream);
+    }
+  } else {
+    // INT8 tensor-core path: z-major product in w_cts (free until the fold starts), then inverse NTT into w_mult
+    c->w_qf.ensure(imma_query_cells(db->F));
+    for (size_t qi = 0; qi < count; qi += 4) {
+      const int nq = (int)std::min<size_t>(4, count - qi);
+      {
+        b200pir_ctx::Scope sc(c, ST_MUL);
+        launch_query_to_frag(db->F, c->w_qdev.p + qi * q_stride, q_stride, nq, c->w_qf.p, c->stream);
+        launch_multiply_imma(c->dp, db->F, db->f.p, c->w_qf.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
+                             c->stream);
+        c->mul_launches++;
+      }
+    }
+    {
+      b200pir_ctx::Scope sc(c, ST_FROMNTT);
+      launch_intt_from_zmajor(c->dp, db->F, c->w_cts.p, out_stride, c->w_mult.p, (int)count, c->slices, c->stream);
+    }
   }
   {
     b200pir_ctx::Scope sc(c, ST_FOLD);
@@ -466,6 +491,7 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
                                    lo[(1 * 2 + 0) * 64 + i] = f1[i]; lo[(1 * 2 + 1) * 64 + i] = i1[i]; }
     upload_poly_constants(lo.data());
     upload_mul_constants(lo.data());
+    upload_imma_constants(lo.data());
   }
   DevParams& dp = c->dp;
   dp.q[0] = (uint32_t)q0; dp.q[1] = (uint32_t)q1m;
@@ -526,6 +552,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   std::string k(key);
   if (k == "mul_variant") c->mul_variant = (int)value;
   else if (k == "batch") { if (value != 1 && value != 2 && value != 4) throw Error(B200PIR_E_BADARG, "batch must be 1, 2 or 4"); c->max_group = (int)value; }
+  else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
     c->profile = (int)value;
@@ -555,9 +582,17 @@ int b200pir_db_create(b200pir_ctx* c, uint64_t shard_index, uint64_t shard_count
   db->ctx = c;
   db->shard = Shard{(int)shard_index, (int)shard_count};
   db->rows = c->num_per / (int)shard_count;
-  size_t cells = (size_t)c->slices * db->rows * (c->dim0 / 2) * POLY;
-  db->d.alloc(cells);
-  B200_CUDA(cudaMemsetAsync(db->d.p, 0, cells * sizeof(uint4), c->stream));
+  db->format = c->db_format;
+  db->F = make_imma_geom(c->dim0, db->rows);
+  if (db->format == 0) {
+    size_t cells = (size_t)c->slices * db->slice_cells();
+    db->d.alloc(cells);
+    B200_CUDA(cudaMemsetAsync(db->d.p, 0, cells * sizeof(uint4), c->stream));
+  } else {
+    size_t cells = imma_db_cells(db->F, c->slices);
+    db->f.alloc(cells);
+    B200_CUDA(cudaMemsetAsync(db->f.p, 0, cells * sizeof(uint4), c->stream));
+  }
   B200_CUDA(cudaStreamSynchronize(c->stream));
   *out = db.release();
   API_END
@@ -580,11 +615,18 @@ int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, cons
   int zc = (int)std::max<size_t>(1, std::min<size_t>(POLY, ((size_t)64 << 20) / (per_z * 8)));
   DevBuf<uint64_t> stage(per_z * zc);
   MulGeom G = c->geom(db->rows);
-  uint4* dst = db->d.p + (size_t)slice * db->rows * (c->dim0 / 2) * POLY;
+  DevBuf<uint4> tmp;
+  uint4* dst;
+  if (db->format == 0) dst = db->d.p + (size_t)slice * db->slice_cells();
+  else { tmp.alloc(db->slice_cells()); dst = tmp.p; }
   for (int z0 = 0; z0 < POLY; z0 += zc) {
     int cur = std::min(zc, POLY - z0);
     B200_CUDA(cudaMemcpyAsync(stage.p, words + (size_t)z0 * per_z, per_z * cur * 8, cudaMemcpyHostToDevice, c->stream));
     launch_db_retile_chunk(G, db->shard, dst, stage.p, z0, cur, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (db->format == 1) {
+    launch_db_to_frag(db->F, tmp.p, db->f.p, (int)slice, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
   }
   B200_CUDA(cudaGetLastError());
@@ -610,7 +652,8 @@ int b200pir_db_upsert_item(b200pir_ctx* c, b200pir_db* db, uint64_t slice, uint6
   if (ii % db->shard.count != db->shard.index) return 0;           // row lives on another GPU
   DevBuf<uint64_t> tmp(POLY);
   B200_CUDA(cudaMemcpyAsync(tmp.p, poly, POLY * 8, cudaMemcpyHostToDevice, c->stream));
-  launch_db_upsert(c->geom(db->rows), db->d.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
+  if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
+  else launch_db_upsert_frag(db->F, db->f.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
   // the host RwLock gives upserts exclusive access (bin/server.rs:35,49): finish before returning
   B200_CUDA(cudaStreamSynchronize(c->stream));
   API_END
@@ -624,8 +667,17 @@ int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
   // keep each launch's grid below 2^31 CTAs
   size_t per_slice = (size_t)db->rows * (c->dim0 / 2);
   int step = (int)std::max<size_t>(1, std::min<size_t>(c->slices, ((size_t)1 << 30) / per_slice));
-  for (int s0 = 0; s0 < c->slices; s0 += step)
-    launch_db_synth(c->dp, G, db->shard, db->d.p, seed, c->hp.p, s0, std::min(step, c->slices - s0), c->stream);
+  if (db->format == 0) {
+    for (int s0 = 0; s0 < c->slices; s0 += step)
+      launch_db_synth(c->dp, G, db->shard, db->d.p, seed, c->hp.p, s0, std::min(step, c->slices - s0), c->stream);
+  } else {
+    // build each slice in the IMAD layout in a scratch buffer, then re-tile it into fragment order
+    DevBuf<uint4> tmp(db->slice_cells());
+    for (int s0 = 0; s0 < c->slices; s0++) {
+      launch_db_synth(c->dp, G, db->shard, tmp.p - (size_t)s0 * db->slice_cells(), seed, c->hp.p, s0, 1, c->stream);
+      launch_db_to_frag(db->F, tmp.p, db->f.p, s0, c->stream);
+    }
+  }
   B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
   API_END
@@ -730,7 +782,16 @@ int b200pir_multiply_reg_by_database(b200pir_ctx* c, b200pir_db* db, uint64_t sl
   DevBuf<uint64_t> wide((size_t)rows * 4 * POLY);
   B200_CUDA(cudaMemcpyAsync(vq.p, v_firstdim, vq.n * 8, cudaMemcpyHostToDevice, c->stream));
   launch_query_to_dev(G, qd.p, vq.p, c->stream);
-  launch_multiply(c->dp, G, db->d.p, qd.p, o.p, (int)slice, 1, 1, 0, 0, c->mul_variant, c->stream);
+  if (db->format == 0) {
+    launch_multiply(c->dp, G, db->d.p, qd.p, o.p, (int)slice, 1, 1, 0, 0, c->mul_variant, c->stream);
+  } else {
+    DevBuf<uint2> qf(imma_query_cells(db->F));
+    DevBuf<uint32_t> zm((size_t)c->slices * rows * 4 * POLY);
+    launch_query_to_frag(db->F, qd.p, 0, 1, qf.p, c->stream);
+    launch_multiply_imma(c->dp, db->F, db->f.p, qf.p, zm.p, 0, 1, (int)slice, 1, c->stream);
+    launch_zmajor_to_ntt32(db->F, zm.p, o.p + (size_t)slice * rows * 4 * POLY, (int)slice, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+  }
   launch_widen(wide.p, o.p + (size_t)slice * rows * 4 * POLY, wide.n, c->stream);
   B200_CUDA(cudaMemcpyAsync(out, wide.p, wide.n * 8, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -1032,10 +1093,10 @@ int b200pir_last_stage_ms(b200pir_ctx* c, double* out8) {
 
 // ---------------------------------------------------------------- DoublePIR
 namespace {
-__global__ void k_dpir_synth(uint32_t* a, size_t words, uint64_t seed) {
+__global__ void k_dpir_synth(uint32_t* a, size_t words, uint64_t seed, size_t index0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= words) return;
-  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+  uint64_t z = seed + (index0 + i + 1) * 0x9E3779B97F4A7C15ULL;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   z ^= z >> 31;
@@ -1074,7 +1135,7 @@ int b200pir_dpir_create_synthetic(int device, uint64_t rows, uint64_t cols, uint
   const size_t chunk = (size_t)1 << 30;
   for (size_t off = 0; off < words; off += chunk) {
     size_t cur = std::min(chunk, words - off);
-    k_dpir_synth<<<(unsigned)((cur + 255) / 256), 256, 0, m->stream>>>(m->a.p + off, cur, seed + off);
+    k_dpir_synth<<<(unsigned)((cur + 255) / 256), 256, 0, m->stream>>>(m->a.p + off, cur, seed, off);
   }
   cudaError_t e = cudaStreamSynchronize(m->stream);
   if (e != cudaSuccess) { b200pir_dpir_destroy(m); throw Error(B200PIR_E_CUDA, cudaGetErrorString(e)); }

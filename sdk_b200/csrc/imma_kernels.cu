@@ -1,0 +1,308 @@
+// First dimension on the INT8 tensor-core path (batched queries).
+//
+// multiply_reg_by_database (lib/spiral-rs/src/server.rs:155-221) is, for every NTT coordinate z and CRT
+// modulus n, a small integer GEMM  C[ii][(query,row)] = sum_j A[ii][j] * B[j][(query,row)]  mod q_n  with
+// M = num_per, K = dim0, N = 2 * (number of queries).  With one query the database stream (8 B per word) is the
+// bound and the IMAD kernel in mul_kernels.cu already runs at the HBM roofline; with several queries per
+// database pass the 32x32->64-bit IMADs become the bound.  Here the 28-bit residues are split into four 7-bit
+// limbs and the products are formed by u8 x u8 -> s32 tensor-core MMAs (mma.sync m16n8k32, SASS IMMA.16832.U8.U8):
+//
+//     a * b = sum_{l,m < 4} a_l b_m 2^{7(l+m)}          a_l, b_m < 2^7
+//
+// Every limb product is < 2^14, a K = dim0 <= 1024 accumulation < 2^24, and the (at most 4) limb pairs with the
+// same shift l+m share one s32 accumulator (< 2^26): all integer arithmetic is EXACT.  The seven shift groups
+// are recombined as  sum_s acc_s * (2^{7s} mod q_n)  (< 2^57) and reduced with one Barrett step, which yields the
+// same canonical residue as the reference's u128 accumulate + `%`.  Parity is asserted bit-for-bit against the
+// oracle in tests/test_gpu_parity.py before this path is used by anything.
+//
+// The database is re-tiled once into MMA *fragment order*, so a lane's A operand is one coalesced 16-byte load
+// straight from HBM (no shared memory, no ldmatrix):
+//     dbF[slice][n][z][mt][ks][limb l][lane] = uint4{a0,a1,a2,a3}     (mt: 16 rows, ks: 32 values of j)
+// One CTA = one (slice, n, z): its 8 warps share the query operand B (<= 32 KiB, shared memory) and each streams
+// the fragments of two row tiles.
+#include "kernels.h"
+
+namespace b200pir {
+
+namespace {
+
+__device__ __forceinline__ void mma_u8(int (&c)[4], const uint4& a, const uint2& b) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ uint32_t limb4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, int l) {
+  const int sh = 7 * l;
+  return ((x0 >> sh) & 127u) | (((x1 >> sh) & 127u) << 8) | (((x2 >> sh) & 127u) << 16) | (((x3 >> sh) & 127u) << 24);
+}
+
+// format 0 (mul_kernels.cu: uint4 [row][jp][z]) of one slice  ->  fragment order.  One warp per (z, mt, ks).
+__global__ void __launch_bounds__(256)
+k_db_to_frag(ImmaGeom F, const uint4* __restrict__ db0_slice, uint4* __restrict__ dbf, int slice) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t total = (size_t)POLY * F.mt * F.ks;
+  if (warp >= total) return;
+  const int ks = (int)(warp % F.ks);
+  const int mt = (int)((warp / F.ks) % F.mt);
+  const int z = (int)(warp / ((size_t)F.ks * F.mt));
+  const int g = lane >> 2, t = lane & 3;
+  const int half = F.dim0 >> 1;
+  uint32_t res[2][2][2][4];        // [n][row half (g, g+8)][k half (0, +16)][i]
+#pragma unroll
+  for (int rh = 0; rh < 2; rh++) {
+    const int ii = mt * 16 + g + 8 * rh;
+#pragma unroll
+    for (int kh = 0; kh < 2; kh++) {
+      const int j0 = ks * 32 + 16 * kh + 4 * t;       // j0 .. j0+3
+#pragma unroll
+      for (int p = 0; p < 2; p++) {                   // two uint4 cells: (j0, j0+1), (j0+2, j0+3)
+        const int jp = (j0 >> 1) + p;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (ii < F.rows && jp < half) w = db0_slice[((size_t)ii * half + jp) * POLY + z];
+        res[0][rh][kh][2 * p] = w.x; res[1][rh][kh][2 * p] = w.y;
+        res[0][rh][kh][2 * p + 1] = w.z; res[1][rh][kh][2 * p + 1] = w.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    uint4* dst = dbf + (((((size_t)slice * 2 + n) * POLY + z) * F.mt + mt) * F.ks + ks) * 4 * 32 + lane;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      uint4 o;
+      o.x = limb4(res[n][0][0][0], res[n][0][0][1], res[n][0][0][2], res[n][0][0][3], l);   // a0: row g,   k 4t..
+      o.y = limb4(res[n][1][0][0], res[n][1][0][1], res[n][1][0][2], res[n][1][0][3], l);   // a1: row g+8
+      o.z = limb4(res[n][0][1][0], res[n][0][1][1], res[n][0][1][2], res[n][0][1][3], l);   // a2: row g,   k 16+4t..
+      o.w = limb4(res[n][1][1][0], res[n][1][1][1], res[n][1][1][2], res[n][1][1][3], l);   // a3: row g+8
+      dst[(size_t)l * 32] = o;
+    }
+  }
+}
+
+// one item polynomial (2048 packed words lo|hi<<32) into the fragment-order database (byte writes)
+__global__ void k_db_upsert_frag(ImmaGeom F, uint4* dbf, int slice, int il, int j, const uint64_t* poly) {
+  int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= POLY) return;
+  const int mt = il >> 4, row = il & 15, ks = j >> 5, k = j & 31;
+  const int g = row & 7, rh = row >> 3, kh = k >> 4, t = (k & 15) >> 2, i = k & 3;
+  const int lane = g * 4 + t, reg = rh + 2 * kh;       // a0..a3 = (row g,k lo), (row g+8,k lo), (row g,k hi), (row g+8,k hi)
+  uint64_t w = poly[z];
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    uint32_t r = n ? (uint32_t)(w >> 32) : (uint32_t)w;
+    uint8_t* base = reinterpret_cast<uint8_t*>(dbf + (((((size_t)slice * 2 + n) * POLY + z) * F.mt + mt) * F.ks + ks) * 4 * 32);
+#pragma unroll
+    for (int l = 0; l < 4; l++) base[((size_t)l * 32 + lane) * 16 + reg * 4 + i] = (uint8_t)((r >> (7 * l)) & 127u);
+  }
+}
+
+// expanded queries (format of mul_kernels.cu: uint4 [jp][jb][z]) -> B fragments
+//   qf[n][z][ks][limb m][lane] = uint2{b0, b1};  column = 2*query + ciphertext row
+__global__ void __launch_bounds__(256)
+k_query_to_frag(ImmaGeom F, const uint4* __restrict__ q_dev, size_t q_stride, int nq, uint2* __restrict__ qf) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t total = (size_t)POLY * F.ks;
+  if (warp >= total) return;
+  const int ks = (int)(warp % F.ks);
+  const int z = (int)(warp / F.ks);
+  const int g = lane >> 2, t = lane & 3;
+  const int q = g >> 1, r = g & 1;
+  uint32_t res[2][2][4];      // [n][k half][i]
+#pragma unroll
+  for (int kh = 0; kh < 2; kh++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = ks * 32 + 16 * kh + 4 * t + i;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (q < nq && j < F.dim0) w = q_dev[(size_t)q * q_stride + ((size_t)(j >> 1) * 2 + (j & 1)) * POLY + z];
+      res[0][kh][i] = r ? w.z : w.x;
+      res[1][kh][i] = r ? w.w : w.y;
+    }
+#pragma unroll
+  for (int n = 0; n < 2; n++)
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      uint2 o;
+      o.x = limb4(res[n][0][0], res[n][0][1], res[n][0][2], res[n][0][3], m);
+      o.y = limb4(res[n][1][0], res[n][1][1], res[n][1][2], res[n][1][3], m);
+      qf[((((size_t)n * POLY + z) * F.ks + ks) * 4 + m) * 32 + lane] = o;
+    }
+}
+
+// out_zm[query][slice][n][z][row][ct_row] (u32): the product for up to 4 queries in one database pass.
+__global__ void __launch_bounds__(256, 2)
+k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const uint2* __restrict__ qf,
+                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin) {
+  extern __shared__ __align__(16) uint2 bsm[];            // [ks][m][lane]
+  const int z = blockIdx.x, n = blockIdx.y, slice = slice_begin + blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const uint2* src = qf + ((size_t)n * POLY + z) * F.ks * 4 * 32;
+    for (int i = threadIdx.x; i < F.ks * 128; i += blockDim.x) bsm[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint32_t q = n ? P.q[1] : P.q[0];
+  const uint64_t cr1 = n ? P.cr1[1] : P.cr1[0];
+  uint32_t p7[7];                                          // 2^{7s} mod q_n
+#pragma unroll
+  for (int s = 0; s < 7; s++) p7[s] = (uint32_t)((1ull << (7 * s)) % q);
+  const uint4* base = dbf + (((size_t)slice * 2 + n) * POLY + z) * F.mt * F.ks * 4 * 32 + lane;
+  const int g = lane >> 2, t = lane & 3;
+  const int nwarps = blockDim.x >> 5;
+  for (int mt0 = warp * 2; mt0 < F.mt; mt0 += nwarps * 2) {
+    const bool two = (mt0 + 1) < F.mt;
+    int acc[2][7][4];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int s = 0; s < 7; s++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[a][s][i] = 0;
+    const uint4* a0p = base + (size_t)mt0 * F.ks * 4 * 32;
+    const uint4* a1p = a0p + (size_t)(two ? 1 : 0) * F.ks * 4 * 32;
+#pragma unroll 1
+    for (int ks = 0; ks < F.ks; ks++) {
+      uint4 A0[4], A1[4];
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        A0[l] = ld_stream_v4(a0p + ((size_t)ks * 4 + l) * 32);
+        A1[l] = ld_stream_v4(a1p + ((size_t)ks * 4 + l) * 32);
+      }
+      uint2 B[4];
+#pragma unroll
+      for (int m = 0; m < 4; m++) B[m] = bsm[(ks * 4 + m) * 32 + lane];
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          mma_u8(acc[0][l + m], A0[l], B[m]);
+          mma_u8(acc[1][l + m], A1[l], B[m]);
+        }
+    }
+    // recombine the shift groups, reduce, store:  c0,c1 -> row g, columns 2t, 2t+1 ; c2,c3 -> row g+8
+    const int qi = t;                                    // column pair (2t, 2t+1) = query t, ciphertext rows 0/1
+    if (qi < nq) {
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        if (a == 1 && !two) break;
+#pragma unroll
+        for (int rh = 0; rh < 2; rh++) {
+          const int ii = (mt0 + a) * 16 + g + 8 * rh;
+          if (ii < F.rows) {
+            uint64_t v0 = 0, v1 = 0;
+#pragma unroll
+            for (int s = 0; s < 7; s++) {
+              v0 += (uint64_t)(uint32_t)acc[a][s][2 * rh] * p7[s];
+              v1 += (uint64_t)(uint32_t)acc[a][s][2 * rh + 1] * p7[s];
+            }
+            uint2 o = make_uint2(barrett64(v0, cr1, q), barrett64(v1, cr1, q));
+            uint32_t* dst = out_zm + (size_t)qi * out_stride +
+                            ((((size_t)slice * 2 + n) * POLY + z) * F.rows + ii) * 2;
+            *reinterpret_cast<uint2*>(dst) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+__constant__ Twiddle c_tw_lo_imma[2][2][64];
+struct TwConstI {
+  int n, dir;
+  __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_imma[n][dir][i]; }
+};
+struct TwGlobalI {
+  const Twiddle* p;
+  __device__ __forceinline__ Twiddle operator()(int i) const {
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
+    return Twiddle{v.x, v.y};
+  }
+};
+struct SyncI {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// inverse NTT of every (ciphertext row, modulus) of the z-major product -> residue-form ciphertexts
+//   out[((query*slices + slice)*rows + ii)][ct_row][n][z]     (server.rs:707-709 without the CRT lift)
+// grid = (rows*2 polys, 2 moduli, nq*slices), 256 threads
+__global__ void __launch_bounds__(256)
+k_intt_from_zmajor(DevParams P, ImmaGeom F, const uint32_t* __restrict__ in_zm, size_t in_stride, uint32_t* __restrict__ out,
+                   int slices) {
+  __shared__ __align__(16) uint32_t sm[NTT_SMEM_WORDS];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  const int ii = blockIdx.x >> 1, r = blockIdx.x & 1;
+  const int qs = blockIdx.z, qi = qs / slices, slice = qs % slices;
+  const uint32_t q = n ? P.q[1] : P.q[0];
+  const uint32_t* src = in_zm + (size_t)qi * in_stride + (((size_t)slice * 2 + n) * POLY) * F.rows * 2 + (size_t)ii * 2 + r;
+  uint32_t x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = __ldg(src + (size_t)(tid * 8 + k) * F.rows * 2);
+  ntt_inverse_group(tid, x, sm, TwConstI{n, 1}, TwGlobalI{n ? P.inv[1] : P.inv[0]}, q, SyncI());
+  uint32_t* dst = out + ((((size_t)qs * F.rows + ii) * 2 + r) * 2 + n) * POLY;
+#pragma unroll
+  for (int a = 0; a < 8; a++) dst[a * 256 + tid] = x[a];
+}
+
+// z-major product -> the ABI's [ii][r][n][z] NTT-form layout (stage-level entry point only)
+__global__ void k_zmajor_to_ntt32(ImmaGeom F, const uint32_t* __restrict__ in_zm, uint32_t* __restrict__ out, int slice) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over rows*4*2048, z fastest
+  if (idx >= (size_t)F.rows * 4 * POLY) return;
+  int z = (int)(idx % POLY);
+  int n = (int)((idx / POLY) & 1), r = (int)((idx / (2 * POLY)) & 1);
+  int ii = (int)(idx / (4 * POLY));
+  out[idx] = in_zm[((((size_t)slice * 2 + n) * POLY + z) * F.rows + ii) * 2 + r];
+}
+
+inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
+
+}  // namespace
+
+void upload_imma_constants(const Twiddle* lo) {
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_imma, lo, sizeof(Twiddle) * 2 * 2 * 64));
+}
+size_t imma_db_cells(const ImmaGeom& F, int slices) {
+  return (size_t)slices * 2 * POLY * F.mt * F.ks * 4 * 32;
+}
+size_t imma_query_cells(const ImmaGeom& F) { return (size_t)2 * POLY * F.ks * 4 * 32; }
+
+void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s) {
+  size_t warps = (size_t)POLY * F.mt * F.ks;
+  ++g_kernel_launches;
+  k_db_to_frag<<<grid1d(warps * 32, 256), 256, 0, s>>>(F, db0_slice, dbf, slice);
+}
+void launch_db_upsert_frag(const ImmaGeom& F, uint4* dbf, int slice, int il, int j, const uint64_t* poly, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_db_upsert_frag<<<POLY / 256, 256, 0, s>>>(F, dbf, slice, il, j, poly);
+}
+void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride, int nq, uint2* qf, cudaStream_t s) {
+  size_t warps = (size_t)POLY * F.ks;
+  ++g_kernel_launches;
+  k_query_to_frag<<<grid1d(warps * 32, 256), 256, 0, s>>>(F, q_dev, q_stride, nq, qf);
+}
+void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
+                          size_t out_stride, int nq, int slice_begin, int slice_count, cudaStream_t s) {
+  if (nq < 1 || nq > 4) throw Error(-2, "imma multiply: 1..4 queries per pass");
+  const size_t smem = (size_t)F.ks * 128 * sizeof(uint2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_multiply_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  if (smem > 64 * 1024) throw Error(-2, "imma multiply: dim0 too large");
+  ++g_kernel_launches;
+  k_multiply_imma<<<dim3(POLY, 2, slice_count), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
+}
+void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
+                             int nq, int slices, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_intt_from_zmajor<<<dim3(F.rows * 2, 2, nq * slices), 256, 0, s>>>(P, F, in_zm, in_stride, out, slices);
+}
+void launch_zmajor_to_ntt32(const ImmaGeom& F, const uint32_t* in_zm, uint32_t* out, int slice, cudaStream_t s) {
+  size_t total = (size_t)F.rows * 4 * POLY;
+  ++g_kernel_launches;
+  k_zmajor_to_ntt32<<<grid1d(total, 256), 256, 0, s>>>(F, in_zm, out, slice);
+}
+
+}  // namespace b200pir

@@ -59,6 +59,25 @@ void launch_db_upsert(const MulGeom& G, uint4* db_dev, int slice, int il, int j,
 void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_dev, uint64_t seed, uint64_t pt_modulus,
                      int slice_begin, int slice_count, cudaStream_t s);
 
+// ---- first dimension on INT8 tensor cores (imma_kernels.cu): database in MMA fragment order
+struct ImmaGeom { int dim0, rows, mt /* ceil(rows/16) */, ks /* ceil(dim0/32) */; };
+inline ImmaGeom make_imma_geom(int dim0, int rows) { return ImmaGeom{dim0, rows, (rows + 15) / 16, (dim0 + 31) / 32}; }
+size_t imma_db_cells(const ImmaGeom& F, int slices);      // uint4 cells of the whole database
+size_t imma_query_cells(const ImmaGeom& F);               // uint2 cells of the B operand (up to 4 queries)
+void upload_imma_constants(const Twiddle* lo);
+// one slice in the IMAD layout (uint4 [row][jp][z]) -> fragment order
+void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s);
+void launch_db_upsert_frag(const ImmaGeom& F, uint4* dbf, int slice, int il, int j, const uint64_t* poly, cudaStream_t s);
+void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride, int nq, uint2* qf, cudaStream_t s);
+// out_zm: u32 [query][slice][n][z][row][ct_row]  (queries out_stride words apart)
+void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
+                          size_t out_stride, int nq, int slice_begin, int slice_count, cudaStream_t s);
+// inverse NTT of the z-major product -> residue-form ciphertexts [query*slices + slice][row][ct_row][n][z]
+void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
+                             int nq, int slices, cudaStream_t s);
+// z-major product of one slice -> ntt32 [row][ct_row][n][z]
+void launch_zmajor_to_ntt32(const ImmaGeom& F, const uint32_t* in_zm, uint32_t* out, int slice, cudaStream_t s);
+
 // ---- second dimension
 // mult output ntt32 [cnt][r][n][z] -> raw ciphertexts u64 [cnt][r][z]   (server.rs:707-709)
 // (== launch_from_ntt with 2*cnt polys)

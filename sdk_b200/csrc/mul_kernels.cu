@@ -253,6 +253,51 @@ k_dpir_matvec(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, const 
   }
 }
 
+// One row per warp; every lane keeps U independent 8-byte streaming loads in flight before it consumes them.
+template <int U>
+__global__ void __launch_bounds__(256)
+k_dpir_matvec_row(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t rows,
+                  size_t cols, size_t cols_pad) {
+  extern __shared__ __align__(16) uint32_t bsm[];          // [3][cols_pad]
+  for (size_t k = threadIdx.x; k < cols_pad; k += blockDim.x) {
+    bool in = k < cols;
+    bsm[k] = in ? b[3 * k] : 0u;
+    bsm[cols_pad + k] = in ? b[3 * k + 1] : 0u;
+    bsm[2 * cols_pad + k] = in ? b[3 * k + 2] : 0u;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const size_t pairs = cols >> 1;                           // cols is even on this path
+  for (size_t row = (size_t)blockIdx.x * nwarps + warp; row < rows; row += (size_t)gridDim.x * nwarps) {
+    const uint2* ar = reinterpret_cast<const uint2*>(a + row * cols);
+    uint32_t acc = 0;
+    for (size_t p0 = 0; p0 < pairs; p0 += 32 * U) {
+      uint2 d[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        size_t p = p0 + (size_t)u * 32 + lane;
+        d[u] = make_uint2(0u, 0u);
+        if (p < pairs)
+          asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(d[u].x), "=r"(d[u].y) : "l"(ar + p));
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        size_t p = p0 + (size_t)u * 32 + lane;
+        if (p < pairs) {
+          uint2 b0 = *reinterpret_cast<const uint2*>(bsm + 2 * p);
+          uint2 b1 = *reinterpret_cast<const uint2*>(bsm + cols_pad + 2 * p);
+          uint2 b2 = *reinterpret_cast<const uint2*>(bsm + 2 * cols_pad + 2 * p);
+          acc += (d[u].x & 1023u) * b0.x + ((d[u].x >> 10) & 1023u) * b1.x + ((d[u].x >> 20) & 1023u) * b2.x;
+          acc += (d[u].y & 1023u) * b0.y + ((d[u].y >> 10) & 1023u) * b1.y + ((d[u].y >> 20) & 1023u) * b2.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
 inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
 
 }  // namespace
@@ -320,6 +365,19 @@ void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, siz
   size_t cols_pad = (cols + 3) & ~(size_t)3;
   size_t smem = 3 * cols_pad * 4;
   if (smem > 200 * 1024) throw Error(-2, "dpir: b too large for shared memory");
+  if ((cols & 1) == 0 && variant != 1 && variant != 4) {
+    // default: one row per warp, 8 loads in flight per lane (variant 2: 4 loads)
+    unsigned g = (unsigned)std::min<size_t>((rows + 7) / 8, (size_t)148 * 8);
+    ++g_kernel_launches;
+    if (variant == 2) {
+      cudaFuncSetAttribute(k_dpir_matvec_row<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_dpir_matvec_row<4><<<g, 256, smem, s>>>(out, a, b, rows, cols, cols_pad);
+    } else {
+      cudaFuncSetAttribute(k_dpir_matvec_row<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_dpir_matvec_row<8><<<g, 256, smem, s>>>(out, a, b, rows, cols, cols_pad);
+    }
+    return;
+  }
   const int rows_per_warp = variant == 1 ? 2 : 4;
   size_t warps_needed = (rows + rows_per_warp - 1) / rows_per_warp;
   unsigned grid = (unsigned)std::min<size_t>((warps_needed + 7) / 8, (size_t)148 * 8);

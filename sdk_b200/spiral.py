@@ -90,17 +90,21 @@ class Params:
 class Database:
     """The `db: &[u64]` argument of process_query, resident in HBM."""
 
-    def __init__(self, params, shard_index=0, shard_count=1):
+    def __init__(self, params, shard_index=0, shard_count=1, fmt=None):
+        """fmt: 0 = IMAD layout (single-query HBM roofline kernel), 1 = INT8 tensor-core fragment order
+        (batched queries); None = the context's current "db_format" option."""
         self.params = params
         h = C.c_void_p()
+        if fmt is not None:
+            params.set_option("db_format", fmt)
         check(LIB.b200pir_db_create(params._h, shard_index, shard_count, C.byref(h)))
         self._h = h
         self.shard_index, self.shard_count = shard_index, shard_count
 
     @classmethod
-    def from_words(cls, params, db):
+    def from_words(cls, params, db, fmt=None):
         """db: the reference's dense layout [instance][trial][z][ii][j] (server.rs:263-266)."""
-        self = cls(params)
+        self = cls(params, fmt=fmt)
         check(LIB.b200pir_db_upload(params._h, self._h, _ptr(db), db.size))
         return self
 

@@ -301,7 +301,17 @@ def test_dpir_matvec_matches_oracle(rows, cols):
     a = rng.integers(0, 2**30, rows * cols, dtype=np.uint32)
     b = rng.integers(0, 2**32, 3 * cols, dtype=np.uint32)
     m = D.PackedMatrix(a, rows, cols)
-    assert np.array_equal(D.matrix_mul_vec_packed(m, b), O.dpir_matvec_packed(a, b, rows, cols))
+    ref = O.dpir_matvec_packed(a, b, rows, cols)
+    assert np.array_equal(D.matrix_mul_vec_packed(m, b), ref)
+    import torch
+    from sdk_b200._lib import LIB, check
+    db_ = torch.from_numpy(b.view(np.int32)).cuda()
+    for variant in (0, 1, 2, 4):
+        do = torch.zeros(rows, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        check(LIB.b200pir_dpir_matvec_packed_dev(m._h, db_.data_ptr(), do.data_ptr(), variant))
+        D.matrix_mul_vec_packed(m, b)      # host call on the same (library-owned) stream: synchronises it
+        assert np.array_equal(do.cpu().numpy().view(np.uint32), ref), variant
     m.close()
 
 
@@ -428,3 +438,64 @@ def test_e2e_params_full_size_bytes_and_decode(name):
                           P.multiply_reg_by_database(db[(P.slices - 1) * slice_words:], d["v_firstdim"]))
     for h in (g2, gdb, gpp, G):
         h.close()
+
+
+# ------------------------------------------------------------------ INT8 tensor-core first dimension (db format 1)
+@pytest.mark.parametrize("name", CASES)
+def test_imma_multiply_and_process_query_match_oracle(name):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    fdb = S.Database.from_words(G, db, fmt=1)
+    G.set_option("db_format", 0)
+    rng = np.random.default_rng(14)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    slice_words = P.dim0 * P.num_per * P.N
+    for s in sorted({0, P.slices - 1}):
+        ref = P.multiply_reg_by_database(db[s * slice_words:(s + 1) * slice_words], v)
+        assert np.array_equal(S.multiply_reg_by_database(G, fdb, s, v), ref), (name, s)
+    # worst-case operands: every limb 127-ish, checks the exactness bounds of the s32 accumulators
+    w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
+    vmax = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
+    assert np.array_equal(S.multiply_reg_by_database(G, fdb, 0, vmax), P.multiply_reg_by_database(db[:slice_words], vmax))
+    # full pipeline, 7 queries = one group of 4 + one of 3
+    idxs = [0, 3, P.dim0 * P.num_per - 1, 17, 5, 9, 2]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    out = S.process_query_batch(G, gpp, qs, fdb)
+    for k, i in enumerate(idxs):
+        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
+        assert np.array_equal(out[k], ref), (name, k)
+    # synthetic generator and item upsert in fragment order
+    f2 = S.Database(G, fmt=1)
+    f2.fill_synthetic(SEED_DB)
+    assert np.array_equal(S.multiply_reg_by_database(G, f2, P.slices - 1, v), S.multiply_reg_by_database(G, fdb, P.slices - 1, v))
+    f3 = S.Database(G, fmt=1)
+    G.set_option("db_format", 0)
+    sl = db[:slice_words].reshape(P.N, P.num_per, P.dim0)
+    items = [0, 5, P.dim0 * P.num_per - 1, 33 % (P.dim0 * P.num_per)]
+    sparse = np.zeros_like(sl)
+    for it in items:
+        ii, j = it % P.num_per, it // P.num_per
+        f3.upsert_item(0, it, np.ascontiguousarray(sl[:, ii, j]))
+        sparse[:, ii, j] = sl[:, ii, j]
+    assert np.array_equal(S.multiply_reg_by_database(G, f3, 0, v), P.multiply_reg_by_database(sparse.reshape(-1), v))
+    for h in (fdb, f2, f3):
+        h.close()
+
+
+def test_imma_multiply_many_tiles_long_k():
+    # dim0 = 1024 (32 k-steps, accumulators near their exactness bound), 64 rows (4 row tiles over the warps), max operands
+    S = _gpu()
+    kw = dict(O.PARAM_SETS["T"])
+    kw.update(nu_1=10, nu_2=6, n=1, db_item_size=2048)
+    P = O.Params(**kw)
+    G = S.Params(**kw)
+    w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
+    rng = np.random.default_rng(15)
+    dbw = np.full(P.dim0 * P.num_per * P.N, w, dtype=np.uint64)
+    dbw[::5] = rng.integers(0, Q0, dbw[::5].size, dtype=np.uint64) | (rng.integers(0, Q1, dbw[::5].size, dtype=np.uint64) << np.uint64(32))
+    v = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
+    v[::3] = rng.integers(0, Q0, v[::3].size, dtype=np.uint64) | (rng.integers(0, Q1, v[::3].size, dtype=np.uint64) << np.uint64(32))
+    fdb = S.Database.from_words(G, dbw, fmt=1)
+    assert np.array_equal(S.multiply_reg_by_database(G, fdb, 0, v), P.multiply_reg_by_database(dbw, v))
+    fdb.close()
+    G.close()
