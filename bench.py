@@ -15,9 +15,10 @@ over one batch of `--batch` synthetic queries against the HBM-resident database.
                   toolchain exists in the image) on the host cores, on a bounded sample
 
 Workloads: N=1 -> S8 = 2^17 Spiral items x 8 KiB = 2^20 x 1 KiB records, 1 GiB of
-plaintext = 8 GiB HBM-resident.  N>1 (weak scaling) -> the same per-GPU shard, database N times larger
-(nu_2 = 8 + log2 N), second-dimension rows sharded ii mod N, one NCCL all-gather of the surviving
-ciphertexts per batch (DESIGN.md "multi-GPU").
+plaintext = 8 GiB HBM-resident.  N>1 (strong scaling) -> the SAME database with its second-dimension rows
+sharded ii mod N (1/N of the bytes per GPU), the same `--batch` queries per step: every rank expands the
+queries it received, NCCL all-gathers the expanded queries and, after the local first dimension + fold
+rounds, the surviving ciphertexts; each rank finishes its own queries (DESIGN.md "multi-GPU").
 
 Synthetic data: the server computation is data-oblivious, so public parameters and query ciphertexts
 are uniformly random residues of the right shape; the database is generated on the GPU from a
@@ -204,7 +205,7 @@ def run_reference_arm(args, kw, workload_name, rank, world):
     out = {
         "impl": "reference", "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name, "params": kw, "batch": 1},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,8 +221,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "1")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "16")),
+                    help="queries per step (whole job); must be a multiple of --gpus")
     ap.add_argument("--mul-variant", type=int, default=0)
+    ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
+                    help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -236,14 +240,17 @@ def main():
     name = args.workload or "S8"
     kw = dict(WORKLOADS[name])
     import math
+    base_name = {"S8": "S8: Spiral 2^20 x 1 KiB records (2^17 items x 8 KiB), 1 GiB plaintext = 8 GiB HBM-resident",
+                 "S1": "S1: 1 GiB HBM-resident (2^14 items x 8 KiB)", "T": "T: unit-test size"}[name]
     if N > 1:
         if N & (N - 1):
             raise SystemExit("--gpus must be a power of two")
-        kw["nu_2"] += int(math.log2(N))                 # weak scaling: same per-GPU shard, N x larger database
-        workload_name = "%s x%d (nu_2=%d), rows sharded ii mod %d" % (name, N, kw["nu_2"], N)
+        if args.batch % N:
+            raise SystemExit("--batch must be a multiple of --gpus")
+        # strong scaling: the SAME database, second-dimension rows sharded ii mod N (1/N of the bytes per GPU)
+        workload_name = "%s; rows sharded ii mod %d over %d GPUs" % (base_name, N, N)
     else:
-        workload_name = {"S8": "S8: Spiral 2^20 x 1 KiB records (2^17 items x 8 KiB), 1 GiB plaintext = 8 GiB HBM-resident",
-                         "S1": "S1: 1 GiB HBM-resident (2^14 items x 8 KiB)", "T": "T: unit-test size"}[name]
+        workload_name = base_name
 
     if args.impl == "reference":
         run_reference_arm(args, kw, workload_name, rank, world)
@@ -269,33 +276,48 @@ def main():
     stream = torch.cuda.current_stream()
     G.set_stream(stream.cuda_stream)
     G.set_option("mul_variant", args.mul_variant)
-    G.set_option("batch", 4 if B >= 4 else (2 if B >= 2 else 1))
-    gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N)
+    G.set_option("batch", 8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1)))
+    gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)
     rng = np.random.default_rng(20260923)
     pp = synthetic_pp(kw, rng)
     gpp = S.PublicParameters(G, pp["pack"], pp["left"], pp["right"], pp["conv"])
     modulus = Q0 * Q1
     rb = G.response_bytes
-    q_words = B * 2 * POLY
+    q_words = (B // N) * 2 * POLY
     # pinned host buffers for the e2e leg
     h_q = torch.empty(q_words, dtype=torch.int64).pin_memory()
     h_q.numpy().view(np.uint64)[:] = rng.integers(0, modulus, q_words, dtype=np.uint64)
-    h_out = torch.empty(B * rb, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((B // N) * rb, dtype=torch.uint8).pin_memory()
     d_q = h_q.cuda(non_blocking=False)
-    d_out = torch.zeros(B * rb, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((B // N) * rb, dtype=torch.uint8, device="cuda")
     rows_local = d["num_per"] // N
+    Bl = B // N                                      # queries this rank receives / answers per step
     if N > 1:
-        d_partial = torch.zeros(B * d["slices"] * 2 * POLY, dtype=torch.int64, device="cuda")
-        d_gather = torch.zeros(N * B * d["slices"] * 2 * POLY, dtype=torch.int64, device="cuda")
+        fold_words = kw["nu_2"] * 2 * 2 * kw["t_gsw"] * 2 * POLY
+        ct_words = 4 * POLY
+        d_qexp_l = torch.zeros(Bl * d["dim0"] * POLY * 4, dtype=torch.int32, device="cuda")
+        d_vf_l = torch.zeros(Bl * fold_words, dtype=torch.int32, device="cuda")
+        d_qexp = torch.zeros(B * d["dim0"] * POLY * 4, dtype=torch.int32, device="cuda")
+        d_vf = torch.zeros(B * fold_words, dtype=torch.int32, device="cuda")
+        d_partial = torch.zeros(B * d["slices"] * ct_words, dtype=torch.int32, device="cuda")
+        d_gather = torch.zeros(N * B * d["slices"] * ct_words, dtype=torch.int32, device="cuda")
+        coll_bytes = (N - 1) * (d_qexp_l.numel() + d_vf_l.numel() + d_partial.numel()) * 4
 
     def step_dev():
         if N == 1:
             check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), B, d_out.data_ptr()))
         else:
-            check(LIB.b200pir_query_stage_a_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), B, d_partial.data_ptr()))
+            # each rank expands the Bl queries it received; expanded queries are all-gathered; every rank runs the
+            # first dimension + local fold rounds of ALL B queries on its rows; survivors are all-gathered; each rank
+            # finishes (last log2 N rounds + pack + encode) its own Bl queries.
+            check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr(), Bl, d_qexp_l.data_ptr(), d_vf_l.data_ptr()))
+            dist.all_gather_into_tensor(d_qexp, d_qexp_l)
+            dist.all_gather_into_tensor(d_vf, d_vf_l)
+            check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, d_qexp.data_ptr(), d_vf.data_ptr(), B, d_partial.data_ptr()))
             dist.all_gather_into_tensor(d_gather, d_partial)
-            check(LIB.b200pir_query_stage_b_dev(G._h, gpp._h, d_gather.data_ptr(), N, B, d_out.data_ptr()))
+            check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, d_gather.data_ptr(), N, B, rank * Bl, Bl, d_vf_l.data_ptr(),
+                                                 d_out.data_ptr()))
 
     def step_e2e():
         if N == 1:
@@ -342,6 +364,20 @@ def main():
     ms_per_step = ms_total / args.steps
     qps = B * 1e3 / ms_per_step
 
+    # ---- single-query latency (device-resident, batch of 1), N == 1 only
+    single_ms = None
+    if N == 1:
+        for _ in range(3):
+            check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), 1, d_out.data_ptr()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), 1, d_out.data_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / 10
+
     # ---- end to end (host buffers, copies inside the timed region)
     for _ in range(2):
         step_e2e()
@@ -362,10 +398,16 @@ def main():
     mul_ms = stage["multiply"] / mul_launches
     nq_per_launch = B * args.steps / mul_launches
     db_bytes = d["slices"] * d["dim0"] * rows_local * POLY * 8
-    alg_bytes = db_bytes + nq_per_launch * (d["dim0"] * POLY * 16 + d["slices"] * rows_local * 4 * POLY * 4)
+    if args.db_format == 0:
+        operand_bytes = nq_per_launch * d["dim0"] * POLY * 16
+    else:   # limb fragments of the query operand: [n][z][column tiles][dim0/32][4 limbs][32 lanes] x 8 B
+        operand_bytes = 2 * POLY * (2 if nq_per_launch > 4 else 1) * ((d["dim0"] + 31) // 32) * 4 * 32 * 8
+    alg_bytes = db_bytes + operand_bytes + nq_per_launch * d["slices"] * rows_local * 4 * POLY * 4
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (mul_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_multiply (multiply_reg_by_database, server.rs:155-221)",
+    kname = "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)"
+    roofline = {"bound": "hbm", "kernel": kname + " = multiply_reg_by_database, server.rs:155-221",
+                "queries_per_launch": nq_per_launch,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(name, B), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mul_ms,
@@ -382,16 +424,19 @@ def main():
         out = {
             "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name, "params": kw, "batch": B, "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
-                       "parallelism": "rows ii mod %d + 1 NCCL all-gather" % N if N > 1 else "single GPU",
+                       "first_dimension_kernel": "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)",
+                       "parallelism": ("rows ii mod %d; queries expanded by the receiving rank; NCCL all-gather of expanded "
+                                       "queries and of surviving ciphertexts (%d bytes received per rank per step)" % (N, coll_bytes))
+                       if N > 1 else "single GPU",
                        "l2": "inputs larger than L2 (database %.1f GiB per GPU streamed every step)" % (db_bytes / 2**30)},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 2 * POLY * 8,
-                    "d2h_bytes_per_step": B * rb if N == 1 else B * rb},
+                    "d2h_bytes_per_step": B * rb},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
-            "single_query_latency_ms": ms_per_step if B == 1 else None,
+            "single_query_latency_ms": single_ms,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -51,7 +51,8 @@ void b200pir_ctx_destroy(b200pir_ctx* ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this context. */
 int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
-/* knobs: "mul_variant" (kernel tiling), "batch" (queries per database pass: 1, 2 or 4), "profile" (0 off, 1 per call,
+/* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4 or 8;
+ * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again);
  * unknown keys -> B200PIR_E_BADARG */
 int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);
@@ -120,7 +121,8 @@ int b200pir_encode(b200pir_ctx* ctx, const uint64_t* v_packed_raw, uint8_t* out,
  * out: response_bytes bytes. */
 int b200pir_process_query(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_ct,
                           const uint64_t* v_buf, const uint64_t* v_ct, uint8_t* out, size_t* out_len);
-/* `count` queries of one client in one call; the database is streamed once per group of up to 4 queries.
+/* `count` queries of one client in one call; the database is streamed once per group of up to 4 (IMAD layout)
+ * or 8 (INT8 tensor-core layout) queries.
  * queries: count x PolyMatrixRaw(2,1); out: count x response_bytes. */
 int b200pir_process_query_batch(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts,
                                 size_t count, uint8_t* out, size_t* out_len_each);
@@ -137,6 +139,20 @@ int b200pir_query_stage_a_dev(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, 
                               size_t count, uint32_t* partial_dev);
 int b200pir_query_stage_b_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world,
                               size_t count, uint8_t* out_dev);
+
+/* The same three phases with caller-owned device buffers in between (so a collective can sit between them):
+ *   expand:  count queries -> q_expanded_dev (count x dim0 x 2048 x 16 B, the first-dimension operand) and
+ *            v_folding_dev (count x nu_2 x 2 x 2 t_gsw x 2 x 2048 u32, NTT form)
+ *   first_dim_fold: any `count` expanded queries against this GPU's rows -> partial_dev (count x slices residue-form cts)
+ *   finish:  queries [first, first+count) of gathered_dev ([world][total_count][slices][ct]) -> responses; v_folding_dev holds
+ *            the folding matrices of exactly those `count` queries. */
+int b200pir_expand_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count,
+                               void* q_expanded_dev, uint32_t* v_folding_dev);
+int b200pir_first_dim_fold_dev(b200pir_ctx* ctx, b200pir_db* db, const void* q_expanded_dev, const uint32_t* v_folding_dev,
+                               size_t count, uint32_t* partial_dev);
+int b200pir_finish_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world,
+                               size_t total_count, size_t first, size_t count, const uint32_t* v_folding_dev,
+                               uint8_t* out_dev);
 
 /* Per-stage device time of the last profiled call, in milliseconds, measured with CUDA events on the
  * context's stream.  Enable with b200pir_ctx_set_option(ctx, "profile", 1).

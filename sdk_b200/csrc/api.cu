@@ -126,7 +126,7 @@ struct b200pir_ctx {
   DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
-  int mul_variant = 0, max_group = 4, profile = 0;
+  int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
@@ -183,6 +183,12 @@ struct b200pir_ctx {
       last_ms[6] += ms;
     }
     last_ms[7] = mul_launches;
+  }
+  // buffers of the first dimension / fold / pack only (queries expanded elsewhere)
+  void ensure_workspace_lite(size_t queries, size_t rows) {
+    w_mult.ensure(queries * slices * rows * 4 * POLY);
+    w_cts.ensure(queries * slices * rows * 4 * POLY);
+    w_packed.ensure(queries * hp.instances * (hp.n + 1) * hp.n * POLY);
   }
   void ensure_workspace(size_t queries, size_t rows) {
     if (queries <= ws_queries && rows <= ws_rows) return;
@@ -335,7 +341,10 @@ void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
 }
 
 // first dimension + from_ntt + local fold.  Leaves survivors at w_cts[(qi*slices + slice)*rows*2*POLY].
-void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
+void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const uint4* qdev = nullptr,
+                            const uint32_t* vfold = nullptr) {
+  if (!qdev) qdev = c->w_qdev.p;
+  if (!vfold) vfold = c->w_vfold.p;
   const int rows = db->rows;
   MulGeom G = c->geom(rows);
   const size_t q_stride = (size_t)c->dim0 * POLY;
@@ -348,7 +357,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
         int nq = 1;
         if (count - qi >= 4 && c->max_group >= 4) nq = 4;
         else if (count - qi >= 2 && c->max_group >= 2) nq = 2;
-        launch_multiply(c->dp, G, db->d.p, c->w_qdev.p + qi * q_stride, c->w_mult.p + qi * out_stride, 0, c->slices, nq,
+        launch_multiply(c->dp, G, db->d.p, qdev + qi * q_stride, c->w_mult.p + qi * out_stride, 0, c->slices, nq,
                         q_stride, out_stride, c->mul_variant, c->stream);
         c->mul_launches++;
         qi += nq;
@@ -362,11 +371,12 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
   } else {
     // INT8 tensor-core path: z-major product in w_cts (free until the fold starts), then inverse NTT into w_mult
     c->w_qf.ensure(imma_query_cells(db->F));
-    for (size_t qi = 0; qi < count; qi += 4) {
-      const int nq = (int)std::min<size_t>(4, count - qi);
+    const size_t per_pass = c->max_group >= 8 ? 8 : 4;
+    for (size_t qi = 0; qi < count; qi += per_pass) {
+      const int nq = (int)std::min<size_t>(per_pass, count - qi);
       {
         b200pir_ctx::Scope sc(c, ST_MUL);
-        launch_query_to_frag(db->F, c->w_qdev.p + qi * q_stride, q_stride, nq, c->w_qf.p, c->stream);
+        launch_query_to_frag(db->F, qdev + qi * q_stride, q_stride, nq, c->w_qf.p, c->stream);
         launch_multiply_imma(c->dp, db->F, db->f.p, c->w_qf.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
                              c->stream);
         c->mul_launches++;
@@ -383,7 +393,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count) {
     c->folded_stride = (size_t)rows * 4 * POLY;
     if (rows > 1)
       c->folded = run_fold_res(c, c->w_mult.p, c->w_cts.p, count * c->slices, (size_t)rows * 4 * POLY, rows,
-                               (int)c->hp.nu_2 - 1, c->w_vfold.p, c->slices);
+                               (int)c->hp.nu_2 - 1, vfold, c->slices);
   }
 }
 
@@ -406,11 +416,16 @@ void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* folded, siz
   }
 }
 
+// handles may be used from any context with identical parameters on the same device (one context per host
+// thread / CUDA stream sharing one HBM-resident database)
+bool same_params(const b200pir_ctx* a, const b200pir_ctx* b) {
+  return a == b || (a->device == b->device && std::memcmp(&a->hp, &b->hp, sizeof(b200pir_params)) == 0);
+}
 void check_db(b200pir_ctx* c, b200pir_db* db) {
-  if (!db || db->ctx != c) throw Error(B200PIR_E_BADARG, "db handle does not belong to this context");
+  if (!db || !same_params(db->ctx, c)) throw Error(B200PIR_E_BADARG, "db handle was created for different parameters / device");
 }
 void check_pp(b200pir_ctx* c, b200pir_pp* pp) {
-  if (!pp || pp->ctx != c) throw Error(B200PIR_E_BADARG, "pp handle does not belong to this context");
+  if (!pp || !same_params(pp->ctx, c)) throw Error(B200PIR_E_BADARG, "pp handle was created for different parameters / device");
 }
 
 }  // namespace
@@ -551,7 +566,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   Guard gd(c);
   std::string k(key);
   if (k == "mul_variant") c->mul_variant = (int)value;
-  else if (k == "batch") { if (value != 1 && value != 2 && value != 4) throw Error(B200PIR_E_BADARG, "batch must be 1, 2 or 4"); c->max_group = (int)value; }
+  else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4 or 8"); c->max_group = (int)value; }
   else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
@@ -1028,6 +1043,68 @@ int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const 
   B200_CUDA(cudaStreamSynchronize(c->stream));
   if (c->profile == 1) c->prof_collect();
   if (out_len) *out_len = c->response_bytes;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// ---- multi-GPU building blocks: the three phases with caller-owned device buffers in between, so the host can put a
+// collective between them (bench.py: queries are expanded by the rank that received them, everything is all-gathered)
+int b200pir_expand_queries_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count,
+                               void* q_expanded_dev, uint32_t* v_folding_dev) {
+  API_BEGIN
+  if (!c || !query_cts_dev || !q_expanded_dev || (!v_folding_dev && c->hp.nu_2)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "needs expand_queries");
+  if (count == 0) return 0;
+  c->w_v.ensure(count * c->v_words());
+  c->prof_reset();
+  {
+    b200pir_ctx::Scope sc(c, ST_EXPAND);
+    run_expand_query(c, pp, query_cts_dev, c->w_v.p, (uint4*)q_expanded_dev, v_folding_dev, (int)count);
+  }
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_first_dim_fold_dev(b200pir_ctx* c, b200pir_db* db, const void* q_expanded_dev, const uint32_t* v_folding_dev,
+                               size_t count, uint32_t* partial_dev) {
+  API_BEGIN
+  if (!c || !q_expanded_dev || !partial_dev || (!v_folding_dev && c->hp.nu_2)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  if (count == 0) return 0;
+  c->ensure_workspace_lite(count, db->rows);
+  run_first_dim_and_fold(c, db, count, (const uint4*)q_expanded_dev, v_folding_dev);
+  B200_CUDA(cudaMemcpy2DAsync(partial_dev, 4 * POLY * 4, c->folded, c->folded_stride * 4, 4 * POLY * 4, count * c->slices,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_finish_queries_dev(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world, size_t total_count,
+                               size_t first, size_t count, const uint32_t* v_folding_dev, uint8_t* out_dev) {
+  API_BEGIN
+  if (!c || !gathered_dev || !out_dev || (!v_folding_dev && world > 1)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (world == 0 || (world & (world - 1)) || world > (size_t)c->num_per) throw Error(B200PIR_E_SHAPE, "bad world size");
+  if (first + count > total_count) throw Error(B200PIR_E_SHAPE, "query range out of bounds");
+  if (count == 0) return 0;
+  c->ensure_workspace_lite(count, world);
+  const size_t ct = 4 * POLY;
+  for (size_t w = 0; w < world; w++)
+    B200_CUDA(cudaMemcpy2DAsync(c->w_mult.p + w * ct, world * ct * 4, gathered_dev + (w * total_count + first) * c->slices * ct,
+                                ct * 4, ct * 4, count * c->slices, cudaMemcpyDeviceToDevice, c->stream));
+  int dims = 0;
+  while (((size_t)1 << dims) < world) dims++;
+  {
+    b200pir_ctx::Scope sc(c, ST_FOLD);
+    c->folded = c->w_mult.p;
+    c->folded_stride = world * ct;
+    if (world > 1)
+      c->folded = run_fold_res(c, c->w_mult.p, c->w_cts.p, count * c->slices, world * ct, world, dims - 1, v_folding_dev,
+                               c->slices);
+  }
+  run_pack_encode(c, pp, c->folded, c->folded_stride, count, out_dev);
   B200_CUDA(cudaGetLastError());
   API_END
 }

@@ -98,17 +98,18 @@ __global__ void k_db_upsert_frag(ImmaGeom F, uint4* dbf, int slice, int il, int 
 }
 
 // expanded queries (format of mul_kernels.cu: uint4 [jp][jb][z]) -> B fragments
-//   qf[n][z][ks][limb m][lane] = uint2{b0, b1};  column = 2*query + ciphertext row
+//   qf[n][z][nt][ks][limb m][lane] = uint2{b0, b1};  column (nt*8 + g) = 2*query + ciphertext row
 __global__ void __launch_bounds__(256)
-k_query_to_frag(ImmaGeom F, const uint4* __restrict__ q_dev, size_t q_stride, int nq, uint2* __restrict__ qf) {
+k_query_to_frag(ImmaGeom F, const uint4* __restrict__ q_dev, size_t q_stride, int nq, int ntiles, uint2* __restrict__ qf) {
   const int lane = threadIdx.x & 31;
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t total = (size_t)POLY * F.ks;
+  const size_t total = (size_t)POLY * ntiles * F.ks;
   if (warp >= total) return;
   const int ks = (int)(warp % F.ks);
-  const int z = (int)(warp / F.ks);
+  const int nt = (int)((warp / F.ks) % ntiles);
+  const int z = (int)(warp / ((size_t)F.ks * ntiles));
   const int g = lane >> 2, t = lane & 3;
-  const int q = g >> 1, r = g & 1;
+  const int q = nt * 4 + (g >> 1), r = g & 1;
   uint32_t res[2][2][4];      // [n][k half][i]
 #pragma unroll
   for (int kh = 0; kh < 2; kh++)
@@ -127,20 +128,24 @@ k_query_to_frag(ImmaGeom F, const uint4* __restrict__ q_dev, size_t q_stride, in
       uint2 o;
       o.x = limb4(res[n][0][0], res[n][0][1], res[n][0][2], res[n][0][3], m);
       o.y = limb4(res[n][1][0], res[n][1][1], res[n][1][2], res[n][1][3], m);
-      qf[((((size_t)n * POLY + z) * F.ks + ks) * 4 + m) * 32 + lane] = o;
+      qf[(((((size_t)n * POLY + z) * ntiles + nt) * F.ks + ks) * 4 + m) * 32 + lane] = o;
     }
 }
 
-// out_zm[query][slice][n][z][row][ct_row] (u32): the product for up to 4 queries in one database pass.
+// out_zm[query][slice][n][z][row][ct_row] (u32): the product for up to 4*NT queries in one database pass.
+// NT = 1: each warp iteration covers 2 row tiles x 1 column tile; NT = 2: 1 row tile x 2 column tiles.
+template <int NT>
 __global__ void __launch_bounds__(256, 2)
 k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const uint2* __restrict__ qf,
                 uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin) {
-  extern __shared__ __align__(16) uint2 bsm[];            // [ks][m][lane]
-  const int z = blockIdx.x, n = blockIdx.y, slice = slice_begin + blockIdx.z;
+  extern __shared__ __align__(16) uint2 bsm[];            // [nt][ks][m][lane]
+  constexpr int RT = NT == 1 ? 2 : 1;                     // row tiles per warp iteration
+  // slices vary fastest across CTAs so that the CTAs sharing one B operand (same n, z) run together (L2 reuse)
+  const int z = blockIdx.y, n = blockIdx.z, slice = slice_begin + blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
-    const uint2* src = qf + ((size_t)n * POLY + z) * F.ks * 4 * 32;
-    for (int i = threadIdx.x; i < F.ks * 128; i += blockDim.x) bsm[i] = __ldg(src + i);
+    const uint2* src = qf + ((size_t)n * POLY + z) * NT * F.ks * 4 * 32;
+    for (int i = threadIdx.x; i < NT * F.ks * 128; i += blockDim.x) bsm[i] = __ldg(src + i);
   }
   __syncthreads();
   const uint32_t q = n ? P.q[1] : P.q[0];
@@ -151,9 +156,9 @@ k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const ui
   const uint4* base = dbf + (((size_t)slice * 2 + n) * POLY + z) * F.mt * F.ks * 4 * 32 + lane;
   const int g = lane >> 2, t = lane & 3;
   const int nwarps = blockDim.x >> 5;
-  for (int mt0 = warp * 2; mt0 < F.mt; mt0 += nwarps * 2) {
-    const bool two = (mt0 + 1) < F.mt;
-    int acc[2][7][4];
+  for (int mt0 = warp * RT; mt0 < F.mt; mt0 += nwarps * RT) {
+    const bool two = RT == 2 && (mt0 + 1) < F.mt;
+    int acc[2][7][4];                                      // [row tile (NT=1) or column tile (NT=2)][shift][c]
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -168,40 +173,43 @@ k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const ui
 #pragma unroll
       for (int l = 0; l < 4; l++) {
         A0[l] = ld_stream_v4(a0p + ((size_t)ks * 4 + l) * 32);
-        A1[l] = ld_stream_v4(a1p + ((size_t)ks * 4 + l) * 32);
+        if (RT == 2) A1[l] = ld_stream_v4(a1p + ((size_t)ks * 4 + l) * 32);
       }
-      uint2 B[4];
+      uint2 B0[4], B1[4];
 #pragma unroll
-      for (int m = 0; m < 4; m++) B[m] = bsm[(ks * 4 + m) * 32 + lane];
+      for (int m = 0; m < 4; m++) {
+        B0[m] = bsm[(ks * 4 + m) * 32 + lane];
+        if (NT == 2) B1[m] = bsm[((F.ks + ks) * 4 + m) * 32 + lane];
+      }
 #pragma unroll
       for (int l = 0; l < 4; l++)
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-          mma_u8(acc[0][l + m], A0[l], B[m]);
-          mma_u8(acc[1][l + m], A1[l], B[m]);
+          mma_u8(acc[0][l + m], A0[l], B0[m]);
+          if (RT == 2) mma_u8(acc[1][l + m], A1[l], B0[m]);
+          if (NT == 2) mma_u8(acc[1][l + m], A0[l], B1[m]);
         }
     }
     // recombine the shift groups, reduce, store:  c0,c1 -> row g, columns 2t, 2t+1 ; c2,c3 -> row g+8
-    const int qi = t;                                    // column pair (2t, 2t+1) = query t, ciphertext rows 0/1
-    if (qi < nq) {
 #pragma unroll
-      for (int a = 0; a < 2; a++) {
-        if (a == 1 && !two) break;
+    for (int a = 0; a < 2; a++) {
+      const int mt = RT == 2 ? mt0 + a : mt0;
+      const int qi = (NT == 2 ? a * 4 : 0) + t;            // column pair (2t, 2t+1) of column tile = query, ct rows 0/1
+      if (RT == 2 && a == 1 && !two) break;
+      if (qi >= nq) continue;
 #pragma unroll
-        for (int rh = 0; rh < 2; rh++) {
-          const int ii = (mt0 + a) * 16 + g + 8 * rh;
-          if (ii < F.rows) {
-            uint64_t v0 = 0, v1 = 0;
+      for (int rh = 0; rh < 2; rh++) {
+        const int ii = mt * 16 + g + 8 * rh;
+        if (ii < F.rows) {
+          uint64_t v0 = 0, v1 = 0;
 #pragma unroll
-            for (int s = 0; s < 7; s++) {
-              v0 += (uint64_t)(uint32_t)acc[a][s][2 * rh] * p7[s];
-              v1 += (uint64_t)(uint32_t)acc[a][s][2 * rh + 1] * p7[s];
-            }
-            uint2 o = make_uint2(barrett64(v0, cr1, q), barrett64(v1, cr1, q));
-            uint32_t* dst = out_zm + (size_t)qi * out_stride +
-                            ((((size_t)slice * 2 + n) * POLY + z) * F.rows + ii) * 2;
-            *reinterpret_cast<uint2*>(dst) = o;
+          for (int s = 0; s < 7; s++) {
+            v0 += (uint64_t)(uint32_t)acc[a][s][2 * rh] * p7[s];
+            v1 += (uint64_t)(uint32_t)acc[a][s][2 * rh + 1] * p7[s];
           }
+          uint2 o = make_uint2(barrett64(v0, cr1, q), barrett64(v1, cr1, q));
+          uint32_t* dst = out_zm + (size_t)qi * out_stride + ((((size_t)slice * 2 + n) * POLY + z) * F.rows + ii) * 2;
+          *reinterpret_cast<uint2*>(dst) = o;
         }
       }
     }
@@ -265,7 +273,7 @@ void upload_imma_constants(const Twiddle* lo) {
 size_t imma_db_cells(const ImmaGeom& F, int slices) {
   return (size_t)slices * 2 * POLY * F.mt * F.ks * 4 * 32;
 }
-size_t imma_query_cells(const ImmaGeom& F) { return (size_t)2 * POLY * F.ks * 4 * 32; }
+size_t imma_query_cells(const ImmaGeom& F) { return (size_t)2 * POLY * 2 * F.ks * 4 * 32; }   // up to 2 column tiles
 
 void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s) {
   size_t warps = (size_t)POLY * F.mt * F.ks;
@@ -277,22 +285,28 @@ void launch_db_upsert_frag(const ImmaGeom& F, uint4* dbf, int slice, int il, int
   k_db_upsert_frag<<<POLY / 256, 256, 0, s>>>(F, dbf, slice, il, j, poly);
 }
 void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride, int nq, uint2* qf, cudaStream_t s) {
-  size_t warps = (size_t)POLY * F.ks;
+  const int ntiles = nq > 4 ? 2 : 1;
+  size_t warps = (size_t)POLY * ntiles * F.ks;
   ++g_kernel_launches;
-  k_query_to_frag<<<grid1d(warps * 32, 256), 256, 0, s>>>(F, q_dev, q_stride, nq, qf);
+  k_query_to_frag<<<grid1d(warps * 32, 256), 256, 0, s>>>(F, q_dev, q_stride, nq, ntiles, qf);
 }
 void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
                           size_t out_stride, int nq, int slice_begin, int slice_count, cudaStream_t s) {
-  if (nq < 1 || nq > 4) throw Error(-2, "imma multiply: 1..4 queries per pass");
-  const size_t smem = (size_t)F.ks * 128 * sizeof(uint2);
+  if (nq < 1 || nq > 8) throw Error(-2, "imma multiply: 1..8 queries per pass");
+  const int ntiles = nq > 4 ? 2 : 1;
+  const size_t smem = (size_t)ntiles * F.ks * 128 * sizeof(uint2);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_multiply_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_multiply_imma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(k_multiply_imma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
-  if (smem > 64 * 1024) throw Error(-2, "imma multiply: dim0 too large");
+  if (smem > 96 * 1024) throw Error(-2, "imma multiply: dim0 too large");
   ++g_kernel_launches;
-  k_multiply_imma<<<dim3(POLY, 2, slice_count), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
+  if (ntiles == 1)
+    k_multiply_imma<1><<<dim3(slice_count, POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
+  else
+    k_multiply_imma<2><<<dim3(slice_count, POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
 }
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
                              int nq, int slices, cudaStream_t s) {

@@ -63,7 +63,7 @@ void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_d
 struct ImmaGeom { int dim0, rows, mt /* ceil(rows/16) */, ks /* ceil(dim0/32) */; };
 inline ImmaGeom make_imma_geom(int dim0, int rows) { return ImmaGeom{dim0, rows, (rows + 15) / 16, (dim0 + 31) / 32}; }
 size_t imma_db_cells(const ImmaGeom& F, int slices);      // uint4 cells of the whole database
-size_t imma_query_cells(const ImmaGeom& F);               // uint2 cells of the B operand (up to 4 queries)
+size_t imma_query_cells(const ImmaGeom& F);               // uint2 cells of the B operand (up to 8 queries)
 void upload_imma_constants(const Twiddle* lo);
 // one slice in the IMAD layout (uint4 [row][jp][z]) -> fragment order
 void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s);

@@ -274,7 +274,7 @@ def test_process_query_batch_equals_single(group):
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     G.set_option("batch", group)
     out = S.process_query_batch(G, gpp, qs, gdb)
-    G.set_option("batch", 4)
+    G.set_option("batch", 8)
     for k, i in enumerate(idxs):
         ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
         assert np.array_equal(out[k], ref), (group, k)
@@ -457,13 +457,16 @@ def test_imma_multiply_and_process_query_match_oracle(name):
     w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
     vmax = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
     assert np.array_equal(S.multiply_reg_by_database(G, fdb, 0, vmax), P.multiply_reg_by_database(db[:slice_words], vmax))
-    # full pipeline, 7 queries = one group of 4 + one of 3
-    idxs = [0, 3, P.dim0 * P.num_per - 1, 17, 5, 9, 2]
+    # full pipeline, 11 queries: groups of 4+4+3 (batch 4) and 8+3 (batch 8: two column tiles)
+    idxs = [0, 3, P.dim0 * P.num_per - 1, 17, 5, 9, 2, 11, 1, 30, 6]
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
-    out = S.process_query_batch(G, gpp, qs, fdb)
-    for k, i in enumerate(idxs):
-        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
-        assert np.array_equal(out[k], ref), (name, k)
+    refs = [P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db) for k in range(len(idxs))]
+    for group in (4, 8):
+        G.set_option("batch", group)
+        out = S.process_query_batch(G, gpp, qs, fdb)
+        for k in range(len(idxs)):
+            assert np.array_equal(out[k], refs[k]), (name, group, k)
+    G.set_option("batch", 8)
     # synthetic generator and item upsert in fragment order
     f2 = S.Database(G, fmt=1)
     f2.fill_synthetic(SEED_DB)
@@ -499,3 +502,50 @@ def test_imma_multiply_many_tiles_long_k():
     assert np.array_equal(S.multiply_reg_by_database(G, fdb, 0, v), P.multiply_reg_by_database(dbw, v))
     fdb.close()
     G.close()
+
+
+@pytest.mark.parametrize("name,world,fmt", [("T0", 2, 1), ("T0", 4, 0), ("T1", 2, 1)])
+def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
+    """bench.py's N>1 flow on one GPU: every "rank" expands its own queries, expanded queries are concatenated
+    (all-gather), every rank runs first dimension + local fold for ALL queries on its row shard, survivors are
+    concatenated (all-gather), each rank finishes its own queries.  Responses == oracle bytes."""
+    import torch
+    from sdk_b200._lib import LIB, check
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    per_rank = 2
+    total = per_rank * world
+    idxs = [(7 * k + 3) % (P.dim0 * P.num_per) for k in range(total)]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    d_q = torch.from_numpy(qs.view(np.int64)).cuda()
+    qexp_words = P.dim0 * P.N * 4
+    fold_words = P.nu_2 * 2 * 2 * P.t_gsw * 2 * P.N
+    ct_words = 4 * P.N
+    qexp = torch.zeros(total * qexp_words, dtype=torch.int32, device="cuda")
+    vf = torch.zeros(total * fold_words, dtype=torch.int32, device="cuda")
+    for r in range(world):          # phase 1 on every rank, results land where the all-gather would put them
+        check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + r * per_rank * 2 * P.N * 8, per_rank,
+                                             qexp.data_ptr() + r * per_rank * qexp_words * 4,
+                                             vf.data_ptr() + r * per_rank * fold_words * 4))
+    gathered = torch.zeros(world * total * P.slices * ct_words, dtype=torch.int32, device="cuda")
+    slice_words = P.dim0 * P.num_per * P.N
+    shards = []
+    for r in range(world):          # phase 2
+        sh = S.Database(G, shard_index=r, shard_count=world, fmt=fmt)
+        for sl in range(P.slices):
+            sh.upload_slice(sl, db[sl * slice_words:(sl + 1) * slice_words])
+        shards.append(sh)
+        check(LIB.b200pir_first_dim_fold_dev(G._h, sh._h, qexp.data_ptr(), vf.data_ptr(), total,
+                                             gathered.data_ptr() + r * total * P.slices * ct_words * 4))
+    G.set_option("db_format", 0)
+    out = torch.zeros(total * G.response_bytes, dtype=torch.uint8, device="cuda")
+    for r in range(world):          # phase 3
+        check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, gathered.data_ptr(), world, total, r * per_rank, per_rank,
+                                             vf.data_ptr() + r * per_rank * fold_words * 4,
+                                             out.data_ptr() + r * per_rank * G.response_bytes))
+    G.synchronize()
+    got = out.cpu().numpy().reshape(total, G.response_bytes)
+    for k, i in enumerate(idxs):
+        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
+        assert np.array_equal(got[k], ref), (name, world, k)
+    for sh in shards:
+        sh.close()
