@@ -404,15 +404,13 @@ void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* folded, siz
   const size_t packed_words = (size_t)hp.instances * (hp.n + 1) * hp.n * POLY;
   {
     b200pir_ctx::Scope sc(c, ST_PACK);
-    for (size_t qi = 0; qi < count; qi++)
-      launch_pack(c->dp, c->w_packed.p + qi * packed_words, folded + qi * c->slices * ct_stride, ct_stride, pp->pack.p,
-                  (int)hp.n, (int)hp.instances, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+    launch_pack(c->dp, c->w_packed.p, packed_words, folded, ct_stride, (size_t)c->slices * ct_stride, (int)count, pp->pack.p,
+                (int)hp.n, (int)hp.instances, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
   }
   {
     b200pir_ctx::Scope sc(c, ST_ENCODE);
-    for (size_t qi = 0; qi < count; qi++)
-      launch_encode(c->dp, out_dev + qi * c->response_bytes, c->response_bytes, c->w_packed.p + qi * packed_words,
-                    (int)hp.n, (int)hp.instances, c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
+    launch_encode(c->dp, out_dev, c->response_bytes, c->w_packed.p, packed_words, (int)count, (int)hp.n, (int)hp.instances,
+                  c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
   }
 }
 
@@ -936,7 +934,7 @@ int b200pir_pack(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* v_ct, uint64_t*
   DevBuf<uint32_t> o(outp * 2 * POLY), res(nn * 4 * POLY);
   B200_CUDA(cudaMemcpyAsync(cts.p, v_ct, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
   launch_raw_to_res(c->dp, res.p, cts.p, nn * 2, c->stream);
-  launch_pack(c->dp, raw.p, res.p, 4 * POLY, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+  launch_pack(c->dp, raw.p, 0, res.p, 4 * POLY, 0, 1, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
   // the reference's pack returns the NTT-form matrix (server.rs:467); the kernel already applied .raw()
   launch_to_ntt(c->dp, o.p, raw.p, outp, c->stream);
   launch_widen(wide.p, o.p, o.n, c->stream);
@@ -955,7 +953,7 @@ int b200pir_encode(b200pir_ctx* c, const uint64_t* v_packed_raw, uint8_t* out, s
   DevBuf<uint64_t> in(words);
   DevBuf<uint8_t> o(c->response_bytes);
   B200_CUDA(cudaMemcpyAsync(in.p, v_packed_raw, words * 8, cudaMemcpyHostToDevice, c->stream));
-  launch_encode(c->dp, o.p, c->response_bytes, in.p, (int)hp.n, (int)hp.instances, c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
+  launch_encode(c->dp, o.p, c->response_bytes, in.p, 0, 1, (int)hp.n, (int)hp.instances, c->q2, (int)hp.q2_bits, c->q1, c->q1_bits, c->stream);
   B200_CUDA(cudaMemcpyAsync(out, o.p, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
   if (out_len) *out_len = c->response_bytes;

@@ -119,11 +119,13 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride,
 // ---- packing + encoding (server.rs:429-503; lib/server compute/pack.rs)
 // folded: residue-form ciphertexts, ct (inst, t) at folded + (inst*n*n + t)*ct_stride (u32 words);
 // w: ntt32 packing matrices; out: raw [inst][n+1][n][2048]
-void launch_pack(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
-                 const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
-                 cudaStream_t s);
-void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,
-                   uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s);
+// nq queries per launch: query k reads folded + k*in_q_stride and writes out_raw + k*out_q_stride
+void launch_pack(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride,
+                 size_t in_q_stride, int nq, const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv,
+                 int version, cudaStream_t s);
+// out: nq x out_bytes; packed_raw: nq matrices packed_q_stride words apart
+void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, size_t packed_q_stride,
+                   int nq, int n, int instances, uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s);
 
 // ---- DoublePIR packed matvec (K6): lib/doublepir/src/matrix/kernels.rs:14-178
 void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols, int variant,

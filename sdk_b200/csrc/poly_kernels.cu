@@ -600,8 +600,10 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* 
 // ------------------------------------------------------------------ pack (v0: server.rs:429-468; v1: lib/server pack.rs:45-98)
 template <int ROWS>
 __global__ void __launch_bounds__(CTA, 1)
-k_pack(DevParams P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride, const uint32_t* v_packing, int t_conv,
-       int bits, int version) {
+k_pack(DevParams P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride, size_t in_q_stride,
+       const uint32_t* v_packing, int t_conv, int bits, int version) {
+  out_raw += (size_t)blockIdx.y * out_q_stride;
+  folded += (size_t)blockIdx.y * in_q_stride;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* ntt_smem = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* res = ntt_smem + 4 * NTT_SMEM_WORDS;
@@ -727,10 +729,12 @@ __device__ __forceinline__ uint64_t rescale_dev(uint64_t a, uint64_t inp_mod, ui
 }
 // One thread per output 64-bit word.  Stream = per instance: n*2048 values of q2_bits (row 0 of the
 // packed matrix), then n*n*2048 values of q1_bits (rows 1..n), LSB-first (util.rs:303-321).
-__global__ void k_encode(DevParams P, uint64_t* out, size_t out_words, const uint64_t* packed, int n, int instances,
-                         uint64_t q2, int q2_bits, uint64_t q1, int q1_bits) {
+__global__ void k_encode(DevParams P, uint64_t* out, size_t out_words, const uint64_t* packed, size_t packed_q_stride, int n,
+                         int instances, uint64_t q2, int q2_bits, uint64_t q1, int q1_bits) {
   size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= out_words) return;
+  out += (size_t)blockIdx.y * out_words;
+  packed += (size_t)blockIdx.y * packed_q_stride;
   const uint64_t first_cnt = (uint64_t)n * POLY, rest_cnt = (uint64_t)n * n * POLY;
   const uint64_t inst_bits = first_cnt * q2_bits + rest_cnt * q1_bits;
   uint64_t lo_bit = (uint64_t)w * 64, hi_bit = lo_bit + 64;
@@ -859,35 +863,35 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride,
                                                                                t_conv, bits_conv);
 }
 template <int ROWS>
-static void launch_pack_t(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
-                          const uint32_t* v_packing, int instances, int t_conv, int bits_conv, int version,
-                          cudaStream_t s) {
+static void launch_pack_t(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded,
+                          size_t ct_stride, size_t in_q_stride, int nq, const uint32_t* v_packing, int instances,
+                          int t_conv, int bits_conv, int version, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_pack<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
     attr_set = true;
   }
   ++g_kernel_launches;
-  k_pack<ROWS><<<(unsigned)(instances * (ROWS - 1)), CTA, kDynSmemBig, s>>>(P, out_raw, folded, ct_stride, v_packing,
-                                                                           t_conv, bits_conv, version);
+  k_pack<ROWS><<<dim3((unsigned)(instances * (ROWS - 1)), nq), CTA, kDynSmemBig, s>>>(
+      P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, v_packing, t_conv, bits_conv, version);
 }
-void launch_pack(const DevParams& P, uint64_t* out_raw, const uint32_t* folded, size_t ct_stride,
-                 const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv, int version,
-                 cudaStream_t s) {
+void launch_pack(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride,
+                 size_t in_q_stride, int nq, const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv,
+                 int version, cudaStream_t s) {
   switch (n) {
-    case 1: launch_pack_t<2>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 2: launch_pack_t<3>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 3: launch_pack_t<4>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 4: launch_pack_t<5>(P, out_raw, folded, ct_stride, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 1: launch_pack_t<2>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 2: launch_pack_t<3>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 3: launch_pack_t<4>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 4: launch_pack_t<5>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
     default: throw Error(-2, "pack: n must be 1..4");
   }
 }
-void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, int n, int instances,
-                   uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s) {
+void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, size_t packed_q_stride,
+                   int nq, int n, int instances, uint64_t q2, int q2_bits, uint64_t q1, int q1_bits, cudaStream_t s) {
   size_t words = out_bytes / 8;
   ++g_kernel_launches;
-  k_encode<<<grid1d(words, 128), 128, 0, s>>>(P, reinterpret_cast<uint64_t*>(out), words, packed_raw, n, instances, q2,
-                                              q2_bits, q1, q1_bits);
+  k_encode<<<dim3(grid1d(words, 128), nq), 128, 0, s>>>(P, reinterpret_cast<uint64_t*>(out), words, packed_raw,
+                                                        packed_q_stride, n, instances, q2, q2_bits, q1, q1_bits);
 }
 
 }  // namespace b200pir
