@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--mul-variant", type=int, default=0)
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
                     help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
+    ap.add_argument("--fold-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -276,6 +277,7 @@ def main():
     stream = torch.cuda.current_stream()
     G.set_stream(stream.cuda_stream)
     G.set_option("mul_variant", args.mul_variant)
+    G.set_option("fold_variant", args.fold_variant)
     G.set_option("batch", 8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1)))
     gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)

@@ -127,6 +127,7 @@ struct b200pir_ctx {
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
+  int fold_variant = 0;
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
@@ -327,7 +328,7 @@ const uint32_t* run_fold_res(b200pir_ctx* c, uint32_t* a, uint32_t* b, size_t ba
   uint32_t* dst = b;
   for (size_t half = num / 2; half >= 1; half /= 2, k--) {
     launch_fold_res(c->dp, src, dst, batch, batch_stride, (int)half, vfold + (size_t)k * mat, c->fold_words(),
-                    slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+                    slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, c->stream);
     std::swap(src, dst);
   }
   return src;
@@ -565,6 +566,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   std::string k(key);
   if (k == "mul_variant") c->mul_variant = (int)value;
   else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4 or 8"); c->max_group = (int)value; }
+  else if (k == "fold_variant") c->fold_variant = (int)value;
   else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
@@ -843,7 +845,7 @@ int b200pir_fold_ciphertexts(b200pir_ctx* c, uint64_t* v_cts, size_t num, const 
     int k = dims - 1;
     for (size_t half = num / 2; half >= 1; half /= 2, k--) {
       launch_fold_res(c->dp, a.p, b.p, 1, num * 4 * POLY, (int)half, vf.p + (size_t)k * mat, c->fold_words(), 1,
-                      (int)c->hp.t_gsw, c->bits_gsw, c->stream);
+                      (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, c->stream);
       B200_CUDA(cudaMemcpyAsync(a.p, b.p, half * 4 * POLY * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     launch_res_to_raw(c->dp, cts.p, a.p, num * 2, c->stream);

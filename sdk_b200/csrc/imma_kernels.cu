@@ -137,11 +137,12 @@ k_query_to_frag(ImmaGeom F, const uint4* __restrict__ q_dev, size_t q_stride, in
 template <int NT>
 __global__ void __launch_bounds__(256, 2)
 k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const uint2* __restrict__ qf,
-                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin) {
+                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count) {
   extern __shared__ __align__(16) uint2 bsm[];            // [nt][ks][m][lane]
   constexpr int RT = NT == 1 ? 2 : 1;                     // row tiles per warp iteration
-  // slices vary fastest across CTAs so that the CTAs sharing one B operand (same n, z) run together (L2 reuse)
-  const int z = blockIdx.y, n = blockIdx.z, slice = slice_begin + blockIdx.x;
+  // CTA = one (n, z): the B operand is staged once and shared by every slice; the work items (slice, row tiles) are
+  // spread over the 8 warps, so small row shards (multi-GPU) still keep all warps busy
+  const int z = blockIdx.x, n = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
     const uint2* src = qf + ((size_t)n * POLY + z) * NT * F.ks * 4 * 32;
@@ -153,10 +154,13 @@ k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const ui
   uint32_t p7[7];                                          // 2^{7s} mod q_n
 #pragma unroll
   for (int s = 0; s < 7; s++) p7[s] = (uint32_t)((1ull << (7 * s)) % q);
-  const uint4* base = dbf + (((size_t)slice * 2 + n) * POLY + z) * F.mt * F.ks * 4 * 32 + lane;
   const int g = lane >> 2, t = lane & 3;
   const int nwarps = blockDim.x >> 5;
-  for (int mt0 = warp * RT; mt0 < F.mt; mt0 += nwarps * RT) {
+  const int groups = (F.mt + RT - 1) / RT;                 // row-tile groups per slice
+  for (int item = warp; item < slice_count * groups; item += nwarps) {
+    const int slice = slice_begin + item / groups;
+    const int mt0 = (item % groups) * RT;
+    const uint4* base = dbf + (((size_t)slice * 2 + n) * POLY + z) * F.mt * F.ks * 4 * 32 + lane;
     const bool two = RT == 2 && (mt0 + 1) < F.mt;
     int acc[2][7][4];                                      // [row tile (NT=1) or column tile (NT=2)][shift][c]
 #pragma unroll
@@ -220,12 +224,24 @@ __constant__ Twiddle c_tw_lo_imma[2][2][64];
 struct TwConstI {
   int n, dir;
   __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_imma[n][dir][i]; }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const { t[0] = (*this)(i); t[1] = (*this)(i + 1); }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    t[0] = (*this)(i); t[1] = (*this)(i + 1); t[2] = (*this)(i + 2); t[3] = (*this)(i + 3);
+  }
 };
 struct TwGlobalI {
   const Twiddle* p;
   __device__ __forceinline__ Twiddle operator()(int i) const {
     uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
     return Twiddle{v.x, v.y};
+  }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w};
+  }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i)), w = __ldg(reinterpret_cast<const uint4*>(p + i) + 1);
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w}; t[2] = Twiddle{w.x, w.y}; t[3] = Twiddle{w.z, w.w};
   }
 };
 struct SyncI {
@@ -304,9 +320,9 @@ void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* db
   if (smem > 96 * 1024) throw Error(-2, "imma multiply: dim0 too large");
   ++g_kernel_launches;
   if (ntiles == 1)
-    k_multiply_imma<1><<<dim3(slice_count, POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
+    k_multiply_imma<1><<<dim3(POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin, slice_count);
   else
-    k_multiply_imma<2><<<dim3(slice_count, POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin);
+    k_multiply_imma<2><<<dim3(POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin, slice_count);
 }
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
                              int nq, int slices, cudaStream_t s) {

@@ -23,12 +23,24 @@ __constant__ Twiddle c_tw_lo_mul[2][2][64];
 struct TwConstM {
   int n, dir;
   __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_mul[n][dir][i]; }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const { t[0] = (*this)(i); t[1] = (*this)(i + 1); }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    t[0] = (*this)(i); t[1] = (*this)(i + 1); t[2] = (*this)(i + 2); t[3] = (*this)(i + 3);
+  }
 };
 struct TwGlobalM {
   const Twiddle* p;
   __device__ __forceinline__ Twiddle operator()(int i) const {
     uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
     return Twiddle{v.x, v.y};
+  }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w};
+  }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i)), w = __ldg(reinterpret_cast<const uint4*>(p + i) + 1);
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w}; t[2] = Twiddle{w.x, w.y}; t[3] = Twiddle{w.z, w.w};
   }
 };
 

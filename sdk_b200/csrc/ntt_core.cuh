@@ -73,9 +73,13 @@ NTT_HD uint32_t ntt_canon(uint32_t v, uint32_t q, uint32_t two_q) {
 // tw_base[s] is the table offset 2^mm of stage s; grp[s] the group index of the thread's a=0
 // element at that stage (group of element a is grp[s] + (a >> (3 - s))).
 // `tab` is any callable idx -> Twiddle (plain array, __constant__ bank, shared-memory copy ...).
+// Accessors also provide load2 / load4 for runs of consecutive entries (index multiple of 2 / 4), so that
+// shared-memory tables can be read with 16-byte accesses (conflict-free) instead of strided 8-byte ones.
 struct TwArray {
   const Twiddle* p;
   NTT_HD Twiddle operator()(int i) const { return p[i]; }
+  NTT_HD void load2(int i, Twiddle (&t)[2]) const { t[0] = p[i]; t[1] = p[i + 1]; }
+  NTT_HD void load4(int i, Twiddle (&t)[4]) const { t[0] = p[i]; t[1] = p[i + 1]; t[2] = p[i + 2]; t[3] = p[i + 3]; }
 };
 template <typename Tab>
 NTT_HD void radix8_fwd(uint32_t (&x)[8], Tab tab, int m0, int g0, uint32_t q, uint32_t two_q) {
@@ -83,33 +87,31 @@ NTT_HD void radix8_fwd(uint32_t (&x)[8], Tab tab, int m0, int g0, uint32_t q, ui
   // stage s=1: pairs (a, a+2); group = 2*g0 + (a>>2)         table idx 2*m0 + ...
   // stage s=2: pairs (a, a+1); group = 4*g0 + (a>>1)
   Twiddle t0 = tab(m0 + g0);
+  Twiddle t1[2], t2[4];
+  tab.load2(2 * m0 + 2 * g0, t1);
+  tab.load4(4 * m0 + 4 * g0, t2);
 #pragma unroll
   for (int a = 0; a < 4; a++) bfly_fwd(x[a], x[a + 4], t0, q, two_q);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    Twiddle t1 = tab(2 * m0 + 2 * g0 + h);
 #pragma unroll
-    for (int a = 0; a < 2; a++) bfly_fwd(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
+    for (int a = 0; a < 2; a++) bfly_fwd(x[4 * h + a], x[4 * h + a + 2], t1[h], q, two_q);
   }
 #pragma unroll
-  for (int h = 0; h < 4; h++) {
-    Twiddle t2 = tab(4 * m0 + 4 * g0 + h);
-    bfly_fwd(x[2 * h], x[2 * h + 1], t2, q, two_q);
-  }
+  for (int h = 0; h < 4; h++) bfly_fwd(x[2 * h], x[2 * h + 1], t2[h], q, two_q);
 }
 template <typename Tab>
 NTT_HD void radix8_inv(uint32_t (&x)[8], Tab tab, int m0, int g0, uint32_t q, uint32_t two_q) {
   // exact reverse order of radix8_fwd
+  Twiddle t1[2], t2[4];
+  tab.load4(4 * m0 + 4 * g0, t2);
+  tab.load2(2 * m0 + 2 * g0, t1);
 #pragma unroll
-  for (int h = 0; h < 4; h++) {
-    Twiddle t2 = tab(4 * m0 + 4 * g0 + h);
-    bfly_inv(x[2 * h], x[2 * h + 1], t2, q, two_q);
-  }
+  for (int h = 0; h < 4; h++) bfly_inv(x[2 * h], x[2 * h + 1], t2[h], q, two_q);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    Twiddle t1 = tab(2 * m0 + 2 * g0 + h);
 #pragma unroll
-    for (int a = 0; a < 2; a++) bfly_inv(x[4 * h + a], x[4 * h + a + 2], t1, q, two_q);
+    for (int a = 0; a < 2; a++) bfly_inv(x[4 * h + a], x[4 * h + a + 2], t1[h], q, two_q);
   }
   Twiddle t0 = tab(m0 + g0);
 #pragma unroll
@@ -145,39 +147,41 @@ NTT_HD void fwd_pass_c(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint3
   for (int a = 0; a < 8; a++) smem[ntt_phys(H * 32 + a * 4 + l2)] = x[a];
 }
 // Pass D (stages 9,10) on the contiguous layout e = tid*8 + k, then canonicalise.
-template <typename Tab>
+// CANON = false leaves the outputs in the lazy range [0, 4q) (saves the final correction; legal when the values
+// only feed a multiply-accumulate that is reduced mod q afterwards).
+template <bool CANON = true, typename Tab>
 NTT_HD void fwd_pass_d(int tid, uint32_t (&x)[8], const uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
   int base = ntt_phys(tid * 8);                                         // 8 contiguous words (two 16-byte chunks)
 #pragma unroll
   for (int k = 0; k < 8; k++) x[k] = smem[base + k];
+  Twiddle t9[2], t10[4];
+  tab.load2(512 + 2 * tid, t9);
+  tab.load4(1024 + 4 * tid, t10);
 #pragma unroll
   for (int h = 0; h < 2; h++) {                                         // stage 9: m=512, group = 2*tid + h, pairs (k, k+2)
-    Twiddle t = tab(512 + 2 * tid + h);
-    bfly_fwd(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
-    bfly_fwd(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
+    bfly_fwd(x[4 * h + 0], x[4 * h + 2], t9[h], q, two_q);
+    bfly_fwd(x[4 * h + 1], x[4 * h + 3], t9[h], q, two_q);
   }
 #pragma unroll
-  for (int h = 0; h < 4; h++) {                                         // stage 10: m=1024, group = 4*tid + h
-    Twiddle t = tab(1024 + 4 * tid + h);
-    bfly_fwd(x[2 * h], x[2 * h + 1], t, q, two_q);
-  }
+  for (int h = 0; h < 4; h++) bfly_fwd(x[2 * h], x[2 * h + 1], t10[h], q, two_q);   // stage 10: m=1024, group = 4*tid + h
+  if (CANON) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) x[k] = ntt_canon(x[k], q, two_q);
+    for (int k = 0; k < 8; k++) x[k] = ntt_canon(x[k], q, two_q);
+  }
 }
 
 // Inverse: contiguous layout in (values in [0,2q)), strided layout out (canonical).
 template <typename Tab>
 NTT_HD void inv_pass_d(int tid, uint32_t (&x)[8], uint32_t* smem, Tab tab, uint32_t q, uint32_t two_q) {
+  Twiddle t9[2], t10[4];
+  tab.load4(1024 + 4 * tid, t10);
+  tab.load2(512 + 2 * tid, t9);
 #pragma unroll
-  for (int h = 0; h < 4; h++) {                                         // stage mm=10
-    Twiddle t = tab(1024 + 4 * tid + h);
-    bfly_inv(x[2 * h], x[2 * h + 1], t, q, two_q);
-  }
+  for (int h = 0; h < 4; h++) bfly_inv(x[2 * h], x[2 * h + 1], t10[h], q, two_q);   // stage mm=10
 #pragma unroll
   for (int h = 0; h < 2; h++) {                                         // stage mm=9
-    Twiddle t = tab(512 + 2 * tid + h);
-    bfly_inv(x[4 * h + 0], x[4 * h + 2], t, q, two_q);
-    bfly_inv(x[4 * h + 1], x[4 * h + 3], t, q, two_q);
+    bfly_inv(x[4 * h + 0], x[4 * h + 2], t9[h], q, two_q);
+    bfly_inv(x[4 * h + 1], x[4 * h + 3], t9[h], q, two_q);
   }
   int base = ntt_phys(tid * 8);
 #pragma unroll
@@ -217,7 +221,7 @@ NTT_HD void inv_pass_a(int tid, uint32_t (&x)[8], const uint32_t* smem, Tab tab,
 // before the next transform reuses it (both functions start with that barrier themselves).
 // `lo` serves table indices 1..63 (passes A, B: thread-uniform / warp-uniform -> constant bank),
 // `hi` serves indices 64..2047 (passes C, D: per-thread -> shared memory or L1).
-template <typename Sync, typename TabLo, typename TabHi>
+template <bool CANON = true, typename Sync, typename TabLo, typename TabHi>
 __device__ __forceinline__ void ntt_forward_group(int tid, uint32_t (&x)[8], uint32_t* smem, TabLo lo, TabHi hi,
                                                   uint32_t q, Sync gsync) {
   const uint32_t two_q = 2 * q;
@@ -228,11 +232,11 @@ __device__ __forceinline__ void ntt_forward_group(int tid, uint32_t (&x)[8], uin
   gsync();
   fwd_pass_c(tid, x, smem, hi, q, two_q);
   gsync();
-  fwd_pass_d(tid, x, smem, hi, q, two_q);
+  fwd_pass_d<CANON>(tid, x, smem, hi, q, two_q);
 }
 // two independent transforms between the same barriers (instruction-level parallelism x2, half the
 // barriers per transform)
-template <typename Sync, typename TabLo, typename TabHi>
+template <bool CANON = true, typename Sync, typename TabLo, typename TabHi>
 __device__ __forceinline__ void ntt_forward_group2(int tid, uint32_t (&x0)[8], uint32_t (&x1)[8], uint32_t* smem0,
                                                    uint32_t* smem1, TabLo lo, TabHi hi, uint32_t q, Sync gsync) {
   const uint32_t two_q = 2 * q;
@@ -246,8 +250,8 @@ __device__ __forceinline__ void ntt_forward_group2(int tid, uint32_t (&x0)[8], u
   fwd_pass_c(tid, x0, smem0, hi, q, two_q);
   fwd_pass_c(tid, x1, smem1, hi, q, two_q);
   gsync();
-  fwd_pass_d(tid, x0, smem0, hi, q, two_q);
-  fwd_pass_d(tid, x1, smem1, hi, q, two_q);
+  fwd_pass_d<CANON>(tid, x0, smem0, hi, q, two_q);
+  fwd_pass_d<CANON>(tid, x1, smem1, hi, q, two_q);
 }
 template <typename Sync, typename TabLo, typename TabHi>
 __device__ __forceinline__ void ntt_inverse_group(int tid, uint32_t (&x)[8], uint32_t* smem, TabLo lo, TabHi hi,

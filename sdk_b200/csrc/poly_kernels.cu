@@ -23,16 +23,36 @@ __constant__ Twiddle c_tw_lo[2][2][64];     // [n][0 = forward, 1 = inverse][ind
 struct TwConst {
   int n, dir;
   __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo[n][dir][i]; }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const { t[0] = (*this)(i); t[1] = (*this)(i + 1); }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    t[0] = (*this)(i); t[1] = (*this)(i + 1); t[2] = (*this)(i + 2); t[3] = (*this)(i + 3);
+  }
 };
 struct TwShared {            // shared-memory copy of entries 64..2047
   const Twiddle* p;
   __device__ __forceinline__ Twiddle operator()(int i) const { return p[i - 64]; }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const {
+    uint4 v = *reinterpret_cast<const uint4*>(p + (i - 64));
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w};
+  }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    uint4 v = *reinterpret_cast<const uint4*>(p + (i - 64)), w = *(reinterpret_cast<const uint4*>(p + (i - 64)) + 1);
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w}; t[2] = Twiddle{w.x, w.y}; t[3] = Twiddle{w.z, w.w};
+  }
 };
 struct TwGlobal {            // straight from global memory through L1 (rarely used transforms)
   const Twiddle* p;
   __device__ __forceinline__ Twiddle operator()(int i) const {
     uint2 v = __ldg(reinterpret_cast<const uint2*>(p + i));
     return Twiddle{v.x, v.y};
+  }
+  __device__ __forceinline__ void load2(int i, Twiddle (&t)[2]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w};
+  }
+  __device__ __forceinline__ void load4(int i, Twiddle (&t)[4]) const {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i)), w = __ldg(reinterpret_cast<const uint4*>(p + i) + 1);
+    t[0] = Twiddle{v.x, v.y}; t[1] = Twiddle{v.z, v.w}; t[2] = Twiddle{w.x, w.y}; t[3] = Twiddle{w.z, w.w};
   }
 };
 
@@ -139,7 +159,8 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
         x0[a] = gadget_digit(v[a], k, bits, mask);
         x1[a] = gadget_digit(v[a], k + 1, bits, mask);
       }
-      ntt_forward_group2(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+      // lazy outputs (< 4q < 2^30): products < 2^58, so at most 63 of them fit one 64-bit accumulator
+      ntt_forward_group2<false>(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
       const uint32_t* c = c0 + (size_t)k * col_step;
 #pragma unroll
       for (int r = 0; r < ROWS; r++) {
@@ -152,7 +173,7 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
         for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
       }
       cnt += 2;
-      if (cnt >= 200) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+      if (cnt >= 60) { acc_reduce<ROWS>(acc, g); cnt = 1; }
     }
   }
 #pragma unroll 1
@@ -169,7 +190,7 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
 #pragma unroll
       for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x[e] * cv[e];
     }
-    if (++cnt >= 200) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+    if (++cnt >= 60) { acc_reduce<ROWS>(acc, g); cnt = 1; }
   }
 }
 
@@ -334,7 +355,8 @@ k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const ui
 // transforms, no CRT lift on the way out, and no v_folding_neg at all.
 // grid = (batch*half, 2 moduli), 256 threads.  in/out are distinct buffers (ping-pong): the CTA of
 // modulus n reads BOTH residues of its inputs (for the gadget digits) while the other CTA writes.
-__global__ void __launch_bounds__(256, 2)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
            const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -381,7 +403,7 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
         x0[a] = ntt_min(d0, d0 + q);           // negative differences wrap: add q
         x1[a] = ntt_min(d1, d1 + q);
       }
-      ntt_forward_group2(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
+      ntt_forward_group2<false>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         uint32_t cv[8];
@@ -400,7 +422,7 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
         uint32_t d0 = gadget_digit(vh[a], k, bits, mask) - gadget_digit(vi[a], k, bits, mask);
         x0[a] = ntt_min(d0, d0 + q);
       }
-      ntt_forward_group(g.tid, x0, sm0, lo, hi, q, CtaSync());
+      ntt_forward_group<false>(g.tid, x0, sm0, lo, hi, q, CtaSync());
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         uint32_t cv[8];
@@ -409,7 +431,8 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
         for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
       }
     }
-    // 2 * t_gsw <= 112 products of < 2^56 per accumulator in total: no overflow before the final reduction
+    // lazy NTT outputs (< 2^30): products < 2^58; t_gsw of them per rho -> reduce between the two rows when needed
+    if (rho == 0 && 2 * t_gsw > 60) acc_reduce<2>(acc, g);
   }
   uint32_t y0[8], y1[8];
 #pragma unroll
@@ -484,22 +507,37 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
   stage_fwd_twiddles(g, tw + g.n * HI_TW);
   uint32_t* vi = v + (size_t)i * 4 * POLY;
   uint32_t keep[2][8];
-  // from_ntt + automorph (poly.rs:393-405), scattered into shared memory
-#pragma unroll 1
-  for (int rho = 0; rho < 2; rho++) {
+  // row 0: from_ntt + automorph (poly.rs:393-405), scattered into shared memory for the gadget digits
+  {
     uint32_t x[8];
-    ld8(x, vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
+    ld8(x, vi + (size_t)g.n * POLY + g.tid * 8);
 #pragma unroll
-    for (int e = 0; e < 8; e++) keep[rho][e] = x[e];
+    for (int e = 0; e < 8; e++) keep[0][e] = x[e];
     grp_ntt_inv(g, x);
-    uint64_t* au = autom + rho * POLY;
     const int t_auto = R.t_auto;
     const uint64_t Q = P.modulus;
     crt_lift(x, res, g, P, [&](int z, uint64_t val) {
       unsigned prod = (unsigned)z * (unsigned)t_auto;
       unsigned num = prod >> NTT_LOG_N, rem = prod & (POLY - 1);
-      au[rem] = (num & 1u) ? Q - val : val;             // zero maps to q, as in the reference
+      autom[rem] = (num & 1u) ? Q - val : val;           // zero maps to q, as in the reference
     });
+  }
+  // row 1: the reference computes to_ntt(automorph(from_ntt(row 1))) (server.rs:80-88).  X -> X^t permutes the
+  // roots of X^N + 1, so in the NTT domain the automorphism is a pure permutation of the evaluation slots:
+  // slot s holds the value at psi^(2 br(s) + 1), and tau_t(a) there equals a at psi^((2 br(s) + 1) t).  The
+  // values are canonical residues either way, so the gathered vector is bit-identical to the reference's.
+  uint32_t y[8];
+  {
+    const uint32_t* row1 = vi + ((size_t)2 + g.n) * POLY;
+    ld8(keep[1], row1 + g.tid * 8);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const unsigned sidx = (unsigned)(g.tid * 8 + k);
+      const unsigned e = 2u * (__brev(sidx) >> (32 - NTT_LOG_N)) + 1u;
+      const unsigned e2 = (e * (unsigned)R.t_auto) & (2u * POLY - 1u);
+      const unsigned src = __brev((e2 - 1u) >> 1) >> (32 - NTT_LOG_N);
+      y[k] = row1[src];
+    }
   }
   __syncthreads();
   uint64_t acc[2][8];
@@ -516,10 +554,6 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
     const uint32_t* c0 = W + (size_t)g.n * POLY + g.tid * 8;
     digits_mac<2, true>(acc, cnt, vv, t_exp, bits, c0, (size_t)2 * POLY, (size_t)t_exp * 2 * POLY, g);
   }
-  uint32_t y[8];
-#pragma unroll
-  for (int a = 0; a < 8; a++) y[a] = barrett64(autom[POLY + a * 256 + g.tid], g.cr1, g.q);
-  grp_ntt_fwd<true>(g, y);
 #pragma unroll
   for (int rho = 0; rho < 2; rho++) {
     uint32_t o[8];
@@ -794,16 +828,22 @@ void launch_res_to_raw(const DevParams& P, uint64_t* out, const uint32_t* res, s
 }
 void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size_t batch, size_t batch_stride, int half,
                      const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
-                     cudaStream_t s) {
+                     int variant, cudaStream_t s) {
   if (batch == 0 || half == 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_fold_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
+    cudaFuncSetAttribute(k_fold_res<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
+    cudaFuncSetAttribute(k_fold_res<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
     attr_set = true;
   }
   ++g_kernel_launches;
-  k_fold_res<<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
-                                                                         c_batch_stride, slices_per_query, t_gsw, bits);
+  // variant 1: 3 CTAs per SM (80 registers, a few spills) instead of 2 (128 registers)
+  if (variant == 1)
+    k_fold_res<3><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
+                                                                              c_batch_stride, slices_per_query, t_gsw, bits);
+  else
+    k_fold_res<2><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
+                                                                              c_batch_stride, slices_per_query, t_gsw, bits);
 }
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);
