@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--mul-variant", type=int, default=0)
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
                     help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
-    ap.add_argument("--fold-variant", type=int, default=0)
+    ap.add_argument("--fold-variant", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

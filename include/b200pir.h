@@ -72,6 +72,10 @@ int b200pir_db_upload(b200pir_ctx* ctx, b200pir_db* db, const uint64_t* words, s
 /* One preprocessed item polynomial: 2048 packed words (lib/server/src/db/loading.rs:34-41 pack_ntt_poly,
  * :317-359 update_item_raw -> db.upsert(inst_trial*num_items + db_idx)); item_idx = j*num_per + ii. */
 int b200pir_db_upsert_item(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, uint64_t item_idx, const uint64_t* poly);
+/* lib/server/src/db/loading.rs:317-359 update_item_raw (the /write and /update-row path): `data` = the raw bucket bytes
+ * of item db_idx (at most instances*n^2*bytes_per_chunk, zero padded); chunk c becomes the item polynomial of slice c
+ * (convert_pt_to_poly :278-299: coefficient i = byte i, recenter_mod, NTT; pack_ntt_poly :34-41), all on the GPU. */
+int b200pir_db_update_item_raw(b200pir_ctx* ctx, b200pir_db* db, uint64_t db_idx, const uint8_t* data, size_t len);
 /* Synthetic database generated on the GPU: plaintext coefficient = splitmix64(seed, ((slice*items+item)*2048+z)) % p,
  * then recenter_mod / NTT / pack as generate_random_db_and_get_item does (server.rs:223-275). */
 int b200pir_db_fill_synthetic(b200pir_ctx* ctx, b200pir_db* db, uint64_t seed);

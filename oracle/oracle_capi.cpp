@@ -372,6 +372,12 @@ int orc_db_plain_item(void* h, uint64_t seed, uint64_t idx, uint64_t* out) {
   ORC_CATCH
 }
 uint64_t orc_splitmix64_at(uint64_t seed, uint64_t index) { return splitmix64_at(seed, index); }
+// lib/server/src/db/loading.rs:317-359: bucket bytes -> one packed item polynomial per slice
+int orc_update_item_raw(void* h, const uint8_t* data, size_t len, uint64_t* out) {
+  ORC_TRY
+  update_item_raw(*(Params*)h, data, len, out);
+  ORC_CATCH
+}
 
 // ---- DoublePIR
 int orc_dpir_matvec_packed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols) {

@@ -351,4 +351,22 @@ inline void generate_db(const Params& p, u64 seed, u64* db /* [slices][z][ii][j]
   }
 }
 
+// lib/server/src/db/loading.rs:278-299 convert_pt_to_poly (+ :34-41 pack_ntt_poly) and :317-359 update_item_raw:
+// the bucket bytes are zero-padded to instances*n^2 chunks of bytes_per_chunk; chunk c becomes the item polynomial of
+// slice c (coefficient i = byte i, recentred mod q, NTT'd, packed lo | hi << 32).  out: [slices][poly_len].
+inline void update_item_raw(const Params& p, const uint8_t* data, size_t len, u64* out) {
+  if (log2_ceil(p.pt_modulus) != 8) throw std::runtime_error("convert_pt_to_poly asserts logp == 8");
+  size_t chunks = p.instances * p.n * p.n, pt_len = p.bytes_per_chunk(), N = p.poly_len;
+  if (len > chunks * pt_len) throw std::runtime_error("update too long");
+  if (pt_len > N) throw std::runtime_error("chunk longer than poly_len");
+  std::vector<uint8_t> bucket(chunks * pt_len, 0);
+  std::memcpy(bucket.data(), data, len);
+  for (size_t c = 0; c < chunks; c++) {
+    PolyMatrix item = raw_zero(p, 1, 1);
+    for (size_t i = 0; i < pt_len; i++) item.data[i] = recenter_mod(bucket[c * pt_len + i], p.pt_modulus, p.modulus);
+    PolyMatrix nt = to_ntt_alloc(p, item);
+    for (size_t z = 0; z < N; z++) out[c * N + z] = nt.data[z] | (nt.data[N + z] << 32);
+  }
+}
+
 }  // namespace orc

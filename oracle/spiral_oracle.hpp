@@ -43,7 +43,8 @@ inline u64 multiply_uint_mod(u64 a, u64 b, u64 m) { return (u64)(((u128)a * b) %
 // arith.rs:9-11
 inline u64 log2_floor(u64 a) { return 63 - __builtin_clzll(a); }
 // arith.rs:13-19 (f64 ceil(log2)); exact for the integer ranges used here
-inline u64 log2_ceil(u64 a) { return (u64)std::ceil(std::log2((double)a)); }
+// (Rust's `f64 as usize` saturates: log2(0) = -inf -> 0)
+inline u64 log2_ceil(u64 a) { return a == 0 ? 0 : (u64)std::ceil(std::log2((double)a)); }
 // arith.rs:41-67
 inline u64 exponentiate_uint_mod(u64 operand, u64 exponent, u64 m) {
   u64 result = 1 % m, base = operand % m;

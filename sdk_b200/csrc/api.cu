@@ -127,7 +127,7 @@ struct b200pir_ctx {
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
-  int fold_variant = 0;
+  int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
@@ -673,6 +673,34 @@ int b200pir_db_upsert_item(b200pir_ctx* c, b200pir_db* db, uint64_t slice, uint6
   B200_CUDA(cudaStreamSynchronize(c->stream));
   API_END
 }
+int b200pir_db_update_item_raw(b200pir_ctx* c, b200pir_db* db, uint64_t db_idx, const uint8_t* data, size_t len) {
+  API_BEGIN
+  if (!c || (!data && len)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  const auto& hp = c->hp;
+  if (hp.p != 256) throw Error(B200PIR_E_UNSUPPORTED, "convert_pt_to_poly asserts logp == 8 (loading.rs:291)");
+  const size_t chunks = (size_t)c->slices;
+  const size_t pt_len = (hp.db_item_size + chunks - 1) / chunks;            // params.bytes_per_chunk()
+  if (pt_len > (size_t)POLY) throw Error(B200PIR_E_SHAPE, "bytes_per_chunk exceeds poly_len");
+  if (len > chunks * pt_len) throw Error(B200PIR_E_SHAPE, "update longer than instances*n^2*bytes_per_chunk");   // loading.rs:308-310
+  if (db_idx >= (uint64_t)c->dim0 * c->num_per) throw Error(B200PIR_E_SHAPE, "bad db idx");                      // loading.rs:333-340
+  const int ii = (int)(db_idx % c->num_per), j = (int)(db_idx / c->num_per);
+  if (ii % db->shard.count != db->shard.index) return 0;                      // row lives on another GPU
+  DevBuf<uint8_t> bucket(chunks * pt_len);
+  DevBuf<uint64_t> polys(chunks * POLY);
+  B200_CUDA(cudaMemsetAsync(bucket.p, 0, bucket.n, c->stream));
+  if (len) B200_CUDA(cudaMemcpyAsync(bucket.p, data, len, cudaMemcpyHostToDevice, c->stream));
+  launch_item_from_bytes(c->dp, bucket.p, (int)chunks, (int)pt_len, hp.p, polys.p, c->stream);
+  for (size_t s = 0; s < chunks; s++) {
+    if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
+    else launch_db_upsert_frag(db->F, db->f.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
+  }
+  B200_CUDA(cudaStreamSynchronize(c->stream));                                // writers hold the host write lock
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
 int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
   API_BEGIN
   if (!c) throw Error(B200PIR_E_BADARG, "null ctx");

@@ -54,6 +54,9 @@ void launch_db_retile_chunk(const MulGeom& G, Shard sh, uint4* db_dev_slice, con
                             cudaStream_t s);
 // one item poly (2048 packed words, lo|hi<<32) -> its place in db_dev   (lib/server db/loading.rs:317-359)
 void launch_db_upsert(const MulGeom& G, uint4* db_dev, int slice, int il, int j, const uint64_t* poly, cudaStream_t s);
+// lib/server db/loading.rs:278-299,34-41: `chunks` chunks of pt_len bytes -> packed item polynomials [chunks][2048]
+void launch_item_from_bytes(const DevParams& P, const uint8_t* bucket, int chunks, int pt_len, uint64_t pt_modulus,
+                            uint64_t* out, cudaStream_t s);
 // synthetic DB: plaintext coeff = splitmix64(seed, ((slice*items + item)*2048 + z)) % p, recentred, NTT'd, packed
 // (server.rs:223-275 with a counter PRNG; item = j*num_per_global + ii)
 void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_dev, uint64_t seed, uint64_t pt_modulus,

@@ -206,6 +206,31 @@ k_db_synth(DevParams P, MulGeom G, Shard sh, uint4* db, uint64_t seed, uint64_t 
   for (int z = threadIdx.x; z < POLY; z += 512) dst[z] = c4[z];
 }
 
+// lib/server/src/db/loading.rs:278-299 convert_pt_to_poly + :34-41 pack_ntt_poly for every chunk of one bucket:
+// chunk c (pt_len bytes of `bucket`, zero padded) -> out[c][z] = ntt(coeffs).lo | .hi << 32.  grid = chunks, 512 threads.
+__global__ void __launch_bounds__(512, 1)
+k_item_from_bytes(DevParams P, const uint8_t* __restrict__ bucket, int pt_len, uint64_t pt, uint64_t* __restrict__ out) {
+  __shared__ __align__(16) uint32_t ntt_smem[2 * NTT_SMEM_WORDS];
+  __shared__ uint32_t halves[2][POLY];
+  const int n = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  const uint32_t q = n ? P.q[1] : P.q[0];
+  const uint8_t* src = bucket + (size_t)blockIdx.x * pt_len;
+  struct S { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+  uint32_t x[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int i = a * 256 + tid;
+    const uint64_t v = i < pt_len ? (uint64_t)src[i] : 0;
+    x[a] = (v > pt / 2) ? (uint32_t)(q - (uint32_t)(pt - v)) : (uint32_t)v;       // recenter_mod, then mod q_n
+  }
+  ntt_forward_group(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());
+#pragma unroll
+  for (int k = 0; k < 8; k++) halves[n][tid * 8 + k] = x[k];
+  __syncthreads();
+  for (int z = threadIdx.x; z < POLY; z += 512)
+    out[(size_t)blockIdx.x * POLY + z] = (uint64_t)halves[0][z] | ((uint64_t)halves[1][z] << 32);
+}
+
 // ------------------------------------------------------------------ DoublePIR
 // out[i] = sum_k sum_{m<3} ((a[i][k] >> 10m) & 1023) * b[3k+m]   (wrapping u32; kernels.rs:52-93)
 // One warp per ROWS rows; lanes stride over k.  b is staged in shared memory as three planes
@@ -357,6 +382,11 @@ void launch_db_retile_chunk(const MulGeom& G, Shard sh, uint4* db_dev_slice, con
 void launch_db_upsert(const MulGeom& G, uint4* db_dev, int slice, int il, int j, const uint64_t* poly, cudaStream_t s) {
   ++g_kernel_launches;
   k_db_upsert<<<POLY / 256, 256, 0, s>>>(G, db_dev, slice, il, j, poly);
+}
+void launch_item_from_bytes(const DevParams& P, const uint8_t* bucket, int chunks, int pt_len, uint64_t pt_modulus,
+                            uint64_t* out, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_item_from_bytes<<<chunks, 512, 0, s>>>(P, bucket, pt_len, pt_modulus, out);
 }
 void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_dev, uint64_t seed, uint64_t pt_modulus,
                      int slice_begin, int slice_count, cudaStream_t s) {

@@ -116,6 +116,11 @@ class Database:
             raise ValueError("item polynomial must have 2048 packed words")
         check(LIB.b200pir_db_upsert_item(self.params._h, self._h, slice_idx, item_idx, _ptr(poly)))
 
+    def update_item_raw(self, db_idx, data):
+        """lib/server/src/db/loading.rs:317-359: write the raw bucket bytes of item db_idx."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        check(LIB.b200pir_db_update_item_raw(self.params._h, self._h, db_idx, data.ctypes.data, data.size))
+
     def fill_synthetic(self, seed):
         check(LIB.b200pir_db_fill_synthetic(self.params._h, self._h, seed))
 

@@ -280,6 +280,13 @@ class Params:
         _ck(LIB.orc_generate_db(self.hp, C.c_uint64(seed), _p64(db)))
         return db
 
+    def update_item_raw(self, data):
+        """lib/server db/loading.rs:317-359: bucket bytes -> [slices][2048] packed item polynomials."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(self.slices * self.N, dtype=np.uint64)
+        _ck(LIB.orc_update_item_raw(self.hp, _p8(data), C.c_size_t(data.size), _p64(out)))
+        return out
+
     def db_plain_item(self, seed, idx):
         out = np.zeros(self.instances * self.n * self.n * self.N, dtype=np.uint64)
         _ck(LIB.orc_db_plain_item(self.hp, C.c_uint64(seed), C.c_uint64(idx), _p64(out)))

@@ -549,3 +549,65 @@ def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
         assert np.array_equal(got[k], ref), (name, world, k)
     for sh in shards:
         sh.close()
+
+
+# ------------------------------------------------------------------ /write path: raw bucket bytes -> HBM (lib/server db/loading.rs)
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_update_item_raw_bytes_roundtrip(fmt):
+    """update_item_raw (loading.rs:317-359) on the GPU == oracle's packed item polynomials, and a private read of the
+    written items returns the written bytes (what e2e-tests/tests/simple.ts checks through the HTTP server)."""
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    rng = np.random.default_rng(21)
+    wdb = S.Database(G, fmt=fmt)
+    G.set_option("db_format", 0)
+    sparse = np.zeros((P.slices, P.N, P.num_per, P.dim0), dtype=np.uint64)
+    written = {}
+    for idx, nbytes in ((7, P.db_item_size), (200, 100), (P.dim0 * P.num_per - 1, 1), (31, 0)):
+        data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        wdb.update_item_raw(idx, data)
+        polys = P.update_item_raw(data).reshape(P.slices, P.N)
+        sparse[:, :, idx % P.num_per, idx // P.num_per] = polys
+        written[idx] = data
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    for s in range(P.slices):
+        assert np.array_equal(S.multiply_reg_by_database(G, wdb, s, v),
+                              P.multiply_reg_by_database(np.ascontiguousarray(sparse[s]).reshape(-1), v))
+    pt_len = P.bytes_per_chunk
+    for idx, data in written.items():
+        q = cl.generate_query(idx)
+        resp = S.process_query(G, gpp, S.Query(ct=q["ct"]), wdb)
+        dec = cl.decode_response(resp).reshape(P.slices, P.N)        # (instance*n + trial/n, trial%n) row-major == slice order
+        got = dec[:, :pt_len].astype(np.uint8).reshape(-1)
+        exp = np.zeros(P.slices * pt_len, dtype=np.uint8)
+        exp[: data.size] = data
+        assert np.array_equal(got, exp), idx
+    with pytest.raises(S.B200PirError):
+        wdb.update_item_raw(0, np.zeros(P.slices * pt_len + 1, dtype=np.uint8))      # InvalidLength (loading.rs:308-310)
+    with pytest.raises(S.B200PirError):
+        wdb.update_item_raw(P.dim0 * P.num_per, np.zeros(4, dtype=np.uint8))         # bad db idx (loading.rs:333-340)
+    wdb.close()
+
+
+# ------------------------------------------------------------------ degenerate second dimension (server.rs:554-577, :394-396)
+@pytest.mark.parametrize("nu_2", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_small_second_dimension(nu_2, fmt):
+    S = _gpu()
+    kw = dict(O.PARAM_SETS["T"])
+    kw.update(nu_2=nu_2)
+    P = O.Params(**kw)
+    cl = O.Client(P, 77)
+    pp = cl.generate_keys()
+    db = P.generate_db(SEED_DB)
+    G = S.Params(**kw)
+    gdb = S.Database.from_words(G, db, fmt=fmt)
+    gpp = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
+    for idx in (0, P.dim0 * P.num_per - 1, 17):
+        q = cl.generate_query(idx)
+        ref = P.process_query(pp, q, db)
+        got = S.process_query(G, gpp, S.Query(ct=q["ct"]), gdb)
+        assert np.array_equal(got, ref), (nu_2, fmt, idx)
+        assert np.array_equal(cl.decode_response(got), P.db_plain_item(SEED_DB, idx))
+    for h in (gdb, gpp, G):
+        h.close()
