@@ -174,6 +174,16 @@ int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream);
 /* b: 3*cols u32 ; out: rows u32 */
 int b200pir_dpir_matvec_packed(b200pir_dpir* m, const uint32_t* b, uint32_t* out);
 int b200pir_dpir_matvec_packed_dev(b200pir_dpir* m, const uint32_t* b_dev, uint32_t* out_dev, int variant);
+/* same over the row range [row_begin, row_begin+row_count): answer()'s `db.rows(start, batch)` (doublepir.rs:301) */
+int b200pir_dpir_matvec_packed_rows(b200pir_dpir* m, uint64_t row_begin, uint64_t row_count, const uint32_t* b, uint32_t* out);
+/* The small tail of answer() (doublepir.rs:317-349), host buffers:
+ * matrix_mul_transposed_packed (kernels.rs:180-278): out (a_rows x b_rows); b_cols must be 3*a_cols.
+ * transpose_expand_concat_cols_squish (matrix/indexing.rs:117-143, basis 10, d 3): out (cols*delta*concat) x ceil((rows/concat)/3). */
+int b200pir_dpir_matrix_mul_transposed_packed(int device, const uint32_t* a, uint64_t a_rows, uint64_t a_cols, const uint32_t* b,
+                                              uint64_t b_rows, uint64_t b_cols, uint32_t* out);
+int b200pir_dpir_transpose_expand_concat_cols_squish(int device, const uint32_t* a, uint64_t rows, uint64_t cols, uint64_t modulus,
+                                                     uint64_t delta, uint64_t concat, uint32_t* out, uint64_t* out_rows,
+                                                     uint64_t* out_cols);
 
 #ifdef __cplusplus
 }

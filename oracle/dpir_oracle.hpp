@@ -44,4 +44,39 @@ inline void matrix_mul_vec_packed(uint32_t* out, const uint32_t* a, const uint32
   std::memcpy(out, o.data(), rows * 4);
 }
 
+// kernels.rs:180-278 matrix_mul_transposed_packed: out[i][j] = sum_k sum_m ((a[i][k] >> 10m) & 1023) * b[j][3k+m]
+// (both loop orders of the reference compute this; wrapping u32)
+inline void matrix_mul_transposed_packed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t a_rows, size_t a_cols,
+                                         size_t b_rows, size_t b_cols) {
+  for (size_t i = 0; i < a_rows; i++)
+    for (size_t j = 0; j < b_rows; j++) {
+      uint32_t tmp = 0;
+      for (size_t k = 0; k < a_cols; k++) {
+        uint32_t db = a[i * a_cols + k];
+        for (unsigned m = 0; m < COMPRESSION; m++) tmp += ((db >> (m * BASIS)) & MASK) * b[j * b_cols + k * COMPRESSION + m];
+      }
+      out[i * b_rows + j] = tmp;
+    }
+}
+
+// matrix/indexing.rs:117-143 transpose_expand_concat_cols_squish.  out: (cols*delta*concat) x ceil((rows/concat)/d)
+inline void transpose_expand_concat_cols_squish(std::vector<uint32_t>& out, size_t& out_rows, size_t& out_cols,
+                                                const uint32_t* a, size_t rows, size_t cols, uint64_t modulus, size_t delta,
+                                                size_t concat, uint64_t basis, size_t d) {
+  out_rows = cols * delta * concat;
+  out_cols = (rows / concat + d - 1) / d;
+  out.assign(out_rows * out_cols, 0);
+  for (size_t j = 0; j < rows; j++)
+    for (size_t i = 0; i < cols; i++) {
+      uint64_t val = a[i + j * cols];
+      for (size_t f = 0; f < delta; f++) {
+        uint64_t new_val = val % modulus;
+        size_t r = (i * delta + f) + cols * delta * (j % concat);
+        size_t c = j / concat;
+        out[r * out_cols + c / d] += (uint32_t)(new_val << (basis * (c % d)));
+        val /= modulus;
+      }
+    }
+}
+
 }  // namespace dpir

@@ -386,6 +386,23 @@ int orc_dpir_matvec_packed(uint32_t* out, const uint32_t* a, const uint32_t* b, 
   ORC_CATCH
 }
 
+int orc_dpir_matrix_mul_transposed_packed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t a_rows, size_t a_cols,
+                                          size_t b_rows, size_t b_cols) {
+  ORC_TRY
+  dpir::matrix_mul_transposed_packed(out, a, b, a_rows, a_cols, b_rows, b_cols);
+  ORC_CATCH
+}
+// out must hold cols*delta*concat * ceil((rows/concat)/3) words
+int orc_dpir_transpose_expand_concat_cols_squish(uint32_t* out, const uint32_t* a, size_t rows, size_t cols, uint64_t modulus,
+                                                 size_t delta, size_t concat) {
+  ORC_TRY
+  std::vector<uint32_t> o;
+  size_t r, c;
+  dpir::transpose_expand_concat_cols_squish(o, r, c, a, rows, cols, modulus, delta, concat, 10, 3);
+  std::memcpy(out, o.data(), o.size() * 4);
+  ORC_CATCH
+}
+
 // ---- timing helper for the CPU baseline: runs fn-equivalent loops natively, returns seconds
 double orc_time_multiply(void* h, const uint64_t* db_slice, const uint64_t* v_firstdim, size_t dim0, size_t num_per,
                          uint64_t* out, int reps) {

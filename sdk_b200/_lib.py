@@ -71,6 +71,12 @@ def _load():
         "b200pir_dpir_set_stream": (C.c_int, [vp, vp]),
         "b200pir_dpir_matvec_packed": (C.c_int, [vp, u32p, u32p]),
         "b200pir_dpir_matvec_packed_dev": (C.c_int, [vp, u32p, u32p, C.c_int]),
+        "b200pir_dpir_matvec_packed_rows": (C.c_int, [vp, C.c_uint64, C.c_uint64, u32p, u32p]),
+        "b200pir_dpir_matrix_mul_transposed_packed": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, u32p, C.c_uint64,
+                                                                 C.c_uint64, u32p]),
+        "b200pir_dpir_transpose_expand_concat_cols_squish": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                                        C.c_uint64, C.c_uint64, u32p, C.POINTER(C.c_uint64),
+                                                                        C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # raises AttributeError if the .so does not export a declared symbol

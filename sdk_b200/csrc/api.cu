@@ -1271,6 +1271,53 @@ int b200pir_dpir_matvec_packed_dev(b200pir_dpir* m, const uint32_t* b_dev, uint3
   B200_CUDA(cudaGetLastError());
   API_END
 }
+// matrix_mul_vec_packed over the row range [row_begin, row_begin + row_count)  (answer(): db.rows(start, batch), doublepir.rs:301)
+int b200pir_dpir_matvec_packed_rows(b200pir_dpir* m, uint64_t row_begin, uint64_t row_count, const uint32_t* b, uint32_t* out) {
+  API_BEGIN
+  if (!m || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  if (row_begin + row_count > m->rows) throw Error(B200PIR_E_SHAPE, "row range out of bounds");
+  if (row_count == 0) return 0;
+  cudaSetDevice(m->device);
+  B200_CUDA(cudaMemcpyAsync(m->b.p, b, 3 * m->cols * 4, cudaMemcpyHostToDevice, m->stream));
+  launch_dpir_matvec(m->out.p, m->a.p + row_begin * m->cols, m->b.p, row_count, m->cols, 0, m->stream);
+  B200_CUDA(cudaMemcpyAsync(out, m->out.p, row_count * 4, cudaMemcpyDeviceToHost, m->stream));
+  B200_CUDA(cudaStreamSynchronize(m->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_dpir_matrix_mul_transposed_packed(int device, const uint32_t* a, uint64_t a_rows, uint64_t a_cols, const uint32_t* b,
+                                              uint64_t b_rows, uint64_t b_cols, uint32_t* out) {
+  API_BEGIN
+  if (!a || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  if (b_cols != 3 * a_cols) throw Error(B200PIR_E_SHAPE, "b.cols must equal 3 * a.cols");
+  B200_CUDA(cudaSetDevice(device));
+  DevBuf<uint32_t> da(a_rows * a_cols), db_(b_rows * b_cols), dout(a_rows * b_rows);
+  B200_CUDA(cudaMemcpy(da.p, a, da.n * 4, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(db_.p, b, db_.n * 4, cudaMemcpyHostToDevice));
+  launch_dpir_mul_transposed(dout.p, da.p, db_.p, a_rows, a_cols, b_rows, b_cols, 0);
+  B200_CUDA(cudaMemcpy(out, dout.p, dout.n * 4, cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_dpir_transpose_expand_concat_cols_squish(int device, const uint32_t* a, uint64_t rows, uint64_t cols, uint64_t modulus,
+                                                     uint64_t delta, uint64_t concat, uint32_t* out, uint64_t* out_rows,
+                                                     uint64_t* out_cols) {
+  API_BEGIN
+  if (!a || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  if (modulus < 2 || modulus > 1024 || delta == 0 || concat == 0) throw Error(B200PIR_E_BADARG, "bad modulus / delta / concat");
+  if (rows % concat) throw Error(B200PIR_E_SHAPE, "rows must be a multiple of concat");
+  B200_CUDA(cudaSetDevice(device));
+  const uint64_t orows = cols * delta * concat, ocols = (rows / concat + 2) / 3;
+  DevBuf<uint32_t> da(rows * cols), dout(orows * ocols);
+  B200_CUDA(cudaMemcpy(da.p, a, da.n * 4, cudaMemcpyHostToDevice));
+  launch_dpir_transpose_expand(dout.p, da.p, rows, cols, modulus, delta, concat, orows, ocols, 0);
+  B200_CUDA(cudaMemcpy(out, dout.p, dout.n * 4, cudaMemcpyDeviceToHost));
+  if (out_rows) *out_rows = orows;
+  if (out_cols) *out_cols = ocols;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
 int b200pir_dpir_matvec_packed(b200pir_dpir* m, const uint32_t* b, uint32_t* out) {
   API_BEGIN
   if (!m || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");

@@ -134,4 +134,10 @@ void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uin
 void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols, int variant,
                         cudaStream_t s);
 
+// lib/doublepir/src/matrix/kernels.rs:180-278 and matrix/indexing.rs:117-143 (the small tail of answer())
+void launch_dpir_mul_transposed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t a_rows, size_t a_cols,
+                                size_t b_rows, size_t b_cols, cudaStream_t s);
+void launch_dpir_transpose_expand(uint32_t* out, const uint32_t* a, size_t rows, size_t cols, uint64_t modulus, size_t delta,
+                                  size_t concat, size_t out_rows, size_t out_cols, cudaStream_t s);
+
 }  // namespace b200pir

@@ -335,10 +335,57 @@ k_dpir_matvec_row(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, co
   }
 }
 
+// kernels.rs:180-278: out[i][j] = sum_k sum_m ((a[i][k] >> 10m) & 1023) * b[j][3k+m]   (one warp per output)
+__global__ void k_dpir_mul_transposed(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                      size_t a_rows, size_t a_cols, size_t b_rows, size_t b_cols) {
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a_rows * b_rows) return;
+  const size_t i = warp / b_rows, j = warp % b_rows;
+  uint32_t acc = 0;
+  for (size_t k = lane; k < a_cols; k += 32) {
+    uint32_t d = __ldg(a + i * a_cols + k);
+    const uint32_t* bp = b + j * b_cols + 3 * k;
+    acc += (d & 1023u) * __ldg(bp) + ((d >> 10) & 1023u) * __ldg(bp + 1) + ((d >> 20) & 1023u) * __ldg(bp + 2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[i * b_rows + j] = acc;
+}
+// matrix/indexing.rs:117-143 (basis 10, d 3): one thread per output word
+__global__ void k_dpir_transpose_expand(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, size_t rows, size_t cols,
+                                        uint64_t modulus, size_t delta, size_t concat, size_t out_rows, size_t out_cols) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= out_rows * out_cols) return;
+  const size_t r = idx / out_cols, cd = idx % out_cols;
+  const size_t jmod = r / (cols * delta), rem = r % (cols * delta), i = rem / delta, f = rem % delta;
+  uint32_t acc = 0;
+  for (size_t cc = 0; cc < 3; cc++) {
+    const size_t c = cd * 3 + cc, j = c * concat + jmod;
+    if (j < rows) {
+      uint64_t val = a[i + j * cols];
+      for (size_t t = 0; t < f; t++) val /= modulus;
+      acc += (uint32_t)((val % modulus) << (10 * cc));
+    }
+  }
+  out[idx] = acc;
+}
+
 inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + block - 1) / block); }
 
 }  // namespace
 
+void launch_dpir_mul_transposed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t a_rows, size_t a_cols,
+                                size_t b_rows, size_t b_cols, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_dpir_mul_transposed<<<grid1d(a_rows * b_rows * 32, 256), 256, 0, s>>>(out, a, b, a_rows, a_cols, b_rows, b_cols);
+}
+void launch_dpir_transpose_expand(uint32_t* out, const uint32_t* a, size_t rows, size_t cols, uint64_t modulus, size_t delta,
+                                  size_t concat, size_t out_rows, size_t out_cols, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_dpir_transpose_expand<<<grid1d(out_rows * out_cols, 256), 256, 0, s>>>(out, a, rows, cols, modulus, delta, concat,
+                                                                           out_rows, out_cols);
+}
 void upload_mul_constants(const Twiddle* lo) {
   B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_mul, lo, sizeof(Twiddle) * 2 * 2 * 64));
 }

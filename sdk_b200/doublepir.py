@@ -39,3 +39,56 @@ def matrix_mul_vec_packed(a, b, basis=10, compression=3):
     out = np.zeros(a.rows, dtype=np.uint32)
     check(LIB.b200pir_dpir_matvec_packed(a._h, b.ctypes.data, out.ctypes.data))
     return out
+
+
+def matrix_mul_vec_packed_rows(a, row_begin, row_count, b):
+    """matrix_mul_vec_packed(db.rows(start, n), q) (doublepir.rs:301)."""
+    out = np.zeros(row_count, dtype=np.uint32)
+    check(LIB.b200pir_dpir_matvec_packed_rows(a._h, row_begin, row_count, b.ctypes.data, out.ctypes.data))
+    return out
+
+
+def matrix_mul_transposed_packed(a, a_rows, a_cols, b, b_rows, b_cols, basis=10, compression=3, device=0):
+    """kernels.rs:256-278."""
+    assert basis == 10 and compression == 3
+    out = np.zeros(a_rows * b_rows, dtype=np.uint32)
+    check(LIB.b200pir_dpir_matrix_mul_transposed_packed(device, a.ctypes.data, a_rows, a_cols, b.ctypes.data, b_rows, b_cols,
+                                                        out.ctypes.data))
+    return out
+
+
+def transpose_expand_concat_cols_squish(a, rows, cols, modulus, delta, concat, basis=10, d=3, device=0):
+    """matrix/indexing.rs:117-143 -> (out, out_rows, out_cols)."""
+    assert basis == 10 and d == 3
+    orows, ocols = cols * delta * concat, (rows // concat + 2) // 3
+    out = np.zeros(orows * ocols, dtype=np.uint32)
+    r, c = C.c_uint64(), C.c_uint64()
+    check(LIB.b200pir_dpir_transpose_expand_concat_cols_squish(device, a.ctypes.data, rows, cols, modulus, delta, concat,
+                                                               out.ctypes.data, C.byref(r), C.byref(c)))
+    return out, r.value, c.value
+
+
+def answer(db, queries, h_1, a_2_transpose, p, delta, x, ne):
+    """DoublePIR server answer (doublepir.rs:246-350, raw_data = None, chunk_idx = None).
+    db: PackedMatrix; queries: list of [q_1, q_2, ...]; h_1 / a_2_transpose: (array, rows, cols)."""
+    nq = len(queries)
+    batch = db.rows // nq
+    parts, last = [], 0
+    for b, q in enumerate(queries):
+        bs = db.rows - last if b == nq - 1 else batch
+        parts.append(matrix_mul_vec_packed_rows(db, last, bs, q[0]))
+        last += bs
+    a_1 = np.concatenate(parts)
+    a_1, r1, c1 = transpose_expand_concat_cols_squish(a_1, db.rows, 1, p, delta, x)
+    a2, a2_rows, a2_cols = a_2_transpose
+    msg = [matrix_mul_transposed_packed(a_1, r1, c1, a2, a2_rows, a2_cols)]
+    h, h_rows, h_cols = h_1
+    hm = PackedMatrix(h, h_rows, h_cols)
+    am = PackedMatrix(a_1, r1, c1)
+    for q in queries:
+        for j in range(ne // x):
+            msg.append(matrix_mul_vec_packed(hm, q[1 + j]))
+            msg.append(matrix_mul_vec_packed(am, q[1 + j]))
+    hm.close()
+    am.close()
+    return msg

@@ -344,3 +344,37 @@ def dpir_matvec_packed(a, b, rows, cols):
     out = np.zeros(rows, dtype=np.uint32)
     _ck(LIB.orc_dpir_matvec_packed(_p32(out), _p32(a), _p32(b), C.c_size_t(rows), C.c_size_t(cols)))
     return out
+
+
+def dpir_matrix_mul_transposed_packed(a, b, a_rows, a_cols, b_rows, b_cols):
+    out = np.zeros(a_rows * b_rows, dtype=np.uint32)
+    _ck(LIB.orc_dpir_matrix_mul_transposed_packed(_p32(out), _p32(a), _p32(b), C.c_size_t(a_rows), C.c_size_t(a_cols),
+                                                  C.c_size_t(b_rows), C.c_size_t(b_cols)))
+    return out
+
+
+def dpir_transpose_expand_concat_cols_squish(a, rows, cols, modulus, delta, concat):
+    out_rows, out_cols = cols * delta * concat, (rows // concat + 2) // 3
+    out = np.zeros(out_rows * out_cols, dtype=np.uint32)
+    _ck(LIB.orc_dpir_transpose_expand_concat_cols_squish(_p32(out), _p32(a), C.c_size_t(rows), C.c_size_t(cols),
+                                                         C.c_uint64(modulus), C.c_size_t(delta), C.c_size_t(concat)))
+    return out, out_rows, out_cols
+
+
+def dpir_answer(db, db_rows, db_cols, queries, h_1, h1_rows, h1_cols, a2t, a2t_rows, a2t_cols, p, delta, x, ne):
+    """doublepir.rs:246-350 (raw_data = None, chunk_idx = None).  queries: list of [q_1, q_2...] uint32 arrays."""
+    nq = len(queries)
+    batch = db_rows // nq
+    parts, last = [], 0
+    for b, q in enumerate(queries):
+        bs = db_rows - last if b == nq - 1 else batch
+        parts.append(dpir_matvec_packed(np.ascontiguousarray(db[last * db_cols:(last + bs) * db_cols]), q[0], bs, db_cols))
+        last += bs
+    a_1 = np.concatenate(parts)
+    a_1, r1, c1 = dpir_transpose_expand_concat_cols_squish(a_1, db_rows, 1, p, delta, x)
+    msg = [dpir_matrix_mul_transposed_packed(a_1, a2t, r1, c1, a2t_rows, a2t_cols)]
+    for q in queries:
+        for j in range(ne // x):
+            msg.append(dpir_matvec_packed(h_1, q[1 + j], h1_rows, h1_cols))
+            msg.append(dpir_matvec_packed(a_1, q[1 + j], r1, c1))
+    return msg

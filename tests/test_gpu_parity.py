@@ -611,3 +611,34 @@ def test_small_second_dimension(nu_2, fmt):
         assert np.array_equal(cl.decode_response(got), P.db_plain_item(SEED_DB, idx))
     for h in (gdb, gpp, G):
         h.close()
+
+
+# ------------------------------------------------------------------ DoublePIR answer() tail
+def test_dpir_answer_matches_oracle():
+    import sdk_b200.doublepir as D
+    rng = np.random.default_rng(31)
+    L, cols = 96, 50                   # database: 96 rows x 50 packed words (150 Z_p columns)
+    p, delta, x, ne = 991, 4, 2, 4     # transpose_expand: a_1 -> (1*4*2) x ceil(48/3) = 8 x 16
+    db = rng.integers(0, 2**30, L * cols, dtype=np.uint32)
+    r1, c1 = delta * x, (L // x + 2) // 3
+    h_rows = 20
+    h_1 = rng.integers(0, 2**30, h_rows * c1, dtype=np.uint32)
+    a2_rows, a2_cols = 10, 3 * c1
+    a2t = rng.integers(0, 2**32, a2_rows * a2_cols, dtype=np.uint32)
+    queries = []
+    for _ in range(2):
+        q = [rng.integers(0, 2**32, 3 * cols, dtype=np.uint32)]
+        q += [rng.integers(0, 2**32, 3 * c1, dtype=np.uint32) for _ in range(ne // x)]
+        queries.append(q)
+    ref = O.dpir_answer(db, L, cols, queries, h_1, h_rows, c1, a2t, a2_rows, a2_cols, p, delta, x, ne)
+    m = D.PackedMatrix(db, L, cols)
+    got = D.answer(m, queries, (h_1, h_rows, c1), (a2t, a2_rows, a2_cols), p, delta, x, ne)
+    assert len(got) == len(ref) == 1 + 2 * 2 * (ne // x)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+    # stand-alone pieces on awkward shapes
+    a = rng.integers(0, 2**32, 35 * 3, dtype=np.uint32)
+    out, orows, ocols = D.transpose_expand_concat_cols_squish(a, 35, 3, 1000, 3, 5)
+    ref2, rr, rc = O.dpir_transpose_expand_concat_cols_squish(a, 35, 3, 1000, 3, 5)
+    assert (orows, ocols) == (rr, rc) and np.array_equal(out, ref2)
+    m.close()
