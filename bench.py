@@ -47,6 +47,9 @@ WORKLOADS = {
     "S8": S8,                                     # 8 GiB HBM-resident = 1 GiB plaintext (configs[1])
     "S1": dict(n=2, nu_1=9, nu_2=5, p=256, q2_bits=22, t_gsw=7, t_conv=3, t_exp_left=5, t_exp_right=5, instances=1,
                db_item_size=8192, version=1),     # 1 GiB HBM-resident
+    # configs[2]: 32 GiB plaintext = 256 GiB of packed words, row-sharded over 8 GPUs (32 GiB per GPU)
+    "S256": dict(n=2, nu_1=10, nu_2=12, p=256, q2_bits=22, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1,
+                 db_item_size=8192, version=0),
     "T": dict(n=2, nu_1=6, nu_2=2, p=256, q2_bits=20, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1,
               db_item_size=8192, version=0),      # unit-test size (CI smoke of this script)
 }
@@ -262,7 +265,8 @@ def main():
     kw = dict(WORKLOADS[name])
     import math
     base_name = {"S8": "S8: Spiral 2^20 x 1 KiB records (2^17 items x 8 KiB), 1 GiB plaintext = 8 GiB HBM-resident",
-                 "S1": "S1: 1 GiB HBM-resident (2^14 items x 8 KiB)", "T": "T: unit-test size"}[name]
+                 "S1": "S1: 1 GiB HBM-resident (2^14 items x 8 KiB)", "T": "T: unit-test size",
+                 "S256": "S256: Spiral 2^25 x 1 KiB records (2^22 items x 8 KiB), 32 GiB plaintext = 256 GiB HBM-resident"}[name]
     if N > 1:
         if N & (N - 1):
             raise SystemExit("--gpus must be a power of two")
