@@ -163,6 +163,7 @@ def cpu_process_query_sample(kw, threads=None, sample_rows=64):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib as O
+    simd = "AVX2 first dimension" if O.LIB.orc_use_avx2_multiply(1) else "scalar first dimension"
     if threads:
         O.LIB.orc_set_num_threads(int(threads))
     else:
@@ -199,16 +200,33 @@ def cpu_process_query_sample(kw, threads=None, sample_rows=64):
     t0 = time.perf_counter()
     Pfull.expand_query(pp_full, q["ct"])                       # full-size expansion (g rounds of the real config)
     t_expand_full = time.perf_counter() - t0
+    # the row-proportional part, timed directly on the sample slab: multiply + from_ntt + fold per slice, pack, encode
+    vreg, vf = P.expand_query(pp, q["ct"])
+    slice_words = P.dim0 * P.num_per * POLY
+    use_avx2 = simd.startswith("AVX2")
     t0 = time.perf_counter()
-    P.expand_query(pp, q["ct"])
-    t_expand_small = time.perf_counter() - t0
+    vfn = P.get_v_folding_neg(vf)
+    folded = []
+    for sl in range(P.slices):
+        dsl = db[sl * slice_words:(sl + 1) * slice_words]
+        if use_avx2:
+            mult = np.zeros(P.num_per * 4 * POLY, dtype=np.uint64)
+            O._ck(O.LIB.orc_multiply_reg_by_database_avx2(P.hp, O._p64(mult), O._p64(dsl), O._p64(vreg),
+                                                          O.C.c_size_t(P.dim0), O.C.c_size_t(P.num_per)))
+        else:
+            mult = P.multiply_reg_by_database(dsl, vreg)
+        raw = P.from_ntt(mult)
+        folded.append(P.fold_ciphertexts(raw, vf, vfn)[: 2 * POLY])
+    t_rows = time.perf_counter() - t0
     t0 = time.perf_counter()
-    P.process_query(pp, q, db)
-    t_small = time.perf_counter() - t0
-    row_part = max(t_small - t_expand_small, 0.0)
-    est = t_expand_full + row_part * (full_rows / rows)
-    sample = ("oracle process_query: full query expansion (%.2fs) + %d of %d second-dimension rows of every slice "
-              "(multiply+fold+pack %.2fs, scaled x%d)" % (t_expand_full, rows, full_rows, row_part, full_rows // rows))
+    nn = P.n * P.n
+    packed = [P.from_ntt(P.pack(np.concatenate(folded[i * nn:(i + 1) * nn]), pp["pack"])) for i in range(P.instances)]
+    P.encode(np.concatenate(packed))
+    t_tail = time.perf_counter() - t0
+    est = t_expand_full + t_rows * (full_rows / rows) + t_tail
+    sample = ("oracle process_query (" + simd + ", OpenMP): full query expansion (%.2fs) + %d of %d second-dimension "
+              "rows of every slice (multiply+from_ntt+fold %.2fs, scaled x%d) + pack/encode (%.3fs)"
+              % (t_expand_full, rows, full_rows, t_rows, full_rows // rows, t_tail))
     return est, cores, sample
 
 

@@ -403,6 +403,27 @@ int orc_dpir_transpose_expand_concat_cols_squish(uint32_t* out, const uint32_t* 
   ORC_CATCH
 }
 
+// CPU-baseline switch: 1 = AVX2 first-dimension kernel inside process_query (returns 0 when not compiled with AVX2)
+int orc_use_avx2_multiply(int on) {
+#if defined(__AVX2__)
+  g_use_avx2_multiply = on != 0;
+  return 1;
+#else
+  (void)on;
+  return 0;
+#endif
+}
+int orc_multiply_reg_by_database_avx2(void* h, uint64_t* out, const uint64_t* db_slice, const uint64_t* v_firstdim,
+                                      size_t dim0, size_t num_per) {
+  ORC_TRY
+#if defined(__AVX2__)
+  multiply_reg_by_database_avx2(*(Params*)h, out, db_slice, v_firstdim, dim0, num_per);
+#else
+  throw std::runtime_error("built without AVX2");
+#endif
+  ORC_CATCH
+}
+
 // ---- timing helper for the CPU baseline: runs fn-equivalent loops natively, returns seconds
 double orc_time_multiply(void* h, const uint64_t* db_slice, const uint64_t* v_firstdim, size_t dim0, size_t num_per,
                          uint64_t* out, int reps) {

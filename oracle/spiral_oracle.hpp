@@ -28,8 +28,15 @@
 #include <array>
 #include <stdexcept>
 #include <algorithm>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 namespace orc {
+
+// set by the CPU-baseline legs of bench.py: use the AVX2 first-dimension kernel inside process_query
+static bool g_use_avx2_multiply = false;
+
 
 typedef unsigned __int128 u128;
 typedef __int128 i128;
@@ -719,6 +726,47 @@ inline void regev_to_gsw(const Params& p, std::vector<PolyMatrix>& v_gsw, const 
   }
 }
 
+#if defined(__AVX2__)
+// AVX2 form of the same product, in the style of the reference's vectorised kernel
+// (lib/server/src/compute/dot_product.rs:59-96: _mm256_mul_epu32 + _mm256_add_epi64 on 4 words at a time), but with
+// an exact reduction schedule: every 64-bit lane is folded mod q_n before it can overflow (<= 256 products of < 2^56),
+// so it equals the u128 path for every input (the reference's counter-based schedule does not, SURVEY 7 "hazards").
+// Used only to give the CPU baseline the SIMD the reference builds with (.cargo/config.toml: target-cpu=native).
+inline void multiply_reg_by_database_avx2(const Params& p, u64* out, const u64* db, const u64* v_firstdim, size_t dim0,
+                                          size_t num_per) {
+  size_t N = p.poly_len;
+  const u64 q0 = p.moduli[0], q1 = p.moduli[1];
+#pragma omp parallel for schedule(static)
+  for (size_t z = 0; z < N; z++) {
+    const u64* a = v_firstdim + z * dim0 * 2;
+    const u64* b = db + z * num_per * dim0;
+    for (size_t i = 0; i < num_per; i++) {
+      u64 tot[4] = {0, 0, 0, 0};                       // n0r0, n0r1, n1r0, n1r1 (already reduced)
+      for (size_t j0 = 0; j0 < dim0; j0 += 512) {
+        size_t jend = std::min(dim0, j0 + 512);
+        __m256i acc_lo = _mm256_setzero_si256(), acc_hi = _mm256_setzero_si256();   // lanes: (j even r0, r1, j odd r0, r1)
+        for (size_t j = j0; j < jend; j += 2) {
+          __m128i bw = _mm_loadu_si128((const __m128i*)(b + i * dim0 + j));           // db words j, j+1
+          __m256i bb = _mm256_permute4x64_epi64(_mm256_castsi128_si256(bw), 0x50);    // (b_j, b_j, b_j+1, b_j+1)
+          __m256i av = _mm256_loadu_si256((const __m256i*)(a + 2 * j));               // (a_j r0, a_j r1, a_j+1 r0, a_j+1 r1)
+          acc_lo = _mm256_add_epi64(acc_lo, _mm256_mul_epu32(av, bb));
+          acc_hi = _mm256_add_epi64(acc_hi, _mm256_mul_epu32(_mm256_srli_epi64(av, 32), _mm256_srli_epi64(bb, 32)));
+        }
+        alignas(32) u64 lo[4], hi[4];
+        _mm256_store_si256((__m256i*)lo, acc_lo);
+        _mm256_store_si256((__m256i*)hi, acc_hi);
+        tot[0] = (tot[0] + lo[0] % q0 + lo[2] % q0) % q0;
+        tot[1] = (tot[1] + lo[1] % q0 + lo[3] % q0) % q0;
+        tot[2] = (tot[2] + hi[0] % q1 + hi[2] % q1) % q1;
+        tot[3] = (tot[3] + hi[1] % q1 + hi[3] % q1) % q1;
+      }
+      u64* o = out + i * 4 * N;
+      o[z] = tot[0]; o[2 * N + z] = tot[1]; o[N + z] = tot[2]; o[3 * N + z] = tot[3];
+    }
+  }
+}
+#endif
+
 // server.rs:155-221 (u128 accumulate, one % per output)
 inline void multiply_reg_by_database(const Params& p, u64* out /*[num_per][4*N]*/, const u64* db, const u64* v_firstdim,
                                      size_t dim0, size_t num_per) {
@@ -954,6 +1002,10 @@ inline std::vector<uint8_t> process_query(const Params& p, const PublicParameter
   for (size_t it = 0; it < p.instances * trials; it++) {
     std::vector<u64> inter(num_per * 4 * N);
     const u64* cur_db = db + it * db_slice_sz;
+#if defined(__AVX2__)
+    if (g_use_avx2_multiply && (dim0 % 2) == 0) multiply_reg_by_database_avx2(p, inter.data(), cur_db, v_reg.data(), dim0, num_per);
+    else
+#endif
     multiply_reg_by_database(p, inter.data(), cur_db, v_reg.data(), dim0, num_per);
     if (dump && it == 0) first_mult = inter;
     std::vector<PolyMatrix> inter_raw(num_per, raw_zero(p, 2, 1));

@@ -78,3 +78,23 @@ def test_dpir_matvec_matches_numpy():
     for m in range(3):
         exp += (((A >> np.uint64(10 * m)) & np.uint64(1023)) * B[:, m][None, :]).sum(axis=1)
     assert np.array_equal(out, (exp & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+
+
+def test_avx2_multiply_equals_scalar_u128_path():
+    # the SIMD form used for the CPU baseline must agree with server.rs:155-221 on worst-case operands too
+    P = O.Params.named("T")
+    rng = np.random.default_rng(12)
+    Q0, Q1 = 268369921, 249561089
+    for dim0, num_per, worst in ((64, 4, False), (1024, 2, True)):
+        n = dim0 * num_per * P.N
+        if worst:
+            db = np.full(n, (Q0 - 1) | ((Q1 - 1) << 32), dtype=np.uint64)
+            v = np.full(dim0 * 2 * P.N, (Q0 - 1) | ((Q1 - 1) << 32), dtype=np.uint64)
+        else:
+            db = rng.integers(0, Q0, n, dtype=np.uint64) | (rng.integers(0, Q1, n, dtype=np.uint64) << np.uint64(32))
+            v = (rng.integers(0, Q0, dim0 * 2 * P.N, dtype=np.uint64)
+                 | (rng.integers(0, Q1, dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+        ref = P.multiply_reg_by_database(db, v, dim0, num_per)
+        out = np.zeros_like(ref)
+        O._ck(O.LIB.orc_multiply_reg_by_database_avx2(P.hp, O._p64(out), O._p64(db), O._p64(v), O.C.c_size_t(dim0), O.C.c_size_t(num_per)))
+        assert np.array_equal(out, ref)
