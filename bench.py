@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
                     help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
     ap.add_argument("--fold-variant", type=int, default=1)
+    ap.add_argument("--intt-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
@@ -320,6 +321,7 @@ def main():
     G.set_stream(stream.cuda_stream)
     G.set_option("mul_variant", args.mul_variant)
     G.set_option("fold_variant", args.fold_variant)
+    G.set_option("intt_variant", args.intt_variant)
     G.set_option("batch", 8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1)))
     gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)
@@ -410,10 +412,12 @@ def main():
 
     # ---- single-query latency (device-resident, batch of 1), N == 1 only
     single_ms = None
+    single_roofline = None
     if N == 1 and not args.steps_only:
         for _ in range(3):
             check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), 1, d_out.data_ptr()))
         torch.cuda.synchronize()
+        G.set_option("profile", 2)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
@@ -421,6 +425,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         single_ms = e0.elapsed_time(e1) / 10
+        st1 = G.last_stage_ms()
+        G.set_option("profile", 0)
+        k_ms = st1["multiply"] / max(st1["multiply_launches"], 1)
+        db_b = d["slices"] * d["dim0"] * rows_local * POLY * 8
+        op_b = (d["dim0"] * POLY * 16 if args.db_format == 0 else 2 * POLY * ((d["dim0"] + 31) // 32) * 4 * 32 * 8)
+        alg1 = db_b + op_b + d["slices"] * rows_local * 4 * POLY * 4
+        pk, _src = measured_peak()
+        single_roofline = {"queries_per_launch": 1, "kernel_ms": k_ms, "achieved": alg1 / (k_ms * 1e-3) / 1e9, "peak": pk,
+                           "unit": "GB/s", "frac": alg1 / (k_ms * 1e-3) / 1e9 / pk, "algorithmic_bytes_per_launch": alg1}
 
     # ---- end to end (host buffers, copies inside the timed region)
     e2e_steps = 0 if args.steps_only else args.steps
@@ -481,7 +494,7 @@ def main():
                     "d2h_bytes_per_step": B * rb},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
-            "single_query_latency_ms": single_ms,
+            "single_query_latency_ms": single_ms, "single_query_roofline": single_roofline,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -86,6 +86,10 @@ int b200pir_db_fill_synthetic(b200pir_ctx* ctx, b200pir_db* db, uint64_t seed);
  * Expansion / conversion may be NULL when expand_queries == 0. */
 int b200pir_pp_create(b200pir_ctx* ctx, const uint64_t* v_packing, const uint64_t* v_expansion_left,
                       const uint64_t* v_expansion_right, const uint64_t* v_conversion, b200pir_pp** out);
+/* PublicParameters::deserialize (client.rs:212-259): data = 32-byte seed || rows 1.. of every matrix (raw u64, native
+ * endian) in the order v_packing, v_expansion_left, v_expansion_right (if present), v_conversion; len == setup_bytes.
+ * The first rows are regenerated on the GPU from ChaCha20Rng::from_seed(seed) (rand_chacha 0.3.1 keystream order). */
+int b200pir_pp_create_from_bytes(b200pir_ctx* ctx, const uint8_t* data, size_t len, b200pir_pp** out);
 void b200pir_pp_destroy(b200pir_pp* pp);
 
 /* ---- stage-level entry points (each == one reference function, host buffers) ----------------------- */
@@ -125,6 +129,12 @@ int b200pir_encode(b200pir_ctx* ctx, const uint64_t* v_packed_raw, uint8_t* out,
  * out: response_bytes bytes. */
 int b200pir_process_query(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_ct,
                           const uint64_t* v_buf, const uint64_t* v_ct, uint8_t* out, size_t* out_len);
+/* Query::deserialize (client.rs:303-315, expand_queries only): data = seed || row 1 of ct; query_ct: PolyMatrixRaw(2,1). */
+int b200pir_query_from_bytes(b200pir_ctx* ctx, const uint8_t* data, size_t len, uint64_t* query_ct);
+/* process_query on `count` serialized queries (count x query_bytes, back to back); out: count x response_bytes.
+ * Replaces Query::deserialize + process_query as lib/server's /private-read handler chains them. */
+int b200pir_process_query_bytes(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint8_t* queries, size_t len,
+                                size_t count, uint8_t* out, size_t* out_len_each);
 /* `count` queries of one client in one call; the database is streamed once per group of up to 4 (IMAD layout)
  * or 8 (INT8 tensor-core layout) queries.
  * queries: count x PolyMatrixRaw(2,1); out: count x response_bytes. */

@@ -353,6 +353,42 @@ int orc_client_decrypt_reg(void* c, const uint64_t* ct_ntt, uint64_t* out_raw) {
   std::memcpy(out_raw, d.data.data(), d.data.size() * 8);
   ORC_CATCH
 }
+// ---- wire formats
+void orc_chacha20_block(const uint32_t* init16, uint32_t* out16) { chacha20_block(init16, out16); }
+int orc_client_pp_bytes(void* c, uint8_t* out, size_t* out_len) {
+  ORC_TRY
+  Client& cl = *(Client*)c;
+  std::vector<uint8_t> b = serialize_pp(cl.p, cl.last_pp, cl.pp_seed);
+  std::memcpy(out, b.data(), b.size());
+  *out_len = b.size();
+  ORC_CATCH
+}
+int orc_client_query_bytes(void* c, uint8_t* out, size_t* out_len) {       // the last generated (expand-mode) query
+  ORC_TRY
+  Client& cl = *(Client*)c;
+  std::vector<uint8_t> b = serialize_query(cl.p, cl.last_query_ct, cl.query_seed);
+  std::memcpy(out, b.data(), b.size());
+  *out_len = b.size();
+  ORC_CATCH
+}
+int orc_pp_deserialize(void* h, const uint8_t* data, size_t len, uint64_t* pack, uint64_t* left, uint64_t* right, uint64_t* conv) {
+  ORC_TRY
+  const Params& p = *(Params*)h;
+  PublicParameters pp = deserialize_pp(p, data, len);
+  store_vec(pack, pp.v_packing);
+  if (left) store_vec(left, pp.v_expansion_left);
+  if (right && pp.has_right) store_vec(right, pp.v_expansion_right);
+  if (conv) store_vec(conv, pp.v_conversion);
+  ORC_CATCH
+}
+int orc_query_deserialize(void* h, const uint8_t* data, size_t len, uint64_t* ct) {
+  ORC_TRY
+  const Params& p = *(Params*)h;
+  PolyMatrix m = deserialize_query(p, data, len);
+  std::memcpy(ct, m.data.data(), m.data.size() * 8);
+  ORC_CATCH
+}
+
 int orc_generate_db(void* h, uint64_t seed, uint64_t* db) {
   ORC_TRY
   generate_db(*(Params*)h, seed, db);

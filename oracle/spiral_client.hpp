@@ -32,6 +32,48 @@ struct Rng {                       // xoshiro256**, seeded through splitmix64
   }
 };
 
+// ChaCha20 keystream as rand_chacha 0.3.1's ChaCha20Rng consumes it (lib/spiral-rs/Cargo.lock; call sites
+// client.rs:218, :309): RFC 8439 block function (20 rounds), 32-byte seed = key, 64-bit block counter in words 12-13
+// starting at 0, stream id (words 14-15) = 0, output words in keystream order, next_u64 = word[i] | word[i+1] << 32.
+// PARITY UNPINNED against the reference (no Rust toolchain, no stored vectors in the reference); the block function is
+// pinned by the RFC 8439 section 2.3.2 test vector (tests/test_oracle_kats.py).
+inline void chacha20_block(const u32 init[16], u32 out[16]) {
+  u32 x[16];
+  for (int i = 0; i < 16; i++) x[i] = init[i];
+  auto rotl = [](u32 v, int c) { return (v << c) | (v >> (32 - c)); };
+  auto qr = [&](int a, int b, int c, int d) {
+    x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 16);
+    x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 12);
+    x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 8);
+    x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 7);
+  };
+  for (int r = 0; r < 10; r++) {
+    qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+    qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+  }
+  for (int i = 0; i < 16; i++) out[i] = x[i] + init[i];
+}
+struct ChaCha20Rng {
+  u32 st[16];
+  u32 buf[16];
+  int idx = 16;
+  ChaCha20Rng() { std::memset(st, 0, sizeof(st)); }
+  explicit ChaCha20Rng(const uint8_t seed[32]) {
+    st[0] = 0x61707865; st[1] = 0x3320646e; st[2] = 0x79622d32; st[3] = 0x6b206574;
+    for (int i = 0; i < 8; i++) st[4 + i] = (u32)seed[4 * i] | ((u32)seed[4 * i + 1] << 8) | ((u32)seed[4 * i + 2] << 16) | ((u32)seed[4 * i + 3] << 24);
+    st[12] = st[13] = st[14] = st[15] = 0;
+  }
+  u32 next_u32() {
+    if (idx == 16) {
+      chacha20_block(st, buf);
+      if (++st[12] == 0) ++st[13];
+      idx = 0;
+    }
+    return buf[idx++];
+  }
+  u64 next() { u64 lo = next_u32(); u64 hi = next_u32(); return lo | (hi << 32); }
+};
+
 // discrete_gaussian.rs:64-139
 struct DiscreteGaussian {
   std::vector<u64> cdf_table;
@@ -65,7 +107,8 @@ struct DiscreteGaussian {
   }
 };
 
-inline PolyMatrix random_raw(const Params& p, size_t rows, size_t cols, Rng& rng) {   // poly.rs:105-117
+template <typename R>
+inline PolyMatrix random_raw(const Params& p, size_t rows, size_t cols, R& rng) {   // poly.rs:105-117
   PolyMatrix m = raw_zero(p, rows, cols);
   for (auto& x : m.data) x = rng.next() % p.modulus;
   return m;
@@ -97,12 +140,22 @@ struct Client {
   const Params& p;
   PolyMatrix sk_gsw, sk_reg, sk_gsw_full, sk_reg_full;
   DiscreteGaussian dg;
-  Rng rng, rng_pub;
+  Rng rng;                     // secret randomness (the reference: ChaCha20Rng::from_entropy, client.rs:547,626)
+  ChaCha20Rng rng_pub;         // public randomness, regenerated by the server from the 32-byte seed (client.rs:551,631)
+  Rng seeder;
+  uint8_t pp_seed[32], query_seed[32];
+  PublicParameters last_pp;
+  PolyMatrix last_query_ct;
   Client(const Params& params, u64 seed)
       : p(params), sk_gsw(raw_zero(params, params.n, 1)), sk_reg(raw_zero(params, 1, 1)),
-        dg(params.noise_width), rng(seed), rng_pub(seed ^ 0xA5A5A5A55A5A5A5AULL) {
+        dg(params.noise_width), rng(seed), seeder(seed ^ 0xA5A5A5A55A5A5A5AULL) {
     sk_gsw_full = matrix_with_identity(p, sk_gsw);
     sk_reg_full = matrix_with_identity(p, sk_reg);
+    fresh_seed(pp_seed);
+    rng_pub = ChaCha20Rng(pp_seed);
+  }
+  void fresh_seed(uint8_t out[32]) {
+    for (int i = 0; i < 4; i++) { u64 v = seeder.next(); std::memcpy(out + 8 * i, &v, 8); }
   }
   // client.rs:130-144 (HAMMING_WEIGHT = 256, :13)
   void gen_ternary_mat(PolyMatrix& mat) {
@@ -166,6 +219,8 @@ struct Client {
   }
   // client.rs:533-616
   PublicParameters generate_keys() {
+    fresh_seed(pp_seed);
+    rng_pub = ChaCha20Rng(pp_seed);
     gen_ternary_mat(sk_gsw);
     gen_ternary_mat(sk_reg);
     sk_gsw_full = matrix_with_identity(p, sk_gsw);
@@ -202,6 +257,7 @@ struct Client {
       }
       pp.v_conversion.push_back(conv);
     }
+    last_pp = pp;
     return pp;
   }
   // client.rs:618-721
@@ -211,6 +267,8 @@ struct Client {
     size_t idx_further = idx_target % ((size_t)1 << further_dims);
     u64 scale_k = p.modulus / p.pt_modulus;
     size_t bits_per = get_bits_per(p, p.t_gsw);
+    fresh_seed(query_seed);
+    rng_pub = ChaCha20Rng(query_seed);
     Query q;
     if (p.expand_queries) {
       PolyMatrix sigma = raw_zero(p, 1, 1);
@@ -236,6 +294,7 @@ struct Client {
         }
       }
       q.ct = from_ntt_alloc(p, encrypt_matrix_reg(to_ntt_alloc(p, sigma)));
+      last_query_ct = q.ct;
     } else {
       size_t num_expanded = (size_t)1 << p.db_dim_1;
       std::vector<PolyMatrix> reg_cts;
@@ -349,6 +408,62 @@ inline void generate_db(const Params& p, u64 seed, u64* db /* [slices][z][ii][j]
         db[((slice * N + z) * num_per + ii) * dim0 + j] = nt.data[z] | (nt.data[N + z] << 32);
     }
   }
+}
+
+// ---- wire formats (client.rs:47-93, 198-259, 279-329)
+inline void ser_matrix_excl_first_row(std::vector<uint8_t>& out, const Params& p, const PolyMatrix& raw) {   // :55-60
+  size_t offs = raw.cols * p.poly_len, cnt = (raw.rows - 1) * raw.cols * p.poly_len;
+  size_t pos = out.size();
+  out.resize(pos + cnt * 8);
+  std::memcpy(out.data() + pos, raw.data.data() + offs, cnt * 8);
+}
+inline std::vector<uint8_t> serialize_pp(const Params& p, const PublicParameters& pp, const uint8_t seed[32]) {  // :198-210
+  std::vector<uint8_t> out(seed, seed + 32);
+  for (auto& m : pp.v_packing) ser_matrix_excl_first_row(out, p, from_ntt_alloc(p, m));
+  for (auto& m : pp.v_expansion_left) ser_matrix_excl_first_row(out, p, from_ntt_alloc(p, m));
+  if (pp.has_right) for (auto& m : pp.v_expansion_right) ser_matrix_excl_first_row(out, p, from_ntt_alloc(p, m));
+  for (auto& m : pp.v_conversion) ser_matrix_excl_first_row(out, p, from_ntt_alloc(p, m));
+  return out;
+}
+inline size_t deser_matrix_rng(const Params& p, PolyMatrix& a, const uint8_t* data, ChaCha20Rng& rng) {   // :68-80
+  size_t first = a.cols * p.poly_len;
+  for (size_t i = 0; i < first; i++) a.data[i] = p.modulus - (rng.next() % p.modulus);            // get_inv_from_rng :47-49
+  size_t rest = (a.rows - 1) * a.cols * p.poly_len;
+  std::memcpy(a.data.data() + first, data, rest * 8);
+  return rest * 8;
+}
+inline PublicParameters deserialize_pp(const Params& p, const uint8_t* data, size_t len) {   // :212-259
+  if (len != p.setup_bytes()) throw std::runtime_error("setup data has the wrong length");
+  ChaCha20Rng rng(data);
+  size_t idx = 32;
+  PublicParameters pp;
+  auto take = [&](std::vector<PolyMatrix>& dst, size_t count, size_t rows, size_t cols) {
+    for (size_t i = 0; i < count; i++) {
+      PolyMatrix raw = raw_zero(p, rows, cols);
+      idx += deser_matrix_rng(p, raw, data + idx, rng);
+      dst.push_back(to_ntt_alloc(p, raw));
+    }
+  };
+  take(pp.v_packing, p.n, p.n + 1, p.t_conv);                 // :221 (always params.n matrices)
+  if (p.expand_queries) {
+    take(pp.v_expansion_left, p.g(), 2, p.t_exp_left);
+    if (p.version == 0 || p.t_exp_right != p.t_exp_left) { take(pp.v_expansion_right, p.stop_round() + 1, 2, p.t_exp_right); pp.has_right = true; }
+    take(pp.v_conversion, 1, 2, 2 * p.t_conv);
+  }
+  return pp;
+}
+inline std::vector<uint8_t> serialize_query(const Params& p, const PolyMatrix& ct, const uint8_t seed[32]) {   // :279-301
+  std::vector<uint8_t> out(seed, seed + 32);
+  ser_matrix_excl_first_row(out, p, ct);
+  return out;
+}
+inline PolyMatrix deserialize_query(const Params& p, const uint8_t* data, size_t len) {   // :303-315 (expand_queries)
+  if (len != p.query_bytes()) throw std::runtime_error("query has the wrong length");
+  if (!p.expand_queries) throw std::runtime_error("direct-upload queries are not handled here");
+  ChaCha20Rng rng(data);
+  PolyMatrix ct = raw_zero(p, 2, 1);
+  deser_matrix_rng(p, ct, data + 32, rng);
+  return ct;
 }
 
 // lib/server/src/db/loading.rs:278-299 convert_pt_to_poly (+ :34-41 pack_ntt_poly) and :317-359 update_item_raw:

@@ -42,6 +42,9 @@ def _load():
         "b200pir_db_update_item_raw": (C.c_int, [vp, vp, C.c_uint64, u8p, C.c_size_t]),
         "b200pir_db_fill_synthetic": (C.c_int, [vp, vp, C.c_uint64]),
         "b200pir_pp_create": (C.c_int, [vp, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
+        "b200pir_pp_create_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
+        "b200pir_query_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, u64p]),
+        "b200pir_process_query_bytes": (C.c_int, [vp, vp, vp, u8p, C.c_size_t, C.c_size_t, u8p, szp]),
         "b200pir_pp_destroy": (None, [vp]),
         "b200pir_ntt_forward": (C.c_int, [vp, u64p, C.c_size_t]),
         "b200pir_ntt_inverse": (C.c_int, [vp, u64p, C.c_size_t]),

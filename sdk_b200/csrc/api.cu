@@ -128,6 +128,7 @@ struct b200pir_ctx {
   // options
   int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
   int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
+  int intt_variant = 0;
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
@@ -385,7 +386,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
     }
     {
       b200pir_ctx::Scope sc(c, ST_FROMNTT);
-      launch_intt_from_zmajor(c->dp, db->F, c->w_cts.p, out_stride, c->w_mult.p, (int)count, c->slices, c->stream);
+      launch_intt_from_zmajor(c->dp, db->F, c->w_cts.p, out_stride, c->w_mult.p, (int)count, c->slices, c->intt_variant, c->stream);
     }
   }
   {
@@ -567,6 +568,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   if (k == "mul_variant") c->mul_variant = (int)value;
   else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4 or 8"); c->max_group = (int)value; }
   else if (k == "fold_variant") c->fold_variant = (int)value;
+  else if (k == "intt_variant") c->intt_variant = (int)value;
   else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
@@ -749,6 +751,73 @@ int b200pir_pp_create(b200pir_ctx* c, const uint64_t* v_packing, const uint64_t*
   *out = pp.release();
   API_END
 }
+
+namespace {
+// One group of serialized matrices (client.rs:55-80): `count` raw matrices rows x cols; row 0 regenerated from the seed's
+// keystream (u64 position `word`), rows 1.. copied from the byte stream.  Result: NTT form, ntt32 layout, in `dst`.
+void deserialize_group(b200pir_ctx* c, DevBuf<uint32_t>& dst, const uint8_t* seed, const uint8_t*& data, uint64_t& word,
+                       size_t count, size_t rows, size_t cols) {
+  const size_t row_words = cols * POLY, mat_words = rows * row_words, rest = (rows - 1) * row_words;
+  DevBuf<uint64_t> raw(count * mat_words);
+  launch_chacha_first_rows(raw.p, seed, word, (uint32_t)count, (uint32_t)row_words, mat_words, c->dp.modulus, c->stream);
+  word += count * row_words;
+  for (size_t i = 0; i < count; i++) {
+    B200_CUDA(cudaMemcpyAsync(raw.p + i * mat_words + row_words, data, rest * 8, cudaMemcpyHostToDevice, c->stream));
+    data += rest * 8;
+  }
+  dst.alloc(count * mat_words * 2);
+  launch_to_ntt(c->dp, dst.p, raw.p, count * rows * cols, c->stream);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+}
+}  // namespace
+
+// PublicParameters::deserialize (client.rs:212-259)
+int b200pir_pp_create_from_bytes(b200pir_ctx* c, const uint8_t* data, size_t len, b200pir_pp** out) {
+  API_BEGIN
+  if (!c || !out || !data) throw Error(B200PIR_E_BADARG, "null argument");
+  if (len != c->setup_bytes) throw Error(B200PIR_E_SHAPE, "setup data: expected " + std::to_string(c->setup_bytes) + " bytes");
+  Guard gd(c);
+  const auto& hp = c->hp;
+  std::unique_ptr<b200pir_pp> pp(new b200pir_pp());
+  pp->ctx = c;
+  const uint8_t* seed = data;
+  const uint8_t* cur = data + 32;
+  uint64_t word = 0;
+  deserialize_group(c, pp->pack, seed, cur, word, (size_t)c->num_packing, hp.n + 1, hp.t_conv);
+  if (hp.expand_queries) {
+    deserialize_group(c, pp->left, seed, cur, word, (size_t)c->g, 2, hp.t_exp_left);
+    if (c->has_right) deserialize_group(c, pp->right, seed, cur, word, (size_t)c->stop_round + 1, 2, hp.t_exp_right);
+    deserialize_group(c, pp->conv, seed, cur, word, 1, 2, 2 * hp.t_conv);
+  }
+  if ((size_t)(cur - data) != len) throw Error(B200PIR_E_SHAPE, "setup data: trailing bytes");
+  *out = pp.release();
+  API_END
+}
+
+namespace {
+// Query::deserialize, expand_queries branch (client.rs:303-315): `count` serialized queries -> [count] PolyMatrixRaw(2,1) on device
+void deserialize_queries(b200pir_ctx* c, const uint8_t* data, size_t count, uint64_t* dst_dev) {
+  for (size_t i = 0; i < count; i++) {
+    const uint8_t* q = data + i * c->query_bytes;
+    launch_chacha_first_rows(dst_dev + i * 2 * POLY, q, 0, 1, POLY, 2 * POLY, c->dp.modulus, c->stream);
+    B200_CUDA(cudaMemcpyAsync(dst_dev + i * 2 * POLY + POLY, q + 32, POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+}
+}  // namespace
+
+int b200pir_query_from_bytes(b200pir_ctx* c, const uint8_t* data, size_t len, uint64_t* query_ct) {
+  API_BEGIN
+  if (!c || !data || !query_ct) throw Error(B200PIR_E_BADARG, "null argument");
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_UNSUPPORTED, "serialized direct-upload queries are not supported");
+  if (len != c->query_bytes) throw Error(B200PIR_E_SHAPE, "query: expected " + std::to_string(c->query_bytes) + " bytes");
+  Guard gd(c);
+  DevBuf<uint64_t> ct(2 * POLY);
+  deserialize_queries(c, data, 1, ct.p);
+  B200_CUDA(cudaMemcpyAsync(query_ct, ct.p, 2 * POLY * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
 void b200pir_pp_destroy(b200pir_pp* pp) {
   if (!pp) return;
   cudaSetDevice(pp->ctx->device);
@@ -1030,6 +1099,30 @@ int b200pir_process_query_batch(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, 
   c->ensure_workspace(count, db->rows);
   c->prof_reset();
   B200_CUDA(cudaMemcpyAsync(c->w_query.p, query_cts, count * 2 * POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  run_query_batch_resident(c, db, pp, count, c->w_resp.p);
+  B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, count * c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->profile == 1) c->prof_collect();
+  if (out_len_each) *out_len_each = c->response_bytes;
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// process_query over the wire format: `count` serialized queries (Query::serialize, client.rs:279-301) back to back
+int b200pir_process_query_bytes(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint8_t* queries, size_t len,
+                                size_t count, uint8_t* out, size_t* out_len_each) {
+  API_BEGIN
+  if (!c || !out || !queries) throw Error(B200PIR_E_BADARG, "null argument");
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_UNSUPPORTED, "serialized direct-upload queries are not supported");
+  if (len != count * c->query_bytes) throw Error(B200PIR_E_SHAPE, "queries: expected " + std::to_string(count * c->query_bytes) + " bytes");
+  Guard gd(c);
+  check_db(c, db);
+  check_pp(c, pp);
+  if (db->shard.count != 1) throw Error(B200PIR_E_BADARG, "sharded database: use the stage_a / stage_b entry points");
+  if (count == 0) return 0;
+  c->ensure_workspace(count, db->rows);
+  c->prof_reset();
+  deserialize_queries(c, queries, count, c->w_query.p);
   run_query_batch_resident(c, db, pp, count, c->w_resp.p);
   B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, count * c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));

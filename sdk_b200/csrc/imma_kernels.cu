@@ -269,6 +269,63 @@ k_intt_from_zmajor(DevParams P, ImmaGeom F, const uint32_t* __restrict__ in_zm, 
   for (int a = 0; a < 8; a++) dst[a * 256 + tid] = x[a];
 }
 
+// Tiled variant: one CTA handles PP (= 2, 4 or 8) polynomials that are adjacent in the z-major product, so every
+// 32-byte sector it fetches is fully used (the simple kernel above uses 4 of every 32 bytes).  The PP polynomials are
+// transposed through shared memory, then inverse-transformed two at a time.
+// grid = (rows*2 / PP, 2 moduli, nq*slices), 256 threads, dynamic smem = PP*2048*4 + 2*NTT_SMEM_WORDS*4
+template <int PP>
+__global__ void __launch_bounds__(256)
+k_intt_from_zmajor_tiled(DevParams P, ImmaGeom F, const uint32_t* __restrict__ in_zm, size_t in_stride,
+                         uint32_t* __restrict__ out, int slices) {
+  extern __shared__ __align__(16) uint32_t tsm[];
+  uint32_t* polybuf = tsm;                               // [PP][2048]
+  uint32_t* sm0 = tsm + PP * POLY;
+  uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
+  const int tid = threadIdx.x, n = blockIdx.y;
+  const int p0 = blockIdx.x * PP;                        // index into the flattened [row][ct_row] axis
+  const int qs = blockIdx.z, qi = qs / slices, slice = qs % slices;
+  const uint32_t q = n ? P.q[1] : P.q[0];
+  const size_t zstride = (size_t)F.rows * 2;
+  const uint32_t* src = in_zm + (size_t)qi * in_stride + (((size_t)slice * 2 + n) * POLY) * zstride + p0;
+  for (int z = tid; z < POLY; z += 256) {
+    uint32_t v[PP];
+    const uint32_t* s = src + (size_t)z * zstride;
+    if (PP == 8) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(s)), b = __ldg(reinterpret_cast<const uint4*>(s) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4 % PP] = b.x; v[5 % PP] = b.y; v[6 % PP] = b.z; v[7 % PP] = b.w;
+    } else if (PP == 4) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(s));
+      v[0] = a.x; v[1] = a.y; v[2 % PP] = a.z; v[3 % PP] = a.w;
+    } else {
+      uint2 a = __ldg(reinterpret_cast<const uint2*>(s));
+      v[0] = a.x; v[1] = a.y;
+    }
+#pragma unroll
+    for (int p = 0; p < PP; p++) polybuf[p * POLY + z] = v[p];
+  }
+  __syncthreads();
+  const TwConstI lo{n, 1};
+  const TwGlobalI hi{n ? P.inv[1] : P.inv[0]};
+#pragma unroll 1
+  for (int p = 0; p < PP; p += 2) {
+    uint32_t x0[8], x1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0[k] = polybuf[p * POLY + tid * 8 + k];
+      x1[k] = polybuf[(p + 1) * POLY + tid * 8 + k];
+    }
+    ntt_inverse_group2(tid, x0, x1, sm0, sm1, lo, hi, q, SyncI());
+    const int f0 = p0 + p, f1 = p0 + p + 1;               // flattened (row, ct_row)
+    uint32_t* d0 = out + ((((size_t)qs * F.rows + (f0 >> 1)) * 2 + (f0 & 1)) * 2 + n) * POLY;
+    uint32_t* d1 = out + ((((size_t)qs * F.rows + (f1 >> 1)) * 2 + (f1 & 1)) * 2 + n) * POLY;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      d0[a * 256 + tid] = x0[a];
+      d1[a * 256 + tid] = x1[a];
+    }
+  }
+}
+
 // z-major product -> the ABI's [ii][r][n][z] NTT-form layout (stage-level entry point only)
 __global__ void k_zmajor_to_ntt32(ImmaGeom F, const uint32_t* __restrict__ in_zm, uint32_t* __restrict__ out, int slice) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over rows*4*2048, z fastest
@@ -324,10 +381,26 @@ void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* db
   else
     k_multiply_imma<2><<<dim3(POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin, slice_count);
 }
+template <int PP>
+static void launch_intt_tiled(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
+                              int nq, int slices, cudaStream_t s) {
+  const size_t smem = (size_t)(PP * POLY + 2 * NTT_SMEM_WORDS) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_intt_from_zmajor_tiled<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  k_intt_from_zmajor_tiled<PP><<<dim3(F.rows * 2 / PP, 2, nq * slices), 256, smem, s>>>(P, F, in_zm, in_stride, out, slices);
+}
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
-                             int nq, int slices, cudaStream_t s) {
+                             int nq, int slices, int variant, cudaStream_t s) {
   ++g_kernel_launches;
-  k_intt_from_zmajor<<<dim3(F.rows * 2, 2, nq * slices), 256, 0, s>>>(P, F, in_zm, in_stride, out, slices);
+  const int polys = F.rows * 2;
+  if (variant == 1)
+    k_intt_from_zmajor<<<dim3(F.rows * 2, 2, nq * slices), 256, 0, s>>>(P, F, in_zm, in_stride, out, slices);
+  else if (polys % 8 == 0) launch_intt_tiled<8>(P, F, in_zm, in_stride, out, nq, slices, s);
+  else if (polys % 4 == 0) launch_intt_tiled<4>(P, F, in_zm, in_stride, out, nq, slices, s);
+  else launch_intt_tiled<2>(P, F, in_zm, in_stride, out, nq, slices, s);
 }
 void launch_zmajor_to_ntt32(const ImmaGeom& F, const uint32_t* in_zm, uint32_t* out, int slice, cudaStream_t s) {
   size_t total = (size_t)F.rows * 4 * POLY;

@@ -23,6 +23,9 @@ void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inve
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s);
 // poly.rs:613-638 to_ntt: raw u64 -> ntt32 (reduce mod q_n, forward NTT)
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s);
+// client.rs:47-80: first rows of n_mats raw matrices = q - (ChaCha20 keystream u64 % q), keystream u64 index word0 onwards
+void launch_chacha_first_rows(uint64_t* raw, const uint8_t seed[32], uint64_t word0, uint32_t n_mats, uint32_t row_words,
+                              uint64_t mat_words, uint64_t modulus, cudaStream_t s);
 // poly.rs:646-663 from_ntt: ntt32 -> raw u64 (inverse NTT both moduli + CRT lift)
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s);
 // raw u64 coefficients <-> residue form u32 [poly][n][z] (coefficient domain; the CRT lift is poly.rs:658)
@@ -76,8 +79,9 @@ void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride
 void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
                           size_t out_stride, int nq, int slice_begin, int slice_count, cudaStream_t s);
 // inverse NTT of the z-major product -> residue-form ciphertexts [query*slices + slice][row][ct_row][n][z]
+// variant 0: tiled (sector-efficient) kernel, 1: simple gather kernel
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
-                             int nq, int slices, cudaStream_t s);
+                             int nq, int slices, int variant, cudaStream_t s);
 // z-major product of one slice -> ntt32 [row][ct_row][n][z]
 void launch_zmajor_to_ntt32(const ImmaGeom& F, const uint32_t* in_zm, uint32_t* out, int slice, cudaStream_t s);
 

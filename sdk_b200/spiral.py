@@ -146,6 +146,18 @@ class PublicParameters:
                                     _ptr(v_conversion), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def deserialize(cls, params, data):
+        """PublicParameters::deserialize (client.rs:212-259): seed || rows 1.. of every matrix."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data,
+                                    dtype=np.uint8)
+        self = cls.__new__(cls)
+        self.params = params
+        h = C.c_void_p()
+        check(LIB.b200pir_pp_create_from_bytes(params._h, _ptr(data, np.uint8), data.size, C.byref(h)))
+        self._h = h
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             LIB.b200pir_pp_destroy(self._h)
@@ -163,6 +175,15 @@ class Query:
 
     def __init__(self, ct=None, v_buf=None, v_ct=None):
         self.ct, self.v_buf, self.v_ct = ct, v_buf, v_ct
+
+    @classmethod
+    def deserialize(cls, params, data):
+        """Query::deserialize (client.rs:303-315), expand_queries parameter sets."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data,
+                                    dtype=np.uint8)
+        ct = np.zeros(2 * POLY_LEN, dtype=np.uint64)
+        check(LIB.b200pir_query_from_bytes(params._h, _ptr(data, np.uint8), data.size, _ptr(ct)))
+        return cls(ct=ct)
 
 
 # ---- lib/spiral-rs/src/ntt.rs
@@ -258,6 +279,21 @@ def process_query(params, public_params, query, db):
     check(LIB.b200pir_process_query(params._h, db._h, public_params._h, _ptr(query.ct), _ptr(query.v_buf),
                                     _ptr(query.v_ct), _ptr(out, np.uint8), C.byref(n)))
     return out[: n.value]
+
+
+def process_query_bytes(params, public_params, queries, db):
+    """Query::deserialize + process_query on serialized queries (count x query_bytes back to back), the chain
+    lib/server's private-read handler runs; returns count x response_bytes."""
+    queries = np.ascontiguousarray(np.frombuffer(queries, dtype=np.uint8) if isinstance(queries, (bytes, bytearray))
+                                   else queries, dtype=np.uint8)
+    if queries.size % params.query_bytes:
+        raise ValueError("queries must hold whole serialized queries")
+    count = queries.size // params.query_bytes
+    out = np.zeros(count * params.response_bytes, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(LIB.b200pir_process_query_bytes(params._h, db._h, public_params._h, _ptr(queries, np.uint8), queries.size, count,
+                                          _ptr(out, np.uint8), C.byref(n)))
+    return out.reshape(count, params.response_bytes)
 
 
 def process_query_batch(params, public_params, query_cts, db):

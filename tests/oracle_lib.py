@@ -275,6 +275,21 @@ class Params:
         resp = out[: ln.value].copy()
         return (resp, d) if dump else resp
 
+    def pp_deserialize(self, data):
+        sz = np.zeros(4, dtype=np.uint64)
+        _ck(LIB.orc_pp_sizes(self.hp, _p64(sz)))
+        sz[0] = self.n * (self.n + 1) * self.t_conv * self.W            # deserialize always builds params.n packing matrices
+        arrs = [np.zeros(int(x), dtype=np.uint64) if x else None for x in sz]
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        _ck(LIB.orc_pp_deserialize(self.hp, _p8(data), C.c_size_t(data.size), *[_p64(a) for a in arrs]))
+        return dict(pack=arrs[0], left=arrs[1], right=arrs[2], conv=arrs[3])
+
+    def query_deserialize(self, data):
+        ct = np.zeros(2 * self.N, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        _ck(LIB.orc_query_deserialize(self.hp, _p8(data), C.c_size_t(data.size), _p64(ct)))
+        return ct
+
     def generate_db(self, seed):
         db = np.zeros(self.slices * self.dim0 * self.num_per * self.N, dtype=np.uint64)
         _ck(LIB.orc_generate_db(self.hp, C.c_uint64(seed), _p64(db)))
@@ -321,6 +336,20 @@ class Client:
         v_ct = np.zeros(p.nu_2 * 2 * 2 * p.t_gsw * p.N, dtype=np.uint64)
         _ck(LIB.orc_client_generate_query(C.c_void_p(self.h), C.c_uint64(idx), None, _p64(v_buf), _p64(v_ct)))
         return dict(v_buf=v_buf, v_ct=v_ct)
+
+    def pp_bytes(self):
+        """PublicParameters::serialize of the last generated keys (client.rs:198-210)."""
+        out = np.zeros(self.p.setup_bytes + 64, dtype=np.uint8)
+        n = C.c_size_t(0)
+        _ck(LIB.orc_client_pp_bytes(C.c_void_p(self.h), _p8(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def query_bytes(self):
+        """Query::serialize of the last generated query (client.rs:279-301)."""
+        out = np.zeros(self.p.query_bytes + 64, dtype=np.uint8)
+        n = C.c_size_t(0)
+        _ck(LIB.orc_client_query_bytes(C.c_void_p(self.h), _p8(out), C.byref(n)))
+        return out[: n.value].copy()
 
     def decode_response(self, resp):
         p = self.p

@@ -642,3 +642,40 @@ def test_dpir_answer_matches_oracle():
     ref2, rr, rc = O.dpir_transpose_expand_concat_cols_squish(a, 35, 3, 1000, 3, 5)
     assert (orows, ocols) == (rr, rc) and np.array_equal(out, ref2)
     m.close()
+
+
+# ------------------------------------------------------------------ wire formats (client.rs:198-329)
+@pytest.mark.parametrize("name", CASES)
+def test_wire_formats_deserialize_and_process(name):
+    """PublicParameters::deserialize / Query::deserialize on the GPU (ChaCha20 first rows regenerated from the seed)
+    against the oracle's restatement, then process_query over the serialized bytes."""
+    S, P, _, _, db, G, gdb, _ = setup_case(name)
+    cl = O.Client(P, 4321)
+    pp = cl.generate_keys()
+    ppb = cl.pp_bytes()
+    assert ppb.size == G.setup_bytes
+    gpp = S.PublicParameters.deserialize(G, ppb)
+    idxs = [3, P.dim0 * P.num_per - 1, 100 % (P.dim0 * P.num_per)]
+    blobs = []
+    for idx in idxs:
+        q = cl.generate_query(idx)
+        qb = cl.query_bytes()
+        assert qb.size == G.query_bytes
+        got_ct = S.Query.deserialize(G, qb).ct
+        assert np.array_equal(got_ct, P.query_deserialize(qb))
+        assert np.array_equal(got_ct, q["ct"])
+        blobs.append((qb, q))
+    out = S.process_query_bytes(G, gpp, np.concatenate([b for b, _ in blobs]), gdb)
+    for k, (qb, q) in enumerate(blobs):
+        ref = P.process_query(pp, q, db)
+        assert np.array_equal(out[k], ref), (name, k)
+        assert np.array_equal(cl.decode_response(out[k]), P.db_plain_item(SEED_DB, idxs[k]))
+    # deserialized parameters == parameters uploaded as arrays
+    gpp2 = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
+    assert np.array_equal(S.process_query(G, gpp2, S.Query(ct=blobs[0][1]["ct"]), gdb), out[0])
+    with pytest.raises(S.B200PirError):
+        S.PublicParameters.deserialize(G, ppb[:-8])
+    with pytest.raises(S.B200PirError):
+        S.Query.deserialize(G, blobs[0][0][:-1])
+    gpp.close()
+    gpp2.close()

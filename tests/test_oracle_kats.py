@@ -202,3 +202,16 @@ def test_rescale_matches_rounding():
             num = c * out_mod + sign * (Q // 2)
             r = abs(num) // Q * (1 if num >= 0 else -1)
             assert LIB.orc_rescale(a, Q, out_mod) == r % out_mod
+
+
+def test_chacha20_block_rfc8439_vector():
+    # RFC 8439 section 2.3.2 (key 00..1f, counter 1, nonce 00:00:00:09:00:00:00:4a:00:00:00:00): pins the block function
+    # the wire formats' seed expansion is built on (rand_chacha 0.3.1; call sites client.rs:218, :309)
+    init = np.array([0x61707865, 0x3320646e, 0x79622d32, 0x6b206574,
+                     0x03020100, 0x07060504, 0x0b0a0908, 0x0f0e0d0c, 0x13121110, 0x17161514, 0x1b1a1918, 0x1f1e1d1c,
+                     0x00000001, 0x09000000, 0x4a000000, 0x00000000], dtype=np.uint32)
+    out = np.zeros(16, dtype=np.uint32)
+    LIB.orc_chacha20_block(O._p32(init), O._p32(out))
+    exp = [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3, 0xc7f4d1c7, 0x0368c033, 0x9aaa2204, 0x4e6cd4c3,
+           0x466482d2, 0x09aa9f07, 0x05d7c214, 0xa2028bd9, 0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
+    assert [int(x) for x in out] == exp

@@ -98,3 +98,23 @@ def test_avx2_multiply_equals_scalar_u128_path():
         out = np.zeros_like(ref)
         O._ck(O.LIB.orc_multiply_reg_by_database_avx2(P.hp, O._p64(out), O._p64(db), O._p64(v), O.C.c_size_t(dim0), O.C.c_size_t(num_per)))
         assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("name", ["T", "T1", "T0"])
+def test_wire_formats_round_trip(name):
+    # client.rs:848-955 public_parameters_serialization_is_correct / query_serialization_is_correct
+    P = O.Params.named(name)
+    cl = O.Client(P, 606)
+    pp = cl.generate_keys()
+    b = cl.pp_bytes()
+    assert b.size == P.setup_bytes
+    pp2 = P.pp_deserialize(b)
+    for k in ("pack", "left", "right", "conv"):
+        if pp[k] is None:
+            assert pp2[k] is None or not pp2[k].any() or k == "right"
+        else:
+            assert np.array_equal(pp[k], pp2[k][: pp[k].size]), k
+    q = cl.generate_query(9)
+    qb = cl.query_bytes()
+    assert qb.size == P.query_bytes
+    assert np.array_equal(P.query_deserialize(qb), q["ct"])
