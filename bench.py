@@ -244,7 +244,7 @@ def run_reference_arm(args, kw, workload_name, rank, world):
     out = {
         "impl": "reference", "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name, "params": kw, "batch": 1},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -260,13 +260,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "16")),
-                    help="queries per step (whole job); must be a multiple of --gpus")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="queries per step (whole job); must be a multiple of --gpus.  Default: --batch-per-gpu x GPUs")
+    ap.add_argument("--batch-per-gpu", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "16")),
+                    help="concurrent queries per GPU (BASELINE.json config #3: 128 concurrent queries on 8 GPUs)")
+    ap.add_argument("--waves", type=int, default=2,
+                    help="N > 1: each rank's queries are processed in this many waves so that the all-gather of one wave's "
+                         "expanded queries overlaps the expansion / first dimension of the other")
     ap.add_argument("--mul-variant", type=int, default=0)
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
                     help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
     ap.add_argument("--fold-variant", type=int, default=1)
     ap.add_argument("--intt-variant", type=int, default=0)
+    ap.add_argument("--imma-variant", type=int, default=0)
+    ap.add_argument("--expand-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
@@ -279,6 +286,8 @@ def main():
     if world != args.gpus and world > 1:
         log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
     N = max(world, 1)
+    if args.batch is None:
+        args.batch = args.batch_per_gpu * N
 
     name = args.workload or "S8"
     kw = dict(WORKLOADS[name])
@@ -291,7 +300,8 @@ def main():
             raise SystemExit("--gpus must be a power of two")
         if args.batch % N:
             raise SystemExit("--batch must be a multiple of --gpus")
-        # strong scaling: the SAME database, second-dimension rows sharded ii mod N (1/N of the bytes per GPU)
+        # the SAME database at every N, second-dimension rows sharded ii mod N (1/N of the bytes per GPU); the number of
+        # concurrent queries grows with N (fixed per GPU), so per-GPU work is constant: weak scaling
         workload_name = "%s; rows sharded ii mod %d over %d GPUs" % (base_name, N, N)
     else:
         workload_name = base_name
@@ -322,6 +332,8 @@ def main():
     G.set_option("mul_variant", args.mul_variant)
     G.set_option("fold_variant", args.fold_variant)
     G.set_option("intt_variant", args.intt_variant)
+    G.set_option("imma_variant", args.imma_variant)
+    G.set_option("expand_variant", args.expand_variant)
     G.set_option("batch", 8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1)))
     gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)
@@ -339,16 +351,20 @@ def main():
     d_out = torch.zeros((B // N) * rb, dtype=torch.uint8, device="cuda")
     rows_local = d["num_per"] // N
     Bl = B // N                                      # queries this rank receives / answers per step
+    W = 1
     if N > 1:
+        W = args.waves if (args.waves >= 1 and Bl % args.waves == 0) else 1
+        Blw, Bw = Bl // W, (Bl // W) * N             # per wave: local queries, global queries
         fold_words = kw["nu_2"] * 2 * 2 * kw["t_gsw"] * 2 * POLY
         ct_words = 4 * POLY
-        d_qexp_l = torch.zeros(Bl * d["dim0"] * POLY * 4, dtype=torch.int32, device="cuda")
-        d_vf_l = torch.zeros(Bl * fold_words, dtype=torch.int32, device="cuda")
-        d_qexp = torch.zeros(B * d["dim0"] * POLY * 4, dtype=torch.int32, device="cuda")
-        d_vf = torch.zeros(B * fold_words, dtype=torch.int32, device="cuda")
-        d_partial = torch.zeros(B * d["slices"] * ct_words, dtype=torch.int32, device="cuda")
-        d_gather = torch.zeros(N * B * d["slices"] * ct_words, dtype=torch.int32, device="cuda")
-        coll_bytes = (N - 1) * (d_qexp_l.numel() + d_vf_l.numel() + d_partial.numel()) * 4
+        zi = lambda n: torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_qexp_l = [zi(Blw * d["dim0"] * POLY * 4) for _ in range(W)]
+        d_vf_l = [zi(Blw * fold_words) for _ in range(W)]
+        d_qexp = [zi(Bw * d["dim0"] * POLY * 4) for _ in range(W)]
+        d_vf = [zi(Bw * fold_words) for _ in range(W)]
+        d_partial = [zi(Bw * d["slices"] * ct_words) for _ in range(W)]
+        d_gather = [zi(N * Bw * d["slices"] * ct_words) for _ in range(W)]
+        coll_bytes = W * (N - 1) * (d_qexp_l[0].numel() + d_vf_l[0].numel() + d_partial[0].numel()) * 4
 
     def step_dev():
         if N == 1:
@@ -356,14 +372,26 @@ def main():
         else:
             # each rank expands the Bl queries it received; expanded queries are all-gathered; every rank runs the
             # first dimension + local fold rounds of ALL B queries on its rows; survivors are all-gathered; each rank
-            # finishes (last log2 N rounds + pack + encode) its own Bl queries.
-            check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr(), Bl, d_qexp_l.data_ptr(), d_vf_l.data_ptr()))
-            dist.all_gather_into_tensor(d_qexp, d_qexp_l)
-            dist.all_gather_into_tensor(d_vf, d_vf_l)
-            check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, d_qexp.data_ptr(), d_vf.data_ptr(), B, d_partial.data_ptr()))
-            dist.all_gather_into_tensor(d_gather, d_partial)
-            check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, d_gather.data_ptr(), N, B, rank * Bl, Bl, d_vf_l.data_ptr(),
-                                                 d_out.data_ptr()))
+            # finishes (last log2 N rounds + pack + encode) its own Bl queries.  The queries go through in W waves: the
+            # collectives are asynchronous (NCCL's stream), so wave w's all-gather runs under wave w+1's expansion and
+            # wave w-1's first dimension; .wait() orders the compute stream after the collective, never the host.
+            ag = []
+            for w in range(W):
+                check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw,
+                                                     d_qexp_l[w].data_ptr(), d_vf_l[w].data_ptr()))
+                ag.append((dist.all_gather_into_tensor(d_qexp[w], d_qexp_l[w], async_op=True),
+                           dist.all_gather_into_tensor(d_vf[w], d_vf_l[w], async_op=True)))
+            sv = []
+            for w in range(W):
+                ag[w][0].wait()
+                ag[w][1].wait()
+                check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, d_qexp[w].data_ptr(), d_vf[w].data_ptr(), Bw,
+                                                     d_partial[w].data_ptr()))
+                sv.append(dist.all_gather_into_tensor(d_gather[w], d_partial[w], async_op=True))
+            for w in range(W):
+                sv[w].wait()
+                check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, d_gather[w].data_ptr(), N, Bw, rank * Blw, Blw,
+                                                     d_vf_l[w].data_ptr(), d_out.data_ptr() + w * Blw * rb))
 
     def step_e2e():
         if N == 1:
@@ -482,12 +510,14 @@ def main():
         out = {
             "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name, "params": kw, "batch": B, "db_bytes_per_gpu": db_bytes,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W,
+                       "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
                        "first_dimension_kernel": "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)",
-                       "parallelism": ("rows ii mod %d; queries expanded by the receiving rank; NCCL all-gather of expanded "
-                                       "queries and of surviving ciphertexts (%d bytes received per rank per step)" % (N, coll_bytes))
+                       "parallelism": ("rows ii mod %d, %d concurrent queries per GPU; queries expanded by the receiving rank; "
+                                       "asynchronous NCCL all-gather of expanded queries and of surviving ciphertexts in %d "
+                                       "waves (%d bytes received per rank per step)" % (N, B // N, W, coll_bytes))
                        if N > 1 else "single GPU",
                        "l2": "inputs larger than L2 (database %.1f GiB per GPU streamed every step)" % (db_bytes / 2**30)},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 2 * POLY * 8,

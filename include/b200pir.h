@@ -53,7 +53,9 @@ int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
 /* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4 or 8;
  * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments), "profile" (0 off, 1 per call,
- * 2 accumulate over calls until set again);
+ * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
+ * "expand_variant" (0 = default everywhere); "expand_pair_min_ctas" (expansion rounds with at least this many active
+ * ciphertexts use the paired kernel, default 592);
  * unknown keys -> B200PIR_E_BADARG */
 int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);
 /* params.setup_bytes / query_bytes / response length (params.rs:146-182, server.rs:476-481) */

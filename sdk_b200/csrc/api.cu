@@ -129,6 +129,9 @@ struct b200pir_ctx {
   int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
   int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
   int intt_variant = 0;
+  int expand_variant = 0;        // 0: paired expansion rounds when wide enough, 1: always one CTA per output
+  long pair_min_ctas = 592;      // 4 x 148 SMs
+  int imma_variant = 0;          // 0: cp.async-pipelined kernel for 5..8 queries per pass, 1: load-then-use kernel
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
   // workspace, sized for `ws_queries` queries
@@ -265,7 +268,7 @@ void upload_ntt32(b200pir_ctx* c, DevBuf<uint32_t>& dst, const uint64_t* host, s
 // ---- pipeline pieces (all stream-ordered, device pointers)
 
 // server.rs:19-121 over `nq` queries at once (v: [nq][2^g][4][2048], v_stride words apart)
-void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size_t v_stride, int nq) {
+void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size_t v_stride, int nq, bool all_slots) {
   const auto& hp = c->hp;
   cudaStream_t s = c->stream;
   const int g = c->g;
@@ -273,9 +276,14 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
   const int max_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
   for (int r = 0; r < g; r++) {
     const int num_in = 1 << r;
-    launch_expand_scalar(c->dp, v, v_stride, nq, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    // wide rounds: one CTA per input ciphertext produces both outputs (no scalar-multiply pass, one inverse transform);
+    // narrow rounds keep one CTA per output, which halves their latency
+    const long active = (long)((stop_round > 0 && r > stop_round) ? num_in / 2 : num_in) * nq;
+    const bool pair = c->expand_variant == 0 && active >= c->pair_min_ctas;
+    if (!pair) launch_expand_scalar(c->dp, v, v_stride, nq, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
     ExpandRound R;
     R.r = r; R.num_in = num_in; R.stop_round = stop_round; R.max_bits_to_gen_right = max_right;
+    R.fill_skipped = all_slots ? 1 : 0;
     R.t_auto = (POLY >> r) + 1;
     R.t_left = (int)hp.t_exp_left; R.bits_left = c->bits_left;
     R.w_left = pp->left.p + (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
@@ -288,7 +296,8 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
     } else {
       R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;   // unwrap_or(v_w_left), server.rs:549
     }
-    launch_expand_round(c->dp, v, v_stride, nq, R, s);
+    if (pair) launch_expand_round_pair(c->dp, v, v_stride, nq, R, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    else launch_expand_round(c->dp, v, v_stride, nq, R, s);
   }
 }
 
@@ -297,10 +306,10 @@ void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw,
                       uint32_t* v_fold, int nq) {
   const auto& hp = c->hp;
   cudaStream_t s = c->stream;
-  B200_CUDA(cudaMemsetAsync(v, 0, (size_t)nq * c->v_words() * 4, s));
+  // no clear of v: every slot the query path reads (even slots < 2 dim0, odd slots < 2 t_gsw nu_2) is written by the rounds
   for (int qi = 0; qi < nq; qi++)
     launch_to_ntt(c->dp, v + (size_t)qi * c->v_words(), query_raw + (size_t)qi * 2 * POLY, 2, s);   // v[0] = query.ct.ntt()
-  run_coefficient_expansion(c, pp, v, c->v_words(), nq);
+  run_coefficient_expansion(c, pp, v, c->v_words(), nq, false);
   const int factor = hp.nu_2 > 0 ? 2 : 1;
   launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
   if (hp.nu_2 > 0)
@@ -380,7 +389,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
         b200pir_ctx::Scope sc(c, ST_MUL);
         launch_query_to_frag(db->F, qdev + qi * q_stride, q_stride, nq, c->w_qf.p, c->stream);
         launch_multiply_imma(c->dp, db->F, db->f.p, c->w_qf.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
-                             c->stream);
+                             c->imma_variant, c->stream);
         c->mul_launches++;
       }
     }
@@ -569,6 +578,9 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4 or 8"); c->max_group = (int)value; }
   else if (k == "fold_variant") c->fold_variant = (int)value;
   else if (k == "intt_variant") c->intt_variant = (int)value;
+  else if (k == "imma_variant") c->imma_variant = (int)value;
+  else if (k == "expand_variant") c->expand_variant = (int)value;
+  else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
   else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
@@ -900,7 +912,7 @@ int b200pir_multiply_reg_by_database(b200pir_ctx* c, b200pir_db* db, uint64_t sl
     DevBuf<uint2> qf(imma_query_cells(db->F));
     DevBuf<uint32_t> zm((size_t)c->slices * rows * 4 * POLY);
     launch_query_to_frag(db->F, qd.p, 0, 1, qf.p, c->stream);
-    launch_multiply_imma(c->dp, db->F, db->f.p, qf.p, zm.p, 0, 1, (int)slice, 1, c->stream);
+    launch_multiply_imma(c->dp, db->F, db->f.p, qf.p, zm.p, 0, 1, (int)slice, 1, c->imma_variant, c->stream);
     launch_zmajor_to_ntt32(db->F, zm.p, o.p + (size_t)slice * rows * 4 * POLY, (int)slice, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
   }
@@ -983,7 +995,7 @@ int b200pir_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint64_t* v) {
   DevBuf<uint32_t> dv(words);
   B200_CUDA(cudaMemcpyAsync(wide.p, v, words * 8, cudaMemcpyHostToDevice, c->stream));
   launch_narrow(dv.p, wide.p, words, c->stream);
-  run_coefficient_expansion(c, pp, dv.p, words, 1);
+  run_coefficient_expansion(c, pp, dv.p, words, 1, true);
   launch_widen(wide.p, dv.p, words, c->stream);
   B200_CUDA(cudaMemcpyAsync(v, wide.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));

@@ -77,7 +77,7 @@ void launch_db_upsert_frag(const ImmaGeom& F, uint4* dbf, int slice, int il, int
 void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride, int nq, uint2* qf, cudaStream_t s);
 // out_zm: u32 [query][slice][n][z][row][ct_row]  (queries out_stride words apart)
 void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
-                          size_t out_stride, int nq, int slice_begin, int slice_count, cudaStream_t s);
+                          size_t out_stride, int nq, int slice_begin, int slice_count, int variant, cudaStream_t s);
 // inverse NTT of the z-major product -> residue-form ciphertexts [query*slices + slice][row][ct_row][n][z]
 // variant 0: tiled (sector-efficient) kernel, 1: simple gather kernel
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
@@ -113,8 +113,12 @@ struct ExpandRound {
   const uint32_t* w_left;   // ntt32 [2][t_exp_left]  for this round (or null when r == 0 / unused)
   const uint32_t* w_right;  // ntt32 [2][t_exp_right]
   int t_left, t_right, bits_left, bits_right;
+  int fill_skipped;         // paired kernel: also write v[i + num_in] = v[i] (.) neg1 for skipped i (stage-level parity)
 };
 void launch_expand_round(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R, cudaStream_t s);
+// both outputs of every input ciphertext in one CTA; replaces launch_expand_scalar + launch_expand_round for that round
+void launch_expand_round_pair(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R,
+                              const uint32_t* neg1_r, cudaStream_t s);
 // util.rs:323-355 reorient: v[idx_factor*j] -> q_dev   (per query: q_stride uint4 apart)
 void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int nq,
                      int idx_factor, cudaStream_t s);

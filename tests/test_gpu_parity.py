@@ -207,25 +207,52 @@ def test_fold_and_folding_neg_match_oracle(name):
 
 
 # ------------------------------------------------------------------ expansion
+# expand_pair_min_ctas: rounds with at least that many active ciphertexts use the paired kernel (one CTA = both outputs
+# of an input, inverse transform shared through the negacyclic shift); 1 = every round, 1 << 30 = never, 8 = mixed
+@pytest.mark.parametrize("pair_min", [1, 8, 1 << 30])
 @pytest.mark.parametrize("name", CASES)
-def test_expand_query_matches_oracle(name):
+def test_expand_query_matches_oracle(name, pair_min):
     S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
     q = cl.generate_query(P.dim0 * P.num_per - 2)
     vreg_ref, vf_ref = P.expand_query(pp, q["ct"])
-    vreg, vf = S.expand_query(G, gpp, S.Query(ct=q["ct"]))
+    G.set_option("expand_pair_min_ctas", pair_min)
+    try:
+        vreg, vf = S.expand_query(G, gpp, S.Query(ct=q["ct"]))
+    finally:
+        G.set_option("expand_pair_min_ctas", 592)
     assert np.array_equal(vreg, vreg_ref)
     assert np.array_equal(vf, vf_ref)
 
 
-def test_coefficient_expansion_matches_oracle_all_slots():
-    S, P, cl, pp, db, G, gdb, gpp = setup_case("T0")
+@pytest.mark.parametrize("pair_min", [1, 4, 1 << 30])
+@pytest.mark.parametrize("name", ["T0", "T"])
+def test_coefficient_expansion_matches_oracle_all_slots(name, pair_min):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
     q = cl.generate_query(9)
     v = np.zeros((1 << P.g) * 2 * P.W, dtype=np.uint64)
     v[: 2 * P.W] = P.to_ntt(q["ct"])
     ref = P.coefficient_expansion(v, pp)
     got = v.copy()
-    S.coefficient_expansion(G, gpp, got)
+    G.set_option("expand_pair_min_ctas", pair_min)
+    try:
+        S.coefficient_expansion(G, gpp, got)
+    finally:
+        G.set_option("expand_pair_min_ctas", 592)
     assert np.array_equal(got, ref)
+
+
+def test_process_query_with_paired_expansion_everywhere():
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    idxs = [1, 200, 33, 255, 128]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    G.set_option("expand_pair_min_ctas", 1)
+    try:
+        out = S.process_query_batch(G, gpp, qs, gdb)
+    finally:
+        G.set_option("expand_pair_min_ctas", 592)
+    for k, i in enumerate(idxs):
+        assert np.array_equal(out[k], P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)), k
+        assert np.array_equal(cl.decode_response(out[k]), P.db_plain_item(SEED_DB, i))
 
 
 # ------------------------------------------------------------------ pack / encode
@@ -461,12 +488,15 @@ def test_imma_multiply_and_process_query_match_oracle(name):
     idxs = [0, 3, P.dim0 * P.num_per - 1, 17, 5, 9, 2, 11, 1, 30, 6]
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     refs = [P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db) for k in range(len(idxs))]
-    for group in (4, 8):
+    # imma_variant 0 = cp.async-pipelined 8-query kernel (default), 1 = load-then-use kernel
+    for group, variant in ((4, 0), (8, 0), (8, 1)):
         G.set_option("batch", group)
+        G.set_option("imma_variant", variant)
         out = S.process_query_batch(G, gpp, qs, fdb)
         for k in range(len(idxs)):
-            assert np.array_equal(out[k], refs[k]), (name, group, k)
+            assert np.array_equal(out[k], refs[k]), (name, group, variant, k)
     G.set_option("batch", 8)
+    G.set_option("imma_variant", 0)
     # synthetic generator and item upsert in fragment order
     f2 = S.Database(G, fmt=1)
     f2.fill_synthetic(SEED_DB)
