@@ -129,7 +129,7 @@ struct b200pir_ctx {
   int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
   int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
   int intt_variant = 0;
-  int expand_variant = 0;        // 0: paired expansion rounds when wide enough, 1: always one CTA per output
+  int expand_variant = 0;        // wide rounds: 0 paired + residue pipeline (3 CTAs/SM), 2 paired single kernel; 1: never paired
   long pair_min_ctas = 592;      // 4 x 148 SMs
   int imma_variant = 0;          // 0: cp.async-pipelined kernel for 5..8 queries per pass, 1: load-then-use kernel
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
@@ -138,6 +138,7 @@ struct b200pir_ctx {
   size_t ws_queries = 0, ws_rows = 0;
   DevBuf<uint64_t> w_query;      // [Q][2][2048] raw
   DevBuf<uint32_t> w_v;          // [Q][2^g][2][2][2048]
+  DevBuf<uint32_t> w_xr;         // [Q][num_in][2][2048] residues of row 0 (paired expansion rounds)
   DevBuf<uint4> w_qdev;          // [Q][dim0][2048]
   DevBuf<uint32_t> w_vfold, w_vfold_neg;   // [Q][nu_2][2][2t][2][2048]
   DevBuf<uint32_t> w_mult;       // [Q][slices][rows][2][2][2048]  NTT form, then residue form in place
@@ -279,7 +280,7 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
     // wide rounds: one CTA per input ciphertext produces both outputs (no scalar-multiply pass, one inverse transform);
     // narrow rounds keep one CTA per output, which halves their latency
     const long active = (long)((stop_round > 0 && r > stop_round) ? num_in / 2 : num_in) * nq;
-    const bool pair = c->expand_variant == 0 && active >= c->pair_min_ctas;
+    const bool pair = c->expand_variant != 1 && active >= c->pair_min_ctas;
     if (!pair) launch_expand_scalar(c->dp, v, v_stride, nq, num_in, c->d_neg1.p + (size_t)r * 2 * POLY, s);
     ExpandRound R;
     R.r = r; R.num_in = num_in; R.stop_round = stop_round; R.max_bits_to_gen_right = max_right;
@@ -296,7 +297,11 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
     } else {
       R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;   // unwrap_or(v_w_left), server.rs:549
     }
-    if (pair) launch_expand_round_pair(c->dp, v, v_stride, nq, R, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    if (pair && c->expand_variant == 0) {
+      const size_t xr_stride = (size_t)num_in * 2 * POLY;
+      c->w_xr.ensure((size_t)nq * xr_stride);
+      launch_expand_round_res(c->dp, v, v_stride, c->w_xr.p, xr_stride, nq, R, c->d_neg1.p + (size_t)r * 2 * POLY, s);
+    } else if (pair) launch_expand_round_pair(c->dp, v, v_stride, nq, R, c->d_neg1.p + (size_t)r * 2 * POLY, s);
     else launch_expand_round(c->dp, v, v_stride, nq, R, s);
   }
 }

@@ -119,6 +119,9 @@ void launch_expand_round(const DevParams& P, uint32_t* v, size_t v_stride, int n
 // both outputs of every input ciphertext in one CTA; replaces launch_expand_scalar + launch_expand_round for that round
 void launch_expand_round_pair(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R,
                               const uint32_t* neg1_r, cudaStream_t s);
+// the paired round split into an inverse-transform kernel (residues -> xr) and single-modulus CTAs at 3 per SM
+void launch_expand_round_res(const DevParams& P, uint32_t* v, size_t v_stride, uint32_t* xr, size_t xr_stride, int nq,
+                             const ExpandRound& R, const uint32_t* neg1_r, cudaStream_t s);
 // util.rs:323-355 reorient: v[idx_factor*j] -> q_dev   (per query: q_stride uint4 apart)
 void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int nq,
                      int idx_factor, cudaStream_t s);

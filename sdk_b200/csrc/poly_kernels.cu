@@ -701,6 +701,136 @@ k_expand_round_pair(DevParams P, uint32_t* v, size_t v_stride, ExpandRound R, co
   }
 }
 
+// ---- paired rounds, residue pipeline: the same arithmetic as k_expand_round_pair split the way k_fold_res is, so that
+// the transforms run in 256-thread single-modulus CTAs at 3 CTAs per SM instead of one 512-thread CTA per SM.
+//   k_expand_intt:       inverse transform of row 0 of every processed v[i], residues in coefficient order -> xr
+//   k_expand_round_res:  CTA (i, n): CRT lift (+ negacyclic shift for the second output) + automorphism + gadget digits
+//                        + forward transforms and key products modulo q_n; writes rows (., n) of v[i] and v[i + num_in].
+// xr: [query][i][n][2048] u32.
+__global__ void __launch_bounds__(256)
+k_expand_intt(DevParams P, const uint32_t* __restrict__ v, size_t v_stride, uint32_t* __restrict__ xr, size_t xr_stride,
+              ExpandRound R) {
+  __shared__ __align__(16) uint32_t ntt_smem[NTT_SMEM_WORDS];
+  const int i = blockIdx.x;
+  if ((R.stop_round > 0 && R.r > R.stop_round && (i & 1)) ||
+      (R.stop_round > 0 && R.r == R.stop_round && (i & 1) && (i / 2) >= R.max_bits_to_gen_right))
+    return;
+  Grp g = make_grp_single(P, ntt_smem, blockIdx.y);
+  const uint32_t* src = v + (size_t)blockIdx.z * v_stride + ((size_t)i * 4 + g.n) * POLY;
+  uint32_t x[8];
+  ld8_ro(x, src + g.tid * 8);
+  grp_ntt_inv(g, x);
+  uint32_t* dst = xr + (size_t)blockIdx.z * xr_stride + ((size_t)i * 2 + g.n) * POLY;
+#pragma unroll
+  for (int a = 0; a < 8; a++) dst[a * 256 + g.tid] = x[a];
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_expand_round_res(DevParams P, uint32_t* v, size_t v_stride, const uint32_t* __restrict__ xr, size_t xr_stride,
+                   ExpandRound R, const uint32_t* __restrict__ neg1) {
+  v += (size_t)blockIdx.z * v_stride;
+  xr += (size_t)blockIdx.z * xr_stride;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* sm0 = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
+  uint64_t* autom = reinterpret_cast<uint64_t*>(sm1 + NTT_SMEM_WORDS);     // [2048]
+  Twiddle* tw = reinterpret_cast<Twiddle*>(autom + POLY);                   // [HI_TW]
+  Grp g = make_grp_single(P, sm0, blockIdx.y);
+  g.smem2 = sm1;
+  const int i = blockIdx.x;
+  const uint32_t* ng = neg1 + (size_t)g.n * POLY;
+  uint32_t* vi = v + (size_t)i * 4 * POLY;
+  uint32_t* vo = v + (size_t)(i + R.num_in) * 4 * POLY;
+  if ((R.stop_round > 0 && R.r > R.stop_round && (i & 1)) ||
+      (R.stop_round > 0 && R.r == R.stop_round && (i & 1) && (i / 2) >= R.max_bits_to_gen_right)) {
+    if (R.fill_skipped) {                                  // see k_expand_round_pair
+      uint32_t nn[8];
+      ld8_ro(nn, ng + g.tid * 8);
+#pragma unroll
+      for (int rho = 0; rho < 2; rho++) {
+        uint32_t x[8];
+        ld8(x, vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = barrett64((uint64_t)x[e] * nn[e], g.cr1, g.q);
+        st8(vo + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8, x);
+      }
+    }
+    return;
+  }
+  const bool left = (R.r != 0) && ((i & 1) == 0);
+  const uint32_t* W = left ? R.w_left : R.w_right;
+  const int t_exp = left ? R.t_left : R.t_right;
+  const int bits = left ? R.bits_left : R.bits_right;
+  stage_fwd_twiddles(g, tw);
+  const uint32_t* x0r = xr + (size_t)i * 2 * POLY;         // residues mod q_0 / q_1 of from_ntt(row 0 of v[i])
+  const uint32_t* x1r = x0r + POLY;
+  const uint32_t* row1 = vi + ((size_t)2 + g.n) * POLY;
+  const uint64_t Q = P.modulus;
+  const uint32_t q0 = P.q[0], q1 = P.q[1];
+#pragma unroll 1
+  for (int half = 1; half >= 0; half--) {
+    const int shift = half ? R.num_in : 0;                 // 2^r
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int k = a * 256 + g.tid;
+      const int zs = (k + shift) & (POLY - 1);
+      uint32_t a0 = __ldg(x0r + zs), a1 = __ldg(x1r + zs);
+      if (k + shift >= POLY) {
+        a0 = a0 ? q0 - a0 : 0u;
+        a1 = a1 ? q1 - a1 : 0u;
+      }
+      const uint64_t val = crt_compose(a0, a1, P);
+      const unsigned prod = (unsigned)k * (unsigned)R.t_auto;
+      const unsigned num = prod >> NTT_LOG_N, rem = prod & (POLY - 1);
+      autom[rem] = (num & 1u) ? Q - val : val;             // zero maps to q, as in the reference
+    }
+    __syncthreads();                                       // autom complete (and the staged twiddles visible)
+    uint64_t acc[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[r][e] = 0;
+    int cnt = 0;
+    {
+      uint64_t vv[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) vv[a] = autom[a * 256 + g.tid];
+      const uint32_t* c0 = W + (size_t)g.n * POLY + g.tid * 8;
+      digits_mac<2, true>(acc, cnt, vv, t_exp, bits, c0, (size_t)2 * POLY, (size_t)t_exp * 2 * POLY, g);
+    }
+    // row 1 automorphism = slot permutation (see k_expand_round); gather before any thread overwrites v[i]
+    uint32_t yy[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const unsigned sidx = (unsigned)(g.tid * 8 + e);
+      const unsigned ee = 2u * (__brev(sidx) >> (32 - NTT_LOG_N)) + 1u;
+      const unsigned e2 = (ee * (unsigned)R.t_auto) & (2u * POLY - 1u);
+      const unsigned src = __brev((e2 - 1u) >> 1) >> (32 - NTT_LOG_N);
+      uint32_t t = row1[src];
+      if (half) t = barrett64((uint64_t)t * __ldg(ng + src), g.cr1, g.q);
+      yy[e] = t;
+    }
+    __syncthreads();
+    uint32_t* dst = half ? vo : vi;
+    uint32_t nn[8];
+    if (half) ld8_ro(nn, ng + g.tid * 8);
+#pragma unroll
+    for (int rho = 0; rho < 2; rho++) {
+      uint32_t o[8];
+      ld8(o, vi + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8);
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        uint32_t base = o[e];
+        if (half) base = barrett64((uint64_t)base * nn[e], g.cr1, g.q);
+        uint32_t s = addmod(base, barrett64(acc[rho][e], g.cr1, g.q), g.q);
+        o[e] = rho ? addmod(s, yy[e], g.q) : s;
+      }
+      st8(dst + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8, o);
+    }
+  }
+}
+
 // util.rs:323-355
 __global__ void k_reorient(MulGeom G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int idx_factor) {
   q_dev += (size_t)blockIdx.y * q_stride;
@@ -1026,6 +1156,18 @@ void launch_expand_round_pair(const DevParams& P, uint32_t* v, size_t v_stride, 
   }
   ++g_kernel_launches;
   k_expand_round_pair<<<dim3((unsigned)R.num_in, nq), CTA, kDynSmemBig, s>>>(P, v, v_stride, R, neg1_r);
+}
+void launch_expand_round_res(const DevParams& P, uint32_t* v, size_t v_stride, uint32_t* xr, size_t xr_stride, int nq,
+                             const ExpandRound& R, const uint32_t* neg1_r, cudaStream_t s) {
+  const size_t smem = (size_t)2 * NTT_SMEM_WORDS * 4 + (size_t)POLY * 8 + (size_t)HI_TW * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_expand_round_res<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  g_kernel_launches += 2;
+  k_expand_intt<<<dim3((unsigned)R.num_in, 2, nq), 256, 0, s>>>(P, v, v_stride, xr, xr_stride, R);
+  k_expand_round_res<3><<<dim3((unsigned)R.num_in, 2, nq), 256, smem, s>>>(P, v, v_stride, xr, xr_stride, R, neg1_r);
 }
 void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint32_t* v, size_t v_stride, int nq,
                      int idx_factor, cudaStream_t s) {

@@ -224,9 +224,10 @@ def test_expand_query_matches_oracle(name, pair_min):
     assert np.array_equal(vf, vf_ref)
 
 
-@pytest.mark.parametrize("pair_min", [1, 4, 1 << 30])
+@pytest.mark.parametrize("pair_min,variant", [(1, 0), (4, 0), (1, 2), (4, 2), (1 << 30, 0)])
 @pytest.mark.parametrize("name", ["T0", "T"])
-def test_coefficient_expansion_matches_oracle_all_slots(name, pair_min):
+def test_coefficient_expansion_matches_oracle_all_slots(name, pair_min, variant):
+    # expand_variant 0: paired rounds as inverse-transform kernel + single-modulus CTAs; 2: paired rounds in one kernel
     S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
     q = cl.generate_query(9)
     v = np.zeros((1 << P.g) * 2 * P.W, dtype=np.uint64)
@@ -234,10 +235,12 @@ def test_coefficient_expansion_matches_oracle_all_slots(name, pair_min):
     ref = P.coefficient_expansion(v, pp)
     got = v.copy()
     G.set_option("expand_pair_min_ctas", pair_min)
+    G.set_option("expand_variant", variant)
     try:
         S.coefficient_expansion(G, gpp, got)
     finally:
         G.set_option("expand_pair_min_ctas", 592)
+        G.set_option("expand_variant", 0)
     assert np.array_equal(got, ref)
 
 
