@@ -274,6 +274,9 @@ def main():
     ap.add_argument("--intt-variant", type=int, default=0)
     ap.add_argument("--imma-variant", type=int, default=0)
     ap.add_argument("--expand-variant", type=int, default=0)
+    ap.add_argument("--queries-per-pass", type=int, default=None,
+                    help="queries per database pass (1, 2, 4, 8 or 16).  Default 8 on one GPU (the first dimension stays "
+                         "near the HBM roof), 16 on row shards (half the passes, each re-staging the query operand)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
@@ -334,7 +337,10 @@ def main():
     G.set_option("intt_variant", args.intt_variant)
     G.set_option("imma_variant", args.imma_variant)
     G.set_option("expand_variant", args.expand_variant)
-    G.set_option("batch", 8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1)))
+    if args.queries_per_pass is None:
+        args.queries_per_pass = 8 if N == 1 else 16
+    per_pass = min(args.queries_per_pass, 16 if B >= 16 else (8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1))))
+    G.set_option("batch", per_pass)
     gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)
     rng = np.random.default_rng(20260923)
@@ -487,7 +493,8 @@ def main():
     if args.db_format == 0:
         operand_bytes = nq_per_launch * d["dim0"] * POLY * 16
     else:   # limb fragments of the query operand: [n][z][column tiles][dim0/32][4 limbs][32 lanes] x 8 B
-        operand_bytes = 2 * POLY * (2 if nq_per_launch > 4 else 1) * ((d["dim0"] + 31) // 32) * 4 * 32 * 8
+        tiles = 4 if nq_per_launch > 8 else (2 if nq_per_launch > 4 else 1)
+        operand_bytes = 2 * POLY * tiles * ((d["dim0"] + 31) // 32) * 4 * 32 * 8
     alg_bytes = db_bytes + operand_bytes + nq_per_launch * d["slices"] * rows_local * 4 * POLY * 4
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (mul_ms * 1e-3) / 1e9
@@ -511,7 +518,7 @@ def main():
             "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W,
+            "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W, "queries_per_pass": per_pass,
                        "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
                        "first_dimension_kernel": "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)",

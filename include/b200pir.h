@@ -51,7 +51,7 @@ void b200pir_ctx_destroy(b200pir_ctx* ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this context. */
 int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
-/* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4 or 8;
+/* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4, 8 or 16;
  * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
  * "expand_variant" (0 = default everywhere); "expand_pair_min_ctas" (expansion rounds with at least this many active
@@ -138,7 +138,7 @@ int b200pir_query_from_bytes(b200pir_ctx* ctx, const uint8_t* data, size_t len, 
 int b200pir_process_query_bytes(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint8_t* queries, size_t len,
                                 size_t count, uint8_t* out, size_t* out_len_each);
 /* `count` queries of one client in one call; the database is streamed once per group of up to 4 (IMAD layout)
- * or 8 (INT8 tensor-core layout) queries.
+ * or 16 (INT8 tensor-core layout) queries.
  * queries: count x PolyMatrixRaw(2,1); out: count x response_bytes. */
 int b200pir_process_query_batch(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_cts,
                                 size_t count, uint8_t* out, size_t* out_len_each);

@@ -126,7 +126,7 @@ struct b200pir_ctx {
   DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
-  int mul_variant = 0, max_group = 8, profile = 0;   // max_group: queries per database pass (IMAD path: <= 4)
+  int mul_variant = 0, max_group = 16, profile = 0;  // max_group: queries per database pass (IMAD path: <= 4)
   int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
   int intt_variant = 0;
   int expand_variant = 0;        // wide rounds: 0 paired + residue pipeline (3 CTAs/SM), 2 paired single kernel; 1: never paired
@@ -312,8 +312,7 @@ void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw,
   const auto& hp = c->hp;
   cudaStream_t s = c->stream;
   // no clear of v: every slot the query path reads (even slots < 2 dim0, odd slots < 2 t_gsw nu_2) is written by the rounds
-  for (int qi = 0; qi < nq; qi++)
-    launch_to_ntt(c->dp, v + (size_t)qi * c->v_words(), query_raw + (size_t)qi * 2 * POLY, 2, s);   // v[0] = query.ct.ntt()
+  launch_to_ntt_strided(c->dp, v, c->v_words(), query_raw, (size_t)2 * POLY, 2, nq, s);   // v[0] = query.ct.ntt()
   run_coefficient_expansion(c, pp, v, c->v_words(), nq, false);
   const int factor = hp.nu_2 > 0 ? 2 : 1;
   launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
@@ -387,7 +386,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
   } else {
     // INT8 tensor-core path: z-major product in w_cts (free until the fold starts), then inverse NTT into w_mult
     c->w_qf.ensure(imma_query_cells(db->F));
-    const size_t per_pass = c->max_group >= 8 ? 8 : 4;
+    const size_t per_pass = (c->max_group >= 16 && imma_supports_16(db->F)) ? 16 : (c->max_group >= 8 ? 8 : 4);
     for (size_t qi = 0; qi < count; qi += per_pass) {
       const int nq = (int)std::min<size_t>(per_pass, count - qi);
       {
@@ -580,7 +579,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   Guard gd(c);
   std::string k(key);
   if (k == "mul_variant") c->mul_variant = (int)value;
-  else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4 or 8"); c->max_group = (int)value; }
+  else if (k == "batch") { if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16) throw Error(B200PIR_E_BADARG, "batch must be 1, 2, 4, 8 or 16"); c->max_group = (int)value; }
   else if (k == "fold_variant") c->fold_variant = (int)value;
   else if (k == "intt_variant") c->intt_variant = (int)value;
   else if (k == "imma_variant") c->imma_variant = (int)value;
@@ -994,7 +993,6 @@ int b200pir_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint64_t* v) {
   Guard gd(c);
   check_pp(c, pp);
   if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "context was created with expand_queries = 0");
-  const auto& hp = c->hp;
   const size_t words = c->v_words();
   DevBuf<uint64_t> wide(words);
   DevBuf<uint32_t> dv(words);

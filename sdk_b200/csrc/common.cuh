@@ -47,9 +47,13 @@ __device__ __forceinline__ uint64_t crt_compose(uint32_t x, uint32_t y, const De
   return (uint64_t)y + (uint64_t)P.q[1] * m;
 }
 // gadget digit k of a raw coefficient (gadget.rs:34-60)
+// bits <= 32 for every parameter set (bits_per of t >= 2 is at most 29), so a digit is the low word of v >> sh: two
+// clamped funnel shifts (the second one is a no-op until sh >= 32 and yields 0 from sh >= 64) and one AND.
 __device__ __forceinline__ uint32_t gadget_digit(uint64_t v, int k, int bits, uint64_t mask) {
-  int sh = k * bits;
-  return sh >= 64 ? 0u : (uint32_t)((v >> sh) & mask);
+  const int sh = k * bits;
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  const uint32_t w = __funnelshift_rc(__funnelshift_rc(lo, hi, sh), 0u, sh > 32 ? sh - 32 : 0);
+  return w & (uint32_t)mask;
 }
 
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {

@@ -227,7 +227,8 @@ k_multiply_imma(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const ui
 // does: every warp runs its own IMMA_STAGES-deep cp.async ring (2 KiB = one k-step of A fragments per stage, each lane
 // copies and later reads only its own 16-byte chunks, so no barrier is involved), flattened over all of its (slice, row
 // tile) work items so that the ring never drains at an item boundary.
-constexpr int IMMA_STAGES = 4;
+constexpr int IMMA_STAGES = 4;          // NT = 2: two CTAs per SM
+constexpr int IMMA_STAGES16 = 8;        // NT = 4 (9..16 queries per pass): one CTA per SM, 112 accumulator registers
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -236,14 +237,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2)
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(256, NT == 2 ? 2 : 1)
 k_multiply_imma8(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const uint2* __restrict__ qf,
                  uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count) {
-  extern __shared__ __align__(16) uint2 bsm[];            // [nt = 2][ks][m][lane], then the per-warp A rings
+  extern __shared__ __align__(16) uint2 bsm[];            // [nt][ks][m][lane], then the per-warp A rings
   const int z = blockIdx.x, n = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  uint4* ring = reinterpret_cast<uint4*>(bsm + (size_t)2 * F.ks * 128) + (size_t)warp * IMMA_STAGES * 128;
+  uint4* ring = reinterpret_cast<uint4*>(bsm + (size_t)NT * F.ks * 128) + (size_t)warp * STAGES * 128;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
   const int total_items = slice_count * F.mt;
   const int my_items = warp < total_items ? (total_items - warp + nwarps - 1) / nwarps : 0;
@@ -255,17 +257,17 @@ k_multiply_imma8(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const u
       const int item = warp + (it / F.ks) * nwarps, ks = it % F.ks;
       const int slice = slice_begin + item / F.mt, mt = item % F.mt;
       const uint4* src = zbase + (size_t)slice * slice_words + ((size_t)mt * F.ks + ks) * 128;
-      const uint32_t dst = ring_s + (uint32_t)(((it % IMMA_STAGES) * 128 + lane) * 16);
+      const uint32_t dst = ring_s + (uint32_t)(((it % STAGES) * 128 + lane) * 16);
 #pragma unroll
       for (int l = 0; l < 4; l++) cp_async16(dst + l * 32 * 16, src + l * 32);
     }
     cp_async_commit();
   };
 #pragma unroll
-  for (int s = 0; s < IMMA_STAGES - 1; s++) issue(s);
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
   {
-    const uint2* src = qf + ((size_t)n * POLY + z) * 2 * F.ks * 128;
-    for (int i = threadIdx.x; i < 2 * F.ks * 128; i += blockDim.x) bsm[i] = __ldg(src + i);
+    const uint2* src = qf + ((size_t)n * POLY + z) * NT * F.ks * 128;
+    for (int i = threadIdx.x; i < NT * F.ks * 128; i += blockDim.x) bsm[i] = __ldg(src + i);
   }
   __syncthreads();
   const uint32_t q = n ? P.q[1] : P.q[0];
@@ -274,9 +276,9 @@ k_multiply_imma8(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const u
 #pragma unroll
   for (int s = 0; s < 7; s++) p7[s] = (uint32_t)((1ull << (7 * s)) % q);
   const int g = lane >> 2, t = lane & 3;
-  int acc[2][7][4];
+  int acc[NT][7][4];
 #pragma unroll
-  for (int a = 0; a < 2; a++)
+  for (int a = 0; a < NT; a++)
 #pragma unroll
     for (int s = 0; s < 7; s++)
 #pragma unroll
@@ -284,27 +286,27 @@ k_multiply_imma8(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const u
   int ks = 0, item = warp;
 #pragma unroll 1
   for (int it = 0; it < T; it++) {
-    cp_async_wait<IMMA_STAGES - 2>();                     // stage `it` has landed (this lane's own chunks)
-    issue(it + IMMA_STAGES - 1);                          // refill the slot consumed in the previous iteration
-    const uint4* st = ring + (it % IMMA_STAGES) * 128 + lane;
+    cp_async_wait<STAGES - 2>();                          // stage `it` has landed (this lane's own chunks)
+    issue(it + STAGES - 1);                               // refill the slot consumed in the previous iteration
+    const uint4* st = ring + (it % STAGES) * 128 + lane;
     uint4 A[4];
 #pragma unroll
     for (int l = 0; l < 4; l++) A[l] = st[l * 32];
 #pragma unroll
     for (int m = 0; m < 4; m++) {
-      const uint2 b0 = bsm[(ks * 4 + m) * 32 + lane];
-      const uint2 b1 = bsm[((F.ks + ks) * 4 + m) * 32 + lane];
+      uint2 b[NT];
 #pragma unroll
-      for (int l = 0; l < 4; l++) {
-        mma_u8(acc[0][l + m], A[l], b0);
-        mma_u8(acc[1][l + m], A[l], b1);
-      }
+      for (int c = 0; c < NT; c++) b[c] = bsm[((c * F.ks + ks) * 4 + m) * 32 + lane];
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int c = 0; c < NT; c++) mma_u8(acc[c][l + m], A[l], b[c]);
     }
     if (++ks == F.ks) {
       // recombine the shift groups, reduce, store:  c0,c1 -> row g, columns 2t, 2t+1 ; c2,c3 -> row g+8
       const int slice = slice_begin + item / F.mt, mt = item % F.mt;
 #pragma unroll
-      for (int a = 0; a < 2; a++) {
+      for (int a = 0; a < NT; a++) {
         const int qi = a * 4 + t;
 #pragma unroll
         for (int rh = 0; rh < 2; rh++) {
@@ -459,7 +461,11 @@ void upload_imma_constants(const Twiddle* lo) {
 size_t imma_db_cells(const ImmaGeom& F, int slices) {
   return (size_t)slices * 2 * POLY * F.mt * F.ks * 4 * 32;
 }
-size_t imma_query_cells(const ImmaGeom& F) { return (size_t)2 * POLY * 2 * F.ks * 4 * 32; }   // up to 2 column tiles
+size_t imma_query_cells(const ImmaGeom& F) { return (size_t)2 * POLY * 4 * F.ks * 4 * 32; }   // up to 4 column tiles
+// 16 queries per pass need the B operand (4 tiles) plus the A rings in one CTA's shared memory
+bool imma_supports_16(const ImmaGeom& F) {
+  return (size_t)4 * F.ks * 128 * sizeof(uint2) + (size_t)8 * IMMA_STAGES16 * 128 * sizeof(uint4) <= 224 * 1024;
+}
 
 void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s) {
   size_t warps = (size_t)POLY * F.mt * F.ks;
@@ -471,28 +477,37 @@ void launch_db_upsert_frag(const ImmaGeom& F, uint4* dbf, int slice, int il, int
   k_db_upsert_frag<<<POLY / 256, 256, 0, s>>>(F, dbf, slice, il, j, poly);
 }
 void launch_query_to_frag(const ImmaGeom& F, const uint4* q_dev, size_t q_stride, int nq, uint2* qf, cudaStream_t s) {
-  const int ntiles = nq > 4 ? 2 : 1;
+  const int ntiles = imma_query_tiles(nq);
   size_t warps = (size_t)POLY * ntiles * F.ks;
   ++g_kernel_launches;
   k_query_to_frag<<<grid1d(warps * 32, 256), 256, 0, s>>>(F, q_dev, q_stride, nq, ntiles, qf);
 }
 void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* dbf, const uint2* qf, uint32_t* out_zm,
                           size_t out_stride, int nq, int slice_begin, int slice_count, int variant, cudaStream_t s) {
-  if (nq < 1 || nq > 8) throw Error(-2, "imma multiply: 1..8 queries per pass");
-  const int ntiles = nq > 4 ? 2 : 1;
+  if (nq < 1 || nq > 16) throw Error(-2, "imma multiply: 1..16 queries per pass");
+  const int ntiles = imma_query_tiles(nq);
   const size_t smem = (size_t)ntiles * F.ks * 128 * sizeof(uint2);
   const size_t smem8 = smem + (size_t)8 * IMMA_STAGES * 128 * sizeof(uint4);
+  const size_t smem16 = smem + (size_t)8 * IMMA_STAGES16 * 128 * sizeof(uint4);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_multiply_imma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(k_multiply_imma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(k_multiply_imma8, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute((k_multiply_imma8<2, IMMA_STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute((k_multiply_imma8<4, IMMA_STAGES16>), cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr_set = true;
   }
-  if (smem > 96 * 1024) throw Error(-2, "imma multiply: dim0 too large");
   ++g_kernel_launches;
+  if (ntiles == 4) {
+    if (smem16 > 224 * 1024) throw Error(-2, "imma multiply: dim0 too large for 16 queries per pass");
+    k_multiply_imma8<4, IMMA_STAGES16><<<dim3(POLY, 2), 256, smem16, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin,
+                                                                        slice_count);
+    return;
+  }
+  if (smem > 96 * 1024) throw Error(-2, "imma multiply: dim0 too large");
   if (ntiles == 2 && variant == 0 && smem8 <= 112 * 1024)
-    k_multiply_imma8<<<dim3(POLY, 2), 256, smem8, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin, slice_count);
+    k_multiply_imma8<2, IMMA_STAGES><<<dim3(POLY, 2), 256, smem8, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin,
+                                                                       slice_count);
   else if (ntiles == 1)
     k_multiply_imma<1><<<dim3(POLY, 2), 256, smem, s>>>(P, F, dbf, qf, out_zm, out_stride, nq, slice_begin, slice_count);
   else

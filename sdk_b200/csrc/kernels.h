@@ -23,6 +23,9 @@ void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inve
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s);
 // poly.rs:613-638 to_ntt: raw u64 -> ntt32 (reduce mod q_n, forward NTT)
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s);
+// `batches` groups of `count` polynomials, groups out_stride (u32) / raw_stride (u64) words apart, in one launch
+void launch_to_ntt_strided(const DevParams& P, uint32_t* out, size_t out_stride, const uint64_t* raw, size_t raw_stride,
+                           size_t count, int batches, cudaStream_t s);
 // client.rs:47-80: first rows of n_mats raw matrices = q - (ChaCha20 keystream u64 % q), keystream u64 index word0 onwards
 void launch_chacha_first_rows(uint64_t* raw, const uint8_t seed[32], uint64_t word0, uint32_t n_mats, uint32_t row_words,
                               uint64_t mat_words, uint64_t modulus, cudaStream_t s);
@@ -69,7 +72,9 @@ void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_d
 struct ImmaGeom { int dim0, rows, mt /* ceil(rows/16) */, ks /* ceil(dim0/32) */; };
 inline ImmaGeom make_imma_geom(int dim0, int rows) { return ImmaGeom{dim0, rows, (rows + 15) / 16, (dim0 + 31) / 32}; }
 size_t imma_db_cells(const ImmaGeom& F, int slices);      // uint4 cells of the whole database
-size_t imma_query_cells(const ImmaGeom& F);               // uint2 cells of the B operand (up to 8 queries)
+size_t imma_query_cells(const ImmaGeom& F);               // uint2 cells of the B operand (up to 16 queries)
+bool imma_supports_16(const ImmaGeom& F);                 // 16 queries per database pass fit one CTA's shared memory
+inline int imma_query_tiles(int nq) { return nq > 8 ? 4 : (nq > 4 ? 2 : 1); }   // column tiles of 4 queries
 void upload_imma_constants(const Twiddle* lo);
 // one slice in the IMAD layout (uint4 [row][jp][z]) -> fragment order
 void launch_db_to_frag(const ImmaGeom& F, const uint4* db0_slice, uint4* dbf, int slice, cudaStream_t s);

@@ -251,9 +251,13 @@ __global__ void __launch_bounds__(256) k_ntt_u64(DevParams P, uint64_t* polys, i
     for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
   }
 }
-__global__ void __launch_bounds__(256) k_to_ntt(DevParams P, uint32_t* out, const uint64_t* raw) {
+// blockIdx.z selects one of several equally shaped batches (out_stride / raw_stride words apart)
+__global__ void __launch_bounds__(256) k_to_ntt(DevParams P, uint32_t* out, const uint64_t* raw, size_t out_stride,
+                                                size_t raw_stride) {
   __shared__ __align__(16) uint32_t ntt_smem[NTT_SMEM_WORDS];
   Grp g = make_grp_single(P, ntt_smem, blockIdx.y);
+  out += (size_t)blockIdx.z * out_stride;
+  raw += (size_t)blockIdx.z * raw_stride;
   const uint64_t* src = raw + (size_t)blockIdx.x * POLY;
   uint32_t x[8];
 #pragma unroll
@@ -1083,7 +1087,12 @@ void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool invers
   if (count) ++g_kernel_launches, k_ntt32<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, polys, inverse ? 1 : 0);
 }
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s) {
-  if (count) ++g_kernel_launches, k_to_ntt<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, out, raw);
+  if (count) ++g_kernel_launches, k_to_ntt<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, out, raw, 0, 0);
+}
+void launch_to_ntt_strided(const DevParams& P, uint32_t* out, size_t out_stride, const uint64_t* raw, size_t raw_stride,
+                           size_t count, int batches, cudaStream_t s) {
+  if (count && batches)
+    ++g_kernel_launches, k_to_ntt<<<dim3((unsigned)count, 2, (unsigned)batches), 256, 0, s>>>(P, out, raw, out_stride, raw_stride);
 }
 void launch_raw_to_res(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t polys, cudaStream_t s) {
   if (polys) ++g_kernel_launches, k_raw_to_res<<<grid1d(polys * POLY, 256), 256, 0, s>>>(P, out, raw, polys);

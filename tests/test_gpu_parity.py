@@ -304,7 +304,7 @@ def test_process_query_batch_equals_single(group):
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     G.set_option("batch", group)
     out = S.process_query_batch(G, gpp, qs, gdb)
-    G.set_option("batch", 8)
+    G.set_option("batch", 16)
     for k, i in enumerate(idxs):
         ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
         assert np.array_equal(out[k], ref), (group, k)
@@ -492,13 +492,24 @@ def test_imma_multiply_and_process_query_match_oracle(name):
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     refs = [P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db) for k in range(len(idxs))]
     # imma_variant 0 = cp.async-pipelined 8-query kernel (default), 1 = load-then-use kernel
-    for group, variant in ((4, 0), (8, 0), (8, 1)):
+    # batch 16: one pass of 11 queries on the four-column-tile kernel (third tile partly, fourth tile entirely padding)
+    for group, variant in ((4, 0), (8, 0), (8, 1), (16, 0)):
         G.set_option("batch", group)
         G.set_option("imma_variant", variant)
         out = S.process_query_batch(G, gpp, qs, fdb)
         for k in range(len(idxs)):
             assert np.array_equal(out[k], refs[k]), (name, group, variant, k)
-    G.set_option("batch", 8)
+    # 19 queries at batch 16: a full 16-query pass followed by a 3-query pass
+    if name == "T":
+        more = [7, 64, 100, 250, 12, 99, 180, 201]
+        qs2 = np.concatenate([qs] + [cl.generate_query(i)["ct"] for i in more])
+        out = S.process_query_batch(G, gpp, qs2, fdb)
+        for k in range(len(idxs)):
+            assert np.array_equal(out[k], refs[k]), (name, "19", k)
+        for k, i in enumerate(more):
+            kk = len(idxs) + k
+            assert np.array_equal(out[kk], P.process_query(pp, dict(ct=qs2[kk * 2 * P.N:(kk + 1) * 2 * P.N]), db)), (name, "19", kk)
+    G.set_option("batch", 16)
     G.set_option("imma_variant", 0)
     # synthetic generator and item upsert in fragment order
     f2 = S.Database(G, fmt=1)
