@@ -275,8 +275,9 @@ def main():
     ap.add_argument("--imma-variant", type=int, default=0)
     ap.add_argument("--expand-variant", type=int, default=0)
     ap.add_argument("--queries-per-pass", type=int, default=None,
-                    help="queries per database pass (1, 2, 4, 8 or 16).  Default 8 on one GPU (the first dimension stays "
-                         "near the HBM roof), 16 on row shards (half the passes, each re-staging the query operand)")
+                    help="queries per database pass (1, 2, 4, 8 or 16).  Default 8: the first dimension stays near the HBM "
+                         "roof.  16 is +2.6%% q/s on one GPU (profiles/bench_r01_final2_qpp16.json) but slower on 1/8 row "
+                         "shards, where a CTA's share of the database is no larger than the query operand it stages")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
@@ -338,7 +339,7 @@ def main():
     G.set_option("imma_variant", args.imma_variant)
     G.set_option("expand_variant", args.expand_variant)
     if args.queries_per_pass is None:
-        args.queries_per_pass = 8 if N == 1 else 16
+        args.queries_per_pass = 8
     per_pass = min(args.queries_per_pass, 16 if B >= 16 else (8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1))))
     G.set_option("batch", per_pass)
     gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
