@@ -52,7 +52,8 @@ void b200pir_ctx_destroy(b200pir_ctx* ctx);
 int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
 /* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4, 8 or 16;
- * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments), "profile" (0 off, 1 per call,
+ * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments,
+ * 2 = tcgen05 tile images — experimental, see tc5_kernels.cu), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
  * "expand_variant" (0 = default everywhere); "expand_pair_min_ctas" (expansion rounds with at least this many active
  * ciphertexts use the paired kernel, default 592);

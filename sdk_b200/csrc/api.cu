@@ -133,7 +133,9 @@ struct b200pir_ctx {
   long pair_min_ctas = 592;      // 4 x 148 SMs
   int imma_variant = 0;          // 0: cp.async-pipelined kernel for 5..8 queries per pass, 1: load-then-use kernel
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
-  DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 4 queries)
+  DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 16 queries)
+  DevBuf<uint8_t> w_qt;          // B operand of the tcgen05 path (tile images, 16 queries)
+  int sm_count = 0;
   // workspace, sized for `ws_queries` queries
   size_t ws_queries = 0, ws_rows = 0;
   DevBuf<uint64_t> w_query;      // [Q][2][2048] raw
@@ -218,9 +220,11 @@ struct b200pir_db {
   b200pir_ctx* ctx;
   Shard shard;
   int rows;                 // local second-dimension rows
-  int format = 0;           // 0: d (IMAD layout)  1: f (INT8 MMA fragment order)
+  int format = 0;           // 0: d (IMAD layout)  1: f (INT8 MMA fragment order)  2: t (tcgen05 tile images)
   DevBuf<uint4> d;          // [slice][row][dim0/2][2048]
   DevBuf<uint4> f;          // [slice][n][z][mt][ks][limb][lane]
+  DevBuf<uint8_t> t;        // format 2: [slice][n][z][mt][ks][4096 B] tile images (tc5_kernels.cu)
+  Tc5Geom T;
   ImmaGeom F;
   size_t slice_cells() const { return (size_t)rows * (ctx->dim0 / 2) * POLY; }
 };
@@ -383,6 +387,21 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
       b200pir_ctx::Scope sc(c, ST_FROMNTT);
       launch_ntt32(c->dp, c->w_mult.p, count * c->slices * rows * 2, true, c->stream);
     }
+  } else if (db->format == 2) {
+    // tcgen05 path: same z-major product as the mma.sync path, 16 queries per database pass
+    c->w_qt.ensure(tc5_query_bytes(db->T));
+    for (size_t qi = 0; qi < count; qi += 16) {
+      const int nq = (int)std::min<size_t>(16, count - qi);
+      b200pir_ctx::Scope sc(c, ST_MUL);
+      launch_query_to_tc5(db->T, qdev + qi * q_stride, q_stride, nq, c->w_qt.p, c->stream);
+      launch_multiply_tc5(c->dp, db->T, db->t.p, c->w_qt.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
+                          c->sm_count, c->stream);
+      c->mul_launches++;
+    }
+    {
+      b200pir_ctx::Scope sc(c, ST_FROMNTT);
+      launch_intt_from_zmajor(c->dp, db->F, c->w_cts.p, out_stride, c->w_mult.p, (int)count, c->slices, c->intt_variant, c->stream);
+    }
   } else {
     // INT8 tensor-core path: z-major product in w_cts (free until the fold starts), then inverse NTT into w_mult
     c->w_qf.ensure(imma_query_cells(db->F));
@@ -461,6 +480,7 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
   B200_CUDA(cudaSetDevice(device));
   std::unique_ptr<b200pir_ctx> c(new b200pir_ctx());
   c->device = device;
+  B200_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   c->hp = *params;
   auto& hp = c->hp;
   if (hp.q2_bits < 14) hp.q2_bits = 14;                       // util.rs:230, params.rs:7
@@ -585,7 +605,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "imma_variant") c->imma_variant = (int)value;
   else if (k == "expand_variant") c->expand_variant = (int)value;
   else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
-  else if (k == "db_format") { if (value != 0 && value != 1) throw Error(B200PIR_E_BADARG, "db_format must be 0 or 1"); c->db_format = (int)value; }
+  else if (k == "db_format") { if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be 0, 1 or 2"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
     c->profile = (int)value;
@@ -617,10 +637,16 @@ int b200pir_db_create(b200pir_ctx* c, uint64_t shard_index, uint64_t shard_count
   db->rows = c->num_per / (int)shard_count;
   db->format = c->db_format;
   db->F = make_imma_geom(c->dim0, db->rows);
+  db->T = make_tc5_geom(c->dim0, db->rows);
   if (db->format == 0) {
     size_t cells = (size_t)c->slices * db->slice_cells();
     db->d.alloc(cells);
     B200_CUDA(cudaMemsetAsync(db->d.p, 0, cells * sizeof(uint4), c->stream));
+  } else if (db->format == 2) {
+    if (!tc5_supported(db->T)) throw Error(B200PIR_E_UNSUPPORTED, "db_format 2: dim0 too large for the tcgen05 kernel");
+    size_t bytes = tc5_db_bytes(db->T, c->slices);
+    db->t.alloc(bytes);
+    B200_CUDA(cudaMemsetAsync(db->t.p, 0, bytes, c->stream));
   } else {
     size_t cells = imma_db_cells(db->F, c->slices);
     db->f.alloc(cells);
@@ -661,6 +687,9 @@ int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, cons
   if (db->format == 1) {
     launch_db_to_frag(db->F, tmp.p, db->f.p, (int)slice, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
+  } else if (db->format == 2) {
+    launch_db_to_tc5(db->T, tmp.p, db->t.p, (int)slice, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
   }
   B200_CUDA(cudaGetLastError());
   API_END
@@ -686,6 +715,7 @@ int b200pir_db_upsert_item(b200pir_ctx* c, b200pir_db* db, uint64_t slice, uint6
   DevBuf<uint64_t> tmp(POLY);
   B200_CUDA(cudaMemcpyAsync(tmp.p, poly, POLY * 8, cudaMemcpyHostToDevice, c->stream));
   if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
+  else if (db->format == 2) launch_db_upsert_tc5(db->T, db->t.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
   else launch_db_upsert_frag(db->F, db->f.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
   // the host RwLock gives upserts exclusive access (bin/server.rs:35,49): finish before returning
   B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -712,6 +742,7 @@ int b200pir_db_update_item_raw(b200pir_ctx* c, b200pir_db* db, uint64_t db_idx, 
   launch_item_from_bytes(c->dp, bucket.p, (int)chunks, (int)pt_len, hp.p, polys.p, c->stream);
   for (size_t s = 0; s < chunks; s++) {
     if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
+    else if (db->format == 2) launch_db_upsert_tc5(db->T, db->t.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
     else launch_db_upsert_frag(db->F, db->f.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
   }
   B200_CUDA(cudaStreamSynchronize(c->stream));                                // writers hold the host write lock
@@ -736,7 +767,8 @@ int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
     DevBuf<uint4> tmp(db->slice_cells());
     for (int s0 = 0; s0 < c->slices; s0++) {
       launch_db_synth(c->dp, G, db->shard, tmp.p - (size_t)s0 * db->slice_cells(), seed, c->hp.p, s0, 1, c->stream);
-      launch_db_to_frag(db->F, tmp.p, db->f.p, s0, c->stream);
+      if (db->format == 2) launch_db_to_tc5(db->T, tmp.p, db->t.p, s0, c->stream);
+      else launch_db_to_frag(db->F, tmp.p, db->f.p, s0, c->stream);
     }
   }
   B200_CUDA(cudaStreamSynchronize(c->stream));
@@ -912,6 +944,13 @@ int b200pir_multiply_reg_by_database(b200pir_ctx* c, b200pir_db* db, uint64_t sl
   launch_query_to_dev(G, qd.p, vq.p, c->stream);
   if (db->format == 0) {
     launch_multiply(c->dp, G, db->d.p, qd.p, o.p, (int)slice, 1, 1, 0, 0, c->mul_variant, c->stream);
+  } else if (db->format == 2) {
+    DevBuf<uint8_t> qt(tc5_query_bytes(db->T));
+    DevBuf<uint32_t> zm((size_t)c->slices * rows * 4 * POLY);
+    launch_query_to_tc5(db->T, qd.p, 0, 1, qt.p, c->stream);
+    launch_multiply_tc5(c->dp, db->T, db->t.p, qt.p, zm.p, 0, 1, (int)slice, 1, c->sm_count, c->stream);
+    launch_zmajor_to_ntt32(db->F, zm.p, o.p + (size_t)slice * rows * 4 * POLY, (int)slice, c->stream);
+    B200_CUDA(cudaStreamSynchronize(c->stream));
   } else {
     DevBuf<uint2> qf(imma_query_cells(db->F));
     DevBuf<uint32_t> zm((size_t)c->slices * rows * 4 * POLY);

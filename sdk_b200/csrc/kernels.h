@@ -8,6 +8,7 @@
 //   matrices   : row-major [row][col] of polys, as PolyMatrixRaw / PolyMatrixNTT (poly.rs:59-71)
 #pragma once
 #include "common.cuh"
+#include "tc5_layout.cuh"
 
 namespace b200pir {
 
@@ -89,6 +90,17 @@ void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32
                              int nq, int slices, int variant, cudaStream_t s);
 // z-major product of one slice -> ntt32 [row][ct_row][n][z]
 void launch_zmajor_to_ntt32(const ImmaGeom& F, const uint32_t* in_zm, uint32_t* out, int slice, cudaStream_t s);
+
+// ---- first dimension on tcgen05 (tc5_kernels.cu): operands stored as shared-memory tile images (database format 2)
+size_t tc5_db_bytes(const Tc5Geom& T, int slices);
+size_t tc5_query_bytes(const Tc5Geom& T);                 // 16 queries
+bool tc5_supported(const Tc5Geom& T);
+void launch_db_to_tc5(const Tc5Geom& T, const uint4* db0_slice, uint8_t* dbt, int slice, cudaStream_t s);
+void launch_db_upsert_tc5(const Tc5Geom& T, uint8_t* dbt, int slice, int il, int j, const uint64_t* poly, cudaStream_t s);
+void launch_query_to_tc5(const Tc5Geom& T, const uint4* q_dev, size_t q_stride, int nq, uint8_t* qt, cudaStream_t s);
+// out_zm as launch_multiply_imma; up to 16 queries per pass; one persistent CTA per SM
+void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint8_t* qt, uint32_t* out_zm,
+                         size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s);
 
 // ---- second dimension
 // mult output ntt32 [cnt][r][n][z] -> raw ciphertexts u64 [cnt][r][z]   (server.rs:707-709)

@@ -1,0 +1,373 @@
+// First dimension on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) — database format 2.
+//
+// STATUS: compiles for sm_100a; NOT yet run on a GPU (written after this round's GPU budget was spent).  Nothing selects
+// this path by default (`db_format` 2 must be requested explicitly) and its parity tests are gated behind
+// B200PIR_TEST_TC5=1 until they have passed on hardware.  The arithmetic is the one already proven bit-exact on the
+// legacy mma.sync path (imma_kernels.cu): 28-bit residues as four 7-bit limbs, exact s32 accumulation, recombination
+// with 2^{7s} and Barrett.
+//
+// multiply_reg_by_database (lib/spiral-rs/src/server.rs:155-221) for one NTT coordinate z and modulus n is the integer
+// GEMM  C[ii][(query,row)] = sum_j A[ii][j] * B[j][(query,row)] mod q_n.  Here both operands carry their limb index as
+// part of the GEMM's M / N index, so one UMMA tile produces all 16 limb-pair products separately:
+//
+//     M index = 4 * row_local + l      (32 database rows x 4 limbs  = 128 = UMMA_M)
+//     N index = 4 * col       + m      (32 columns = 16 queries x 2 ciphertext rows, x 4 limbs = 128 = UMMA_N)
+//     K       = 32 values of j per instruction (kind::i8), dim0 / 32 instructions per tile
+//     D[M][N] = sum_j a_l(ii, j) * b_m(j, col)  < dim0 * 2^14 <= 2^24        (exact in s32)
+//
+// The epilogue reads a row of D from TMEM (lane = M index), folds the four m-limbs of every column in registers, reduces,
+// shifts by 7 l, and adds the four l-limbs, which sit in four adjacent lanes, with two shuffles.
+//
+// Operand images.  Both operands are stored in global memory as exact images of the shared-memory tiles the MMA reads
+// (canonical K-major, no swizzle: 8-row x 16-byte core matrices, LBO = 128 B between the two K halves, SBO = 256 B
+// between 8-row groups; byte (midx, k) of a tile lives at (midx>>3)*256 + (k>>4)*128 + (midx&7)*16 + (k&15)), so a tile
+// moves with ONE 1-D bulk copy (cp.async.bulk ... mbarrier::complete_tx::bytes) and needs no tensor map:
+//     dbT[slice][n][z][mt][ks][4096 B]      (mt: 32 rows, ks: 32 values of j)     == 8 bytes per database word, as before
+//     qT [n][z][ks][4096 B]                 (16 queries)
+// One persistent CTA per SM walks the (n, z) pairs; warp 0 = bulk-copy producer, warp 1 = MMA issuer (one thread),
+// warps 2..5 = epilogue (one per TMEM lane quadrant).  Pipelines: A ring (full/empty mbarriers), double-buffered B operand
+// (bfull/bempty), double-buffered accumulator in TMEM (tfull/tempty).
+#include "kernels.h"
+
+namespace b200pir {
+
+namespace {
+
+constexpr int TC5_KS_PER_STAGE = 4;                     // k-steps per A stage
+constexpr int TC5_STAGE_BYTES = TC5_KS_PER_STAGE * TC5_TILE;   // 16 KiB
+constexpr int TC5_STAGES = 5;
+constexpr int TC5_THREADS = 192;                        // 6 warps
+constexpr int TC5_TMEM_COLS = 256;                      // two accumulator buffers of 128 columns
+
+// ---- raw PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "TC5_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra TC5_DONE;\n\t"
+      "bra TC5_WAIT;\n\t"
+      "TC5_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, LBO, SBO in 16-byte
+// units, version 1 (Blackwell), no swizzle, base offset 0
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // [0,14)   start address
+  d |= (uint64_t)((TC5_LBO >> 4) & 0x3FFF) << 16;       // [16,30)  leading-dimension byte offset (K halves)
+  d |= (uint64_t)((TC5_SBO >> 4) & 0x3FFF) << 32;       // [32,46)  stride byte offset (8-row groups)
+  d |= (uint64_t)1 << 46;                               // [46,48)  descriptor version
+  return d;                                             // [61,64)  layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor (InstrDescriptor): D = s32, A = B = unsigned 8 bit, both K-major, dense, no saturation
+__host__ __device__ constexpr uint32_t tc_instr_desc() {
+  return (2u << 4) /* c_format S32 */ | (0u << 7) /* a u8 */ | (0u << 10) /* b u8 */ | (0u << 15) | (0u << 16) |
+         ((uint32_t)(TC5_N >> 3) << 17) | ((uint32_t)(TC5_M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(tc_instr_desc()), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t of the warp gets row (quadrant base + t)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// ---- operand images ---------------------------------------------------------------------------------------------------
+// format 0 slice (uint4 [row][jp][z]) -> tile images.  CTA = (z, mt, ks); thread = (row_local, group of 4 values of j).
+__global__ void __launch_bounds__(256)
+k_db_to_tc5(Tc5Geom T, const uint4* __restrict__ db0_slice, uint8_t* __restrict__ dbt, int slice) {
+  const int z = blockIdx.x, mt = blockIdx.y, ks = blockIdx.z;
+  const Tc5DbThread t = tc5_db_thread(threadIdx.x, mt, ks);
+  const int half = T.dim0 >> 1;
+  uint32_t res[2][4];
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    const int jp = t.jp0 + p;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (t.ii < T.rows && jp < half) w = db0_slice[((size_t)t.ii * half + jp) * POLY + z];
+    res[0][2 * p] = w.x; res[1][2 * p] = w.y; res[0][2 * p + 1] = w.z; res[1][2 * p + 1] = w.w;
+  }
+#pragma unroll
+  for (int n = 0; n < 2; n++) tc5_db_store(dbt + tc5_db_tile(T, slice, n, z, mt, ks) * TC5_TILE, t, res[n]);
+}
+
+// one item polynomial (2048 packed words lo|hi<<32) into the tile images (byte writes)
+__global__ void k_db_upsert_tc5(Tc5Geom T, uint8_t* dbt, int slice, int il, int j, const uint64_t* poly) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= POLY) return;
+  const int mt = il >> 5, row_local = il & 31, ks = j >> 5, k = j & 31;
+  const uint64_t w = poly[z];
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const uint32_t r = n ? (uint32_t)(w >> 32) : (uint32_t)w;
+    uint8_t* tile = dbt + tc5_db_tile(T, slice, n, z, mt, ks) * TC5_TILE;
+#pragma unroll
+    for (int l = 0; l < 4; l++) tile[tc5_tile_off(tc5_m_index(row_local, l), k)] = (uint8_t)((r >> (7 * l)) & 127u);
+  }
+}
+
+// expanded queries (uint4 [j][z] per query, q_stride apart) -> qT.  CTA = (pair of z, ks): every 32-byte sector it reads is
+// fully used; the four 4 KiB tiles (2 z x 2 n) are assembled in shared memory and written out contiguously.
+__global__ void __launch_bounds__(256)
+k_query_to_tc5(Tc5Geom T, const uint4* __restrict__ q_dev, size_t q_stride, int nq, uint8_t* __restrict__ qt) {
+  __shared__ __align__(16) uint8_t img[2][2][TC5_TILE];          // [z parity][n]
+  const int z0 = blockIdx.x * 2, ks = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * 2 * TC5_TILE / 16; i += blockDim.x) reinterpret_cast<uint4*>(&img[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // 16 queries x 32 values of j x 2 z = 1024 cells, 4 per thread; consecutive threads take consecutive z, then j, then query
+  for (int cell = threadIdx.x; cell < 16 * 32 * 2; cell += blockDim.x) {
+    const Tc5QueryCell qc = tc5_query_cell(cell);
+    const int j = ks * 32 + qc.k;
+    if (qc.q < nq && j < T.dim0) {
+      const uint4 w = q_dev[(size_t)qc.q * q_stride + (size_t)j * POLY + z0 + qc.zp];
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) tc5_query_store(img[qc.zp][n], qc.q, r, qc.k, r ? (n ? w.w : w.z) : (n ? w.y : w.x));
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int zp = 0; zp < 2; zp++)
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      uint4* dst = reinterpret_cast<uint4*>(qt + tc5_q_tile(T, n, z0 + zp, ks) * TC5_TILE);
+      dst[threadIdx.x] = reinterpret_cast<const uint4*>(&img[zp][n][0])[threadIdx.x];
+    }
+}
+
+// ---- the multiply -----------------------------------------------------------------------------------------------------
+struct Tc5Smem {
+  uint64_t full[TC5_STAGES], empty[TC5_STAGES];
+  uint64_t bfull[2], bempty[2];
+  uint64_t tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+// out_zm[query][slice][n][z][row][ct_row] (u32), the format of k_multiply_imma
+__global__ void __launch_bounds__(TC5_THREADS, 1)
+k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const uint8_t* __restrict__ qt,
+               uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count) {
+  extern __shared__ __align__(1024) uint8_t tc5_smem[];
+  uint8_t* smem_b = tc5_smem;                                         // [2][ks][4096]
+  uint8_t* smem_a = smem_b + (size_t)2 * T.ks * TC5_TILE;             // [STAGES][16 KiB]
+  Tc5Smem* S = reinterpret_cast<Tc5Smem*>(smem_a + (size_t)TC5_STAGES * TC5_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages_per_tile = (T.ks + TC5_KS_PER_STAGE - 1) / TC5_KS_PER_STAGE;
+  const int tiles_per_item = slice_count * T.mt;
+  const int n_items = 2 * POLY;
+  const uint32_t b_bytes = (uint32_t)T.ks * TC5_TILE;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC5_STAGES; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&S->bfull[b], 1); mbar_init(&S->bempty[b], 1);
+      mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                                    // TMEM allocation is owned by the MMA warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
+                 "n"(TC5_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S->tmem_base;
+
+  if (warp == 0) {
+    // ===== producer: one thread issues every bulk copy =====
+    if (lane == 0) {
+      int stage = 0; uint32_t sphase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        const int n = item & 1, z = item >> 1, bb = it & 1;
+        mbar_wait(&S->bempty[bb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&S->bfull[bb], b_bytes);
+        bulk_g2s(smem_b + (size_t)bb * b_bytes, qt + tc5_q_tile(T, n, z, 0) * TC5_TILE, b_bytes, &S->bfull[bb]);
+        for (int t = 0; t < tiles_per_item; t++) {
+          const int slice = slice_begin + t / T.mt, mt = t % T.mt;
+          const uint8_t* src = dbt + tc5_db_tile(T, slice, n, z, mt, 0) * TC5_TILE;
+          for (int st = 0; st < stages_per_tile; st++) {
+            const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
+            mbar_wait(&S->empty[stage], sphase ^ 1);
+            mbar_expect_tx(&S->full[stage], (uint32_t)ks_here * TC5_TILE);
+            bulk_g2s(smem_a + (size_t)stage * TC5_STAGE_BYTES, src + (size_t)st * TC5_STAGE_BYTES, (uint32_t)ks_here * TC5_TILE,
+                     &S->full[stage]);
+            if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0) {
+      int stage = 0; uint32_t sphase = 0;
+      int it = 0, tile_no = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        const int bb = it & 1;
+        mbar_wait(&S->bfull[bb], (it >> 1) & 1);
+        const uint32_t b_addr = smem_u32(smem_b + (size_t)bb * b_bytes);
+        for (int t = 0; t < tiles_per_item; t++, tile_no++) {
+          const int ab = tile_no & 1;
+          mbar_wait(&S->tempty[ab], ((tile_no >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + (uint32_t)ab * TC5_N;
+          for (int st = 0; st < stages_per_tile; st++) {
+            const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
+            mbar_wait(&S->full[stage], sphase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
+            for (int kk = 0; kk < ks_here; kk++) {
+              const int ks = st * TC5_KS_PER_STAGE + kk;
+              tc_mma_i8(d_addr, tc_smem_desc(a_addr + kk * TC5_TILE), tc_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
+            }
+            tc_commit(&S->empty[stage]);                              // frees the A stage when these MMAs have completed
+            if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
+          }
+          tc_commit(&S->tfull[ab]);                                   // accumulator ready for the epilogue
+        }
+        tc_commit(&S->bempty[bb]);                                    // every MMA reading this B buffer has completed
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int l = tc5_lane_limb(lane);                                // database limb held by this lane
+    const uint32_t q0 = P.q[0], q1 = P.q[1];
+    int it = 0, tile_no = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int n = item & 1, z = item >> 1;
+      const uint32_t q = n ? q1 : q0;
+      const uint64_t cr1 = n ? P.cr1[1] : P.cr1[0];
+      for (int t = 0; t < tiles_per_item; t++, tile_no++) {
+        const int slice = slice_begin + t / T.mt, mt = t % T.mt;
+        const int ab = tile_no & 1;
+        mbar_wait(&S->tfull[ab], (tile_no >> 1) & 1);
+        tc_fence_after();
+        const int ii = mt * 32 + tc5_lane_row(quad, lane);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * TC5_N;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; chunk++) {                     // 32 TMEM columns = 8 GEMM columns = 4 queries
+          uint32_t v[32];
+          tc_ld32(taddr + chunk * 32, v);
+          tc_wait_ld();
+          uint64_t tot[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            uint64_t u = tc5_fold_column(v + 4 * c, l, cr1, q);       // < 2^49
+            u += shfl_xor_u64(u, 1);
+            u += shfl_xor_u64(u, 2);                                  // all four limb lanes hold the sum (< 2^51)
+            tot[c] = u;
+          }
+          // lane l stores query 4*chunk + l (both ciphertext rows = GEMM columns 2l, 2l+1 of this chunk)
+          uint64_t e = tot[0], o = tot[1];
+#pragma unroll
+          for (int c = 1; c < 4; c++)
+            if (l == c) { e = tot[2 * c]; o = tot[2 * c + 1]; }
+          const int qi = tc5_lane_query(chunk, lane);
+          if (qi < nq && ii < T.rows) {
+            uint2 r = make_uint2(tc5_barrett(e, cr1, q), tc5_barrett(o, cr1, q));
+            uint32_t* dst = out_zm + (size_t)qi * out_stride + ((((size_t)slice * 2 + n) * POLY + z) * T.rows + ii) * 2;
+            *reinterpret_cast<uint2*>(dst) = r;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->tempty[ab]);                   // this quadrant has drained the accumulator
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC5_TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+size_t tc5_db_bytes(const Tc5Geom& T, int slices) { return (size_t)slices * 2 * POLY * T.mt * T.ks * TC5_TILE; }
+size_t tc5_query_bytes(const Tc5Geom& T) { return (size_t)2 * POLY * T.ks * TC5_TILE; }
+static size_t tc5_smem_bytes(const Tc5Geom& T) {
+  return (size_t)2 * T.ks * TC5_TILE + (size_t)TC5_STAGES * TC5_STAGE_BYTES + sizeof(Tc5Smem) + 16;
+}
+bool tc5_supported(const Tc5Geom& T) { return T.dim0 % 2 == 0 && tc5_smem_bytes(T) <= 227 * 1024; }
+
+void launch_db_to_tc5(const Tc5Geom& T, const uint4* db0_slice, uint8_t* dbt, int slice, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_db_to_tc5<<<dim3(POLY, T.mt, T.ks), 256, 0, s>>>(T, db0_slice, dbt, slice);
+}
+void launch_db_upsert_tc5(const Tc5Geom& T, uint8_t* dbt, int slice, int il, int j, const uint64_t* poly, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_db_upsert_tc5<<<POLY / 256, 256, 0, s>>>(T, dbt, slice, il, j, poly);
+}
+void launch_query_to_tc5(const Tc5Geom& T, const uint4* q_dev, size_t q_stride, int nq, uint8_t* qt, cudaStream_t s) {
+  if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
+  ++g_kernel_launches;
+  k_query_to_tc5<<<dim3(POLY / 2, T.ks), 256, 0, s>>>(T, q_dev, q_stride, nq, qt);
+}
+void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint8_t* qt, uint32_t* out_zm,
+                         size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s) {
+  if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
+  if (!tc5_supported(T)) throw Error(-2, "tcgen05 multiply: dim0 too large for one CTA's shared memory");
+  const size_t smem = tc5_smem_bytes(T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_multiply_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  ++g_kernel_launches;
+  const int grid = sm_count > 0 ? (sm_count < 2 * POLY ? sm_count : 2 * POLY) : 148;
+  k_multiply_tc5<<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count);
+}
+
+}  // namespace b200pir

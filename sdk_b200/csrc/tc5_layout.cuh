@@ -1,0 +1,86 @@
+// Index / limb arithmetic of the tcgen05 first dimension (tc5_kernels.cu), as __host__ __device__ functions so that the
+// operand images and the epilogue can be emulated thread by thread on the CPU (tests/cpp/tc5_emul.cpp) against the
+// canonical UMMA shared-memory layout (K-major, no swizzle: cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::K>).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define TC5_HD __host__ __device__ __forceinline__
+#else
+#define TC5_HD inline
+#endif
+
+namespace b200pir {
+
+struct Tc5Geom { int dim0, rows, mt /* ceil(rows/32) */, ks /* ceil(dim0/32) */; };
+inline Tc5Geom make_tc5_geom(int dim0, int rows) { return Tc5Geom{dim0, rows, (rows + 31) / 32, (dim0 + 31) / 32}; }
+
+constexpr int TC5_M = 128, TC5_N = 128, TC5_K = 32;
+constexpr int TC5_TILE = TC5_M * TC5_K;                 // 4096 bytes, A and B tiles alike
+constexpr int TC5_LBO = 128;                            // bytes between the two 16-byte K halves of a core-matrix row group
+constexpr int TC5_SBO = 256;                            // bytes between consecutive 8-row groups
+
+// byte (midx, k) of a 128 x 32 tile: 8-row x 16-byte core matrices
+TC5_HD int tc5_tile_off(int midx, int k) { return (midx >> 3) * TC5_SBO + (k >> 4) * TC5_LBO + (midx & 7) * 16 + (k & 15); }
+// GEMM indices: M = 4 * row_local + l (database row within the 32-row tile, limb), N = 4 * col + m (col = 2 query + ct row)
+TC5_HD int tc5_m_index(int row_local, int l) { return 4 * row_local + l; }
+TC5_HD int tc5_n_index(int col, int m) { return 4 * col + m; }
+TC5_HD size_t tc5_db_tile(const Tc5Geom& T, int slice, int n, int z, int mt, int ks) {
+  return ((((size_t)slice * 2 + n) * 2048 + z) * T.mt + mt) * T.ks + ks;
+}
+TC5_HD size_t tc5_q_tile(const Tc5Geom& T, int n, int z, int ks) { return ((size_t)n * 2048 + z) * T.ks + ks; }
+// limb l (7 bits) of four residues as four bytes, lowest address first
+TC5_HD uint32_t tc5_limb4(const uint32_t (&r)[4], int l) {
+  const int sh = 7 * l;
+  return ((r[0] >> sh) & 127u) | (((r[1] >> sh) & 127u) << 8) | (((r[2] >> sh) & 127u) << 16) | (((r[3] >> sh) & 127u) << 24);
+}
+
+// ---- database image: thread tid of the CTA of row tile mt / k-step ks handles one row and four consecutive j
+struct Tc5DbThread { int row_local, kq, ii, jp0; };
+TC5_HD Tc5DbThread tc5_db_thread(int tid, int mt, int ks) {
+  Tc5DbThread t;
+  t.row_local = tid >> 3;
+  t.kq = tid & 7;
+  t.ii = mt * 32 + t.row_local;
+  t.jp0 = (ks * 32 + 4 * t.kq) >> 1;                    // the thread reads cells jp0 and jp0 + 1 (two j each)
+  return t;
+}
+// res[i] = residue (one modulus) of j = ks*32 + 4 kq + i; writes the thread's four 4-byte words of one tile
+TC5_HD void tc5_db_store(uint8_t* tile, const Tc5DbThread& t, const uint32_t (&res)[4]) {
+  for (int l = 0; l < 4; l++) {
+    const uint32_t v = tc5_limb4(res, l);
+    uint8_t* p = tile + tc5_tile_off(tc5_m_index(t.row_local, l), 4 * t.kq);
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+  }
+}
+
+// ---- query image: cell = (query, k, z parity) of the CTA of k-step ks
+struct Tc5QueryCell { int zp, k, q; };
+TC5_HD Tc5QueryCell tc5_query_cell(int cell) { return Tc5QueryCell{cell & 1, (cell >> 1) & 31, cell >> 6}; }
+// value = residue (one modulus) of query q, ciphertext row r at (j = ks*32 + k): its four limb bytes
+TC5_HD void tc5_query_store(uint8_t* tile, int q, int r, int k, uint32_t value) {
+  for (int m = 0; m < 4; m++) tile[tc5_tile_off(tc5_n_index(2 * q + r, m), k)] = (uint8_t)((value >> (7 * m)) & 127u);
+}
+
+// ---- epilogue: TMEM lane = M index; a warp owns the quadrant `quad` (32 lanes), a chunk is 32 consecutive columns
+TC5_HD int tc5_lane_row(int quad, int lane) { return quad * 8 + (lane >> 2); }     // row_local of this lane
+TC5_HD int tc5_lane_limb(int lane) { return lane & 3; }
+TC5_HD int tc5_lane_query(int chunk, int lane) { return chunk * 4 + (lane & 3); }  // the query this lane stores
+TC5_HD uint32_t tc5_barrett(uint64_t x, uint64_t cr1, uint32_t q) {                // == barrett64 (common.cuh)
+#if defined(__CUDA_ARCH__)
+  const uint64_t t = __umul64hi(x, cr1);
+#else
+  const uint64_t t = (uint64_t)(((unsigned __int128)x * cr1) >> 64);
+#endif
+  const uint32_t r = (uint32_t)(x - t * (uint64_t)q);
+  const uint32_t r2 = r - q;
+  return r < r2 ? r : r2;
+}
+// the four m-limb partial sums of one GEMM column -> this lane's contribution (before the two shuffles over l)
+TC5_HD uint64_t tc5_fold_column(const uint32_t* v4, int l, uint64_t cr1, uint32_t q) {
+  const uint64_t s = (uint64_t)v4[0] + ((uint64_t)v4[1] << 7) + ((uint64_t)v4[2] << 14) + ((uint64_t)v4[3] << 21);   // < 2^46
+  return (uint64_t)tc5_barrett(s, cr1, q) << (7 * l);                                                              // < 2^49
+}
+
+}  // namespace b200pir

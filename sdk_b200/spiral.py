@@ -92,7 +92,8 @@ class Database:
 
     def __init__(self, params, shard_index=0, shard_count=1, fmt=None):
         """fmt: 0 = IMAD layout (single-query HBM roofline kernel), 1 = INT8 tensor-core fragment order
-        (batched queries); None = the context's current "db_format" option."""
+        (batched queries), 2 = tcgen05 tile images (experimental: not yet validated on hardware);
+        None = the context's current "db_format" option."""
         self.params = params
         h = C.c_void_p()
         if fmt is not None:

@@ -46,3 +46,13 @@ def test_cooperative_ntt_emulation_matches_oracle(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "ntt_core_emul.cpp")])
     out = subprocess.check_output([exe], text=True)
     assert out.strip() == "OK", out
+
+
+def test_tcgen05_operand_images_and_epilogue_emulation(tmp_path):
+    """tests/cpp/tc5_emul.cpp: the per-thread image builders and the epilogue lane arithmetic of the tcgen05 first
+    dimension, run on the CPU against the canonical UMMA K-major layout definition and 128-bit reference sums."""
+    exe = str(tmp_path / "tc5_emul")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "tc5_emul.cpp")])
+    out = subprocess.check_output([exe], text=True)
+    assert out.strip() == "tc5 emulation ok", out
