@@ -28,6 +28,9 @@
 // warps 2..5 = epilogue (one per TMEM lane quadrant).  Pipelines: A ring (full/empty mbarriers), double-buffered B operand
 // (bfull/bempty), double-buffered accumulator in TMEM (tfull/tempty).
 #include "kernels.h"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace b200pir {
 
@@ -38,6 +41,7 @@ constexpr int TC5_STAGE_BYTES = TC5_KS_PER_STAGE * TC5_TILE;   // 16 KiB
 constexpr int TC5_STAGES = 5;
 constexpr int TC5_THREADS = 192;                        // 6 warps
 constexpr int TC5_TMEM_COLS = 256;                      // two accumulator buffers of 128 columns
+constexpr int TC5_DBG_TILES = 4;
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -192,7 +196,8 @@ struct Tc5Smem {
 // out_zm[query][slice][n][z][row][ct_row] (u32), the format of k_multiply_imma
 __global__ void __launch_bounds__(TC5_THREADS, 1)
 k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const uint8_t* __restrict__ qt,
-               uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count) {
+               uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count,
+               uint32_t* __restrict__ dbg /* bring-up aid: raw accumulators of CTA 0's first TC5_DBG_TILES tiles, or null */) {
   extern __shared__ __align__(1024) uint8_t tc5_smem[];
   uint8_t* smem_b = tc5_smem;                                         // [2][ks][4096]
   uint8_t* smem_a = smem_b + (size_t)2 * T.ks * TC5_TILE;             // [STAGES][16 KiB]
@@ -299,6 +304,10 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
           uint32_t v[32];
           tc_ld32(taddr + chunk * 32, v);
           tc_wait_ld();
+          if (dbg && blockIdx.x == 0 && tile_no < TC5_DBG_TILES) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) dbg[((size_t)tile_no * TC5_M + quad * 32 + lane) * TC5_N + chunk * 32 + c] = v[c];
+          }
           uint64_t tot[8];
 #pragma unroll
           for (int c = 0; c < 8; c++) {
@@ -367,7 +376,23 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
   }
   ++g_kernel_launches;
   const int grid = sm_count > 0 ? (sm_count < 2 * POLY ? sm_count : 2 * POLY) : 148;
-  k_multiply_tc5<<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count);
+  // bring-up aid (scripts/tc5_probe.py): B200PIR_TC5_DUMP=<file> receives the raw s32 accumulators D[M][N] of the first
+  // tiles CTA 0 computes (item n = 0, z = 0), so a mismatch can be traced to the operand layout / TMEM mapping assumption
+  const char* dump = getenv("B200PIR_TC5_DUMP");
+  uint32_t* dbg = nullptr;
+  const size_t dbg_words = (size_t)TC5_DBG_TILES * TC5_M * TC5_N;
+  if (dump) {
+    B200_CUDA(cudaMalloc(&dbg, dbg_words * 4));
+    B200_CUDA(cudaMemsetAsync(dbg, 0xFF, dbg_words * 4, s));
+  }
+  k_multiply_tc5<<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count, dbg);
+  if (dump) {
+    std::vector<uint32_t> host(dbg_words);
+    B200_CUDA(cudaStreamSynchronize(s));
+    B200_CUDA(cudaMemcpy(host.data(), dbg, dbg_words * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    if (FILE* f = fopen(dump, "wb")) { fwrite(host.data(), 4, dbg_words, f); fclose(f); }
+  }
 }
 
 }  // namespace b200pir
