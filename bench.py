@@ -164,6 +164,7 @@ def cpu_process_query_sample(kw, threads=None, sample_rows=64):
     import numpy as np
     import oracle_lib as O
     simd = "AVX2 first dimension" if O.LIB.orc_use_avx2_multiply(1) else "scalar first dimension"
+    simd += " and transforms" if O.LIB.orc_use_avx2_ntt(1) else ", scalar transforms"
     if threads:
         O.LIB.orc_set_num_threads(int(threads))
     else:

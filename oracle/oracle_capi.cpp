@@ -439,6 +439,41 @@ int orc_dpir_transpose_expand_concat_cols_squish(uint32_t* out, const uint32_t* 
   ORC_CATCH
 }
 
+// CPU-baseline switch: 1 = AVX2 transforms everywhere ntt_forward / ntt_inverse are called (bit-identical to the scalar ones)
+int orc_use_avx2_ntt(int on) {
+#if defined(__AVX2__)
+  g_use_avx2_ntt = on != 0;
+  return 1;
+#else
+  (void)on;
+  return 0;
+#endif
+}
+// direct entry points for the equality test
+int orc_ntt_scalar(void* h, uint64_t* polys, size_t count, int inverse) {
+  ORC_TRY
+  const Params& p = *(Params*)h;
+  for (size_t i = 0; i < count; i++) {
+    if (inverse) ntt_inverse_scalar(p, polys + i * p.crt_count * p.poly_len);
+    else ntt_forward_scalar(p, polys + i * p.crt_count * p.poly_len);
+  }
+  ORC_CATCH
+}
+int orc_ntt_avx2(void* h, uint64_t* polys, size_t count, int inverse) {
+  ORC_TRY
+#if defined(__AVX2__)
+  const Params& p = *(Params*)h;
+  for (size_t i = 0; i < count; i++) {
+    if (inverse) ntt_inverse_avx2(p, polys + i * p.crt_count * p.poly_len);
+    else ntt_forward_avx2(p, polys + i * p.crt_count * p.poly_len);
+  }
+#else
+  (void)h; (void)polys; (void)count; (void)inverse;
+  throw std::runtime_error("built without AVX2");
+#endif
+  ORC_CATCH
+}
+
 // CPU-baseline switch: 1 = AVX2 first-dimension kernel inside process_query (returns 0 when not compiled with AVX2)
 int orc_use_avx2_multiply(int on) {
 #if defined(__AVX2__)

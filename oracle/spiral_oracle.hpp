@@ -335,7 +335,7 @@ inline Params params_from_scalars(size_t n, size_t nu_1, size_t nu_2, u64 p, u64
 
 // ---------------------------------------------------------------- ntt.rs (scalar = the spec)
 // ntt.rs:67-113
-inline void ntt_forward(const Params& p, u64* operand_overall) {
+inline void ntt_forward_scalar(const Params& p, u64* operand_overall) {
   size_t lg = p.poly_len_log2, n = (size_t)1 << lg;
   for (size_t cm = 0; cm < p.crt_count; cm++) {
     u64* op = operand_overall + cm * n;
@@ -365,7 +365,7 @@ inline void ntt_forward(const Params& p, u64* operand_overall) {
   }
 }
 // ntt.rs:212-258
-inline void ntt_inverse(const Params& p, u64* operand_overall) {
+inline void ntt_inverse_scalar(const Params& p, u64* operand_overall) {
   size_t n = p.poly_len;
   for (size_t cm = 0; cm < p.crt_count; cm++) {
     u64* op = operand_overall + cm * n;
@@ -394,6 +394,125 @@ inline void ntt_inverse(const Params& p, u64* operand_overall) {
       op[i] -= (u64)(op[i] >= q) * q;
     }
   }
+}
+
+#if defined(__AVX2__)
+// The reference's AVX2 transforms (ntt.rs:120-210 forward, :260-345 inverse) keep four u64 lanes with 32-bit content
+// and use _mm256_mul_epu32 for the 32x32->64 products.  Restated here for the CPU baseline with ONE deliberate
+// difference: the reference's vector code compares with `>` where its scalar code (and this oracle) compare with
+// `>=`, so it can leave the non-canonical representatives q / 2q where the scalar code produces 0; these versions
+// use `>=` (cmpgt against bound - 1) and are therefore bit-identical to ntt_forward_scalar / ntt_inverse_scalar
+// (asserted in tests/test_oracle_kats.py).
+inline __m256i avx2_sub_if_ge(__m256i x, __m256i bound, __m256i bound_m1) {
+  return _mm256_sub_epi64(x, _mm256_and_si256(_mm256_cmpgt_epi64(x, bound_m1), bound));
+}
+inline void ntt_forward_avx2(const Params& p, u64* operand_overall) {
+  size_t lg = p.poly_len_log2, n = (size_t)1 << lg;
+  for (size_t cm = 0; cm < p.crt_count; cm++) {
+    u64* op = operand_overall + cm * n;
+    const u64* ft = p.ntt_tables[cm][0].data();
+    const u64* ftp = p.ntt_tables[cm][1].data();
+    const u32 q = (u32)p.moduli[cm], two_q = 2 * q;
+    const __m256i vq = _mm256_set1_epi64x(q), v2q = _mm256_set1_epi64x(two_q), v2q_m1 = _mm256_set1_epi64x((long long)two_q - 1),
+                  vq_m1 = _mm256_set1_epi64x((long long)q - 1);
+    for (size_t mm = 0; mm < lg; mm++) {
+      size_t m = (size_t)1 << mm, t = n >> (mm + 1);
+      for (size_t i = 0; i < m; i++) {
+        const u64 w = ft[m + i], wp = ftp[m + i];
+        u64* o = op + i * 2 * t;
+        if (t < 4) {
+          for (size_t j = 0; j < t; j++) {
+            u32 x = (u32)o[j], y = (u32)o[t + j];
+            u32 curr_x = x - (two_q * (u32)(x >= two_q));
+            u64 q_tmp = ((u64)y * wp) >> 32;
+            u64 q_new = w * (u64)y - q_tmp * (u64)q;
+            o[j] = (u64)curr_x + q_new;
+            o[t + j] = (u64)curr_x + ((u64)two_q - q_new);
+          }
+        } else {
+          const __m256i vw = _mm256_set1_epi64x((long long)w), vwp = _mm256_set1_epi64x((long long)wp);
+          for (size_t j = 0; j < t; j += 4) {
+            __m256i x = _mm256_loadu_si256((const __m256i*)(o + j)), y = _mm256_loadu_si256((const __m256i*)(o + t + j));
+            __m256i curr_x = avx2_sub_if_ge(x, v2q, v2q_m1);
+            __m256i q_val = _mm256_srli_epi64(_mm256_mul_epu32(y, vwp), 32);
+            __m256i q_fin = _mm256_sub_epi64(_mm256_mul_epu32(y, vw), _mm256_mul_epu32(q_val, vq));
+            _mm256_storeu_si256((__m256i*)(o + j), _mm256_add_epi64(curr_x, q_fin));
+            _mm256_storeu_si256((__m256i*)(o + t + j), _mm256_add_epi64(curr_x, _mm256_sub_epi64(v2q, q_fin)));
+          }
+        }
+      }
+    }
+    for (size_t i = 0; i < n; i += 4) {
+      __m256i x = _mm256_loadu_si256((const __m256i*)(op + i));
+      x = avx2_sub_if_ge(x, v2q, v2q_m1);
+      x = avx2_sub_if_ge(x, vq, vq_m1);
+      _mm256_storeu_si256((__m256i*)(op + i), x);
+    }
+  }
+}
+inline void ntt_inverse_avx2(const Params& p, u64* operand_overall) {
+  size_t n = p.poly_len;
+  for (size_t cm = 0; cm < p.crt_count; cm++) {
+    u64* op = operand_overall + cm * n;
+    const u64* it = p.ntt_tables[cm][2].data();
+    const u64* itp = p.ntt_tables[cm][3].data();
+    const u64 q = p.moduli[cm], two_q = 2 * q;
+    const __m256i vq = _mm256_set1_epi64x((long long)q), v2q = _mm256_set1_epi64x((long long)two_q),
+                  v2q_m1 = _mm256_set1_epi64x((long long)two_q - 1), vq_m1 = _mm256_set1_epi64x((long long)q - 1),
+                  one = _mm256_set1_epi64x(1);
+    for (size_t mm = p.poly_len_log2; mm-- > 0;) {
+      size_t h = (size_t)1 << mm, t = n >> (mm + 1);
+      for (size_t i = 0; i < h; i++) {
+        const u64 w = it[h + i], wp = itp[h + i];
+        u64* o = op + i * 2 * t;
+        if (t < 4) {
+          for (size_t j = 0; j < t; j++) {
+            u64 x = o[j], y = o[t + j];
+            u64 t_tmp = two_q - y + x;
+            u64 curr_x = x + y - (two_q * (u64)((x << 1) >= t_tmp));
+            u64 h_tmp = (t_tmp * wp) >> 32;
+            o[j] = (curr_x + (q * (t_tmp & 1))) >> 1;
+            o[t + j] = w * t_tmp - h_tmp * q;
+          }
+        } else {
+          const __m256i vw = _mm256_set1_epi64x((long long)w), vwp = _mm256_set1_epi64x((long long)wp);
+          for (size_t j = 0; j < t; j += 4) {
+            __m256i x = _mm256_loadu_si256((const __m256i*)(o + j)), y = _mm256_loadu_si256((const __m256i*)(o + t + j));
+            __m256i t_tmp = _mm256_add_epi64(_mm256_sub_epi64(v2q, y), x);                 // in [1, 4q)
+            __m256i sum = _mm256_add_epi64(x, y);
+            // (x << 1) >= t_tmp  <=>  x + y >= 2q
+            __m256i curr_x = avx2_sub_if_ge(sum, v2q, v2q_m1);
+            __m256i h_tmp = _mm256_srli_epi64(_mm256_mul_epu32(t_tmp, vwp), 32);
+            __m256i odd = _mm256_cmpeq_epi64(_mm256_and_si256(t_tmp, one), one);
+            __m256i res_x = _mm256_srli_epi64(_mm256_add_epi64(curr_x, _mm256_and_si256(odd, vq)), 1);
+            __m256i res_y = _mm256_sub_epi64(_mm256_mul_epu32(t_tmp, vw), _mm256_mul_epu32(h_tmp, vq));
+            _mm256_storeu_si256((__m256i*)(o + j), res_x);
+            _mm256_storeu_si256((__m256i*)(o + t + j), res_y);
+          }
+        }
+      }
+    }
+    for (size_t i = 0; i < n; i += 4) {
+      __m256i x = _mm256_loadu_si256((const __m256i*)(op + i));
+      x = avx2_sub_if_ge(x, v2q, v2q_m1);
+      x = avx2_sub_if_ge(x, vq, vq_m1);
+      _mm256_storeu_si256((__m256i*)(op + i), x);
+    }
+  }
+}
+#endif
+static bool g_use_avx2_ntt = false;     // CPU-baseline switch (oracle_capi.cpp orc_use_avx2_ntt); parity tests use the scalar path
+inline void ntt_forward(const Params& p, u64* operand_overall) {
+#if defined(__AVX2__)
+  if (g_use_avx2_ntt) { ntt_forward_avx2(p, operand_overall); return; }
+#endif
+  ntt_forward_scalar(p, operand_overall);
+}
+inline void ntt_inverse(const Params& p, u64* operand_overall) {
+#if defined(__AVX2__)
+  if (g_use_avx2_ntt) { ntt_inverse_avx2(p, operand_overall); return; }
+#endif
+  ntt_inverse_scalar(p, operand_overall);
 }
 
 // ---------------------------------------------------------------- poly.rs

@@ -215,3 +215,31 @@ def test_chacha20_block_rfc8439_vector():
     exp = [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3, 0xc7f4d1c7, 0x0368c033, 0x9aaa2204, 0x4e6cd4c3,
            0x466482d2, 0x09aa9f07, 0x05d7c214, 0xa2028bd9, 0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
     assert [int(x) for x in out] == exp
+
+
+def test_avx2_transforms_equal_scalar_transforms():
+    # the CPU baseline's AVX2 NTTs (restating ntt.rs:120-210, :260-345 with the scalar code's >= comparisons) must be
+    # bit-identical to the scalar transforms the parity tests use, including lazy-range and boundary inputs
+    P = O.Params.named("T")
+    if not LIB.orc_use_avx2_ntt(0):
+        pytest.skip("oracle built without AVX2")
+    rng = np.random.default_rng(99)
+    q = [268369921, 249561089]
+    count = 24
+    v = np.empty((count, 2, 2048), dtype=np.uint64)
+    for n in range(2):
+        v[:, n, :] = rng.integers(0, q[n], (count, 2048), dtype=np.uint64)
+        v[0, n, :] = 0
+        v[1, n, :] = q[n] - 1
+        v[2, n, :] = rng.integers(0, 4 * q[n], 2048, dtype=np.uint64)       # lazy-range inputs (< 4q)
+        v[3, n, ::2] = q[n] - 1
+        v[3, n, 1::2] = 0
+    for inverse in (0, 1):
+        a, b = v.copy(), v.copy()
+        if inverse:      # inverse transforms take values in [0, 2q)
+            for n in range(2):
+                a[:, n, :] %= np.uint64(2 * q[n])
+            b = a.copy()
+        assert LIB.orc_ntt_scalar(P.hp, O._p64(a.reshape(-1)), count, inverse) == 0
+        assert LIB.orc_ntt_avx2(P.hp, O._p64(b.reshape(-1)), count, inverse) == 0
+        assert np.array_equal(a, b), inverse
