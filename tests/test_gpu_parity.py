@@ -723,3 +723,31 @@ def test_wire_formats_deserialize_and_process(name):
         S.Query.deserialize(G, blobs[0][0][:-1])
     gpp.close()
     gpp2.close()
+
+
+# ------------------------------------------------------------------ golden fixtures (tests/golden/spiral_golden.json)
+@pytest.mark.parametrize("case", ["T_expand", "T1_expand", "T0_expand", "T_direct"])
+def test_cuda_path_reproduces_golden_fixtures(case):
+    """Response bytes of the CUDA path == the frozen fixtures (sha256), for both database layouts."""
+    import json
+    import os
+    import golden_cases as GC
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spiral_golden.json")) as f:
+        gold = json.load(f)["cases"][case]
+    S = _gpu()
+    P, cl, pp, db, queries = GC.build_case(case)
+    expand = GC.GOLDEN_CASES[case][1]
+    assert GC.sha(db) == gold["db_sha256"]
+    G = S.Params(expand_queries=expand, **P.kw)
+    gpp = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
+    for fmt in (1, 0):
+        gdb = S.Database.from_words(G, db, fmt=fmt)
+        for (idx, q), g in zip(queries, gold["queries"]):
+            assert idx == g["idx"]
+            query = S.Query(ct=q["ct"]) if expand else S.Query(v_buf=q["v_buf"], v_ct=q["v_ct"])
+            got = S.process_query(G, gpp, query, gdb)
+            assert GC.sha(got) == g["response_sha256"], (case, fmt, idx)
+            assert [int(x) for x in got[:16]] == g["response_head"]
+        gdb.close()
+    gpp.close()
+    G.close()

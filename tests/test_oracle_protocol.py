@@ -118,3 +118,15 @@ def test_wire_formats_round_trip(name):
     qb = cl.query_bytes()
     assert qb.size == P.query_bytes
     assert np.array_equal(P.query_deserialize(qb), q["ct"])
+
+
+def test_oracle_reproduces_golden_fixtures():
+    # tests/golden/spiral_golden.json was frozen from this oracle after the KAT pinning; any drift shows up here
+    import json
+    import os
+    import golden_cases as GC
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spiral_golden.json")) as f:
+        gold = json.load(f)
+    assert gold["seed_client"] == GC.GOLDEN_SEED_CLIENT and gold["seed_db"] == GC.GOLDEN_SEED_DB
+    for case in GC.GOLDEN_CASES:
+        assert GC.oracle_record(case) == gold["cases"][case], case
