@@ -72,6 +72,10 @@ void b200pir_db_destroy(b200pir_db* db);
 int b200pir_db_upload_slice(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, const uint64_t* words, size_t n_words);
 /* Whole db: &[u64] of instances*n^2 slices. */
 int b200pir_db_upload(b200pir_ctx* ctx, b200pir_db* db, const uint64_t* words, size_t n_words);
+/* load_preprocessed_db_from_file (server.rs:373-386; lib/server/src/db/loading.rs:263-276): `path` holds the native-endian
+ * u64 stream of the whole database (slices*dim0*num_per*2048 words, the layout b200pir_db_upload takes); it is streamed
+ * to the GPU through a staging buffer. */
+int b200pir_db_load_file(b200pir_ctx* ctx, b200pir_db* db, const char* path);
 /* One preprocessed item polynomial: 2048 packed words (lib/server/src/db/loading.rs:34-41 pack_ntt_poly,
  * :317-359 update_item_raw -> db.upsert(inst_trial*num_items + db_idx)); item_idx = j*num_per + ii. */
 int b200pir_db_upsert_item(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, uint64_t item_idx, const uint64_t* poly);

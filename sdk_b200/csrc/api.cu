@@ -4,6 +4,7 @@
 // point either runs on the GPU or returns an error.
 #include "../../include/b200pir.h"
 #include "kernels.h"
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <memory>
@@ -661,14 +662,12 @@ void b200pir_db_destroy(b200pir_db* db) {
   cudaSetDevice(db->ctx->device);
   delete db;
 }
-int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, const uint64_t* words, size_t n_words) {
-  API_BEGIN
-  if (!c || !words) throw Error(B200PIR_E_BADARG, "null argument");
-  Guard gd(c);
-  check_db(c, db);
-  const size_t slice_words = (size_t)c->dim0 * c->num_per * POLY;
-  if (slice >= (uint64_t)c->slices) throw Error(B200PIR_E_SHAPE, "slice out of range");
-  if (n_words != slice_words) throw Error(B200PIR_E_SHAPE, "slice must hold dim0*num_per*2048 words");
+extern "C++" {
+namespace {
+// One slice in the reference's z-major layout, delivered chunk by chunk: fetch(word_offset, n_words) returns a host pointer
+// to that range of the slice (valid until the next call).
+template <typename Fetch>
+void upload_slice_impl(b200pir_ctx* c, b200pir_db* db, uint64_t slice, Fetch fetch) {
   // reference layout is z-major: stage a range of z at a time (<= 64 MiB)
   const size_t per_z = (size_t)c->dim0 * c->num_per;
   int zc = (int)std::max<size_t>(1, std::min<size_t>(POLY, ((size_t)64 << 20) / (per_z * 8)));
@@ -680,7 +679,8 @@ int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, cons
   else { tmp.alloc(db->slice_cells()); dst = tmp.p; }
   for (int z0 = 0; z0 < POLY; z0 += zc) {
     int cur = std::min(zc, POLY - z0);
-    B200_CUDA(cudaMemcpyAsync(stage.p, words + (size_t)z0 * per_z, per_z * cur * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t* src = fetch((size_t)z0 * per_z, per_z * cur);
+    B200_CUDA(cudaMemcpyAsync(stage.p, src, per_z * cur * 8, cudaMemcpyHostToDevice, c->stream));
     launch_db_retile_chunk(G, db->shard, dst, stage.p, z0, cur, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
   }
@@ -692,6 +692,44 @@ int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, cons
     B200_CUDA(cudaStreamSynchronize(c->stream));
   }
   B200_CUDA(cudaGetLastError());
+}
+}  // namespace
+}  // extern "C++"
+
+int b200pir_db_upload_slice(b200pir_ctx* c, b200pir_db* db, uint64_t slice, const uint64_t* words, size_t n_words) {
+  API_BEGIN
+  if (!c || !words) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  const size_t slice_words = (size_t)c->dim0 * c->num_per * POLY;
+  if (slice >= (uint64_t)c->slices) throw Error(B200PIR_E_SHAPE, "slice out of range");
+  if (n_words != slice_words) throw Error(B200PIR_E_SHAPE, "slice must hold dim0*num_per*2048 words");
+  upload_slice_impl(c, db, slice, [&](size_t off, size_t) { return words + off; });
+  API_END
+}
+// load_preprocessed_db_from_file (lib/spiral-rs/src/server.rs:373-386, lib/server/src/db/loading.rs:263-276): the file is the
+// native-endian u64 stream of the whole `db: &[u64]`; it is streamed through a 64 MiB staging buffer, never held in RAM.
+int b200pir_db_load_file(b200pir_ctx* c, b200pir_db* db, const char* path) {
+  API_BEGIN
+  if (!c || !path) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  const size_t slice_words = (size_t)c->dim0 * c->num_per * POLY;
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } file{fopen(path, "rb")};
+  if (!file.f) throw Error(B200PIR_E_BADARG, std::string("cannot open ") + path);
+  if (fseeko(file.f, 0, SEEK_END)) throw Error(B200PIR_E_BADARG, "cannot seek in the database file");
+  const off_t bytes = ftello(file.f);
+  if (bytes < 0 || (uint64_t)bytes != (uint64_t)slice_words * c->slices * 8)
+    throw Error(B200PIR_E_SHAPE, "database file must hold slices*dim0*num_per*2048 u64 words");
+  std::vector<uint64_t> buf;
+  for (int s = 0; s < c->slices; s++) {
+    upload_slice_impl(c, db, (uint64_t)s, [&](size_t off, size_t n) -> const uint64_t* {
+      buf.resize(n);
+      if (fseeko(file.f, (off_t)(((size_t)s * slice_words + off) * 8), SEEK_SET) || fread(buf.data(), 8, n, file.f) != n)
+        throw Error(B200PIR_E_SHAPE, "short read from the database file");
+      return buf.data();
+    });
+  }
   API_END
 }
 int b200pir_db_upload(b200pir_ctx* c, b200pir_db* db, const uint64_t* words, size_t n_words) {

@@ -109,6 +109,13 @@ class Database:
         check(LIB.b200pir_db_upload(params._h, self._h, _ptr(db), db.size))
         return self
 
+    @classmethod
+    def from_file(cls, params, path, fmt=None, shard_index=0, shard_count=1):
+        """load_preprocessed_db_from_file (server.rs:373-386): native-endian u64 stream of the whole database."""
+        self = cls(params, shard_index=shard_index, shard_count=shard_count, fmt=fmt)
+        check(LIB.b200pir_db_load_file(params._h, self._h, str(path).encode()))
+        return self
+
     def upload_slice(self, slice_idx, words):
         check(LIB.b200pir_db_upload_slice(self.params._h, self._h, slice_idx, _ptr(words), words.size))
 

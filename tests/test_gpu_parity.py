@@ -751,3 +751,30 @@ def test_cuda_path_reproduces_golden_fixtures(case):
         gdb.close()
     gpp.close()
     G.close()
+
+
+# ------------------------------------------------------------------ preprocessed database file (server.rs:373-386)
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_database_loaded_from_file_equals_uploaded_database(fmt, tmp_path):
+    S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
+    path = tmp_path / "db.bin"
+    db.tofile(str(path))                                   # native-endian u64 stream, what load_file reads
+    fdb = S.Database.from_file(G, path, fmt=fmt)
+    G.set_option("db_format", 0)
+    rng = np.random.default_rng(31)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    slice_words = P.dim0 * P.num_per * P.N
+    for s in sorted({0, P.slices - 1}):
+        ref = P.multiply_reg_by_database(db[s * slice_words:(s + 1) * slice_words], v)
+        assert np.array_equal(S.multiply_reg_by_database(G, fdb, s, v), ref), (fmt, s)
+    q = cl.generate_query(200)
+    assert np.array_equal(S.process_query(G, gpp, S.Query(ct=q["ct"]), fdb), P.process_query(pp, q, db))
+    fdb.close()
+    short = tmp_path / "short.bin"
+    db[:-1].tofile(str(short))
+    with pytest.raises(S.B200PirError):
+        S.Database.from_file(G, short, fmt=fmt)
+    with pytest.raises(S.B200PirError):
+        S.Database.from_file(G, tmp_path / "missing.bin", fmt=fmt)
+    G.set_option("db_format", 0)
