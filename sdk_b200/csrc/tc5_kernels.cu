@@ -83,21 +83,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, LBO, SBO in 16-byte
-// units, version 1 (Blackwell), no swizzle, base offset 0
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // [0,14)   start address
-  d |= (uint64_t)((TC5_LBO >> 4) & 0x3FFF) << 16;       // [16,30)  leading-dimension byte offset (K halves)
-  d |= (uint64_t)((TC5_SBO >> 4) & 0x3FFF) << 32;       // [32,46)  stride byte offset (8-row groups)
-  d |= (uint64_t)1 << 46;                               // [46,48)  descriptor version
-  return d;                                             // [61,64)  layout type 0 = SWIZZLE_NONE
-}
-// instruction descriptor (InstrDescriptor): D = s32, A = B = unsigned 8 bit, both K-major, dense, no saturation
-__host__ __device__ constexpr uint32_t tc_instr_desc() {
-  return (2u << 4) /* c_format S32 */ | (0u << 7) /* a u8 */ | (0u << 10) /* b u8 */ | (0u << 15) | (0u << 16) |
-         ((uint32_t)(TC5_N >> 3) << 17) | ((uint32_t)(TC5_M >> 4) << 24);
-}
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -105,7 +90,7 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(tc_instr_desc()), "r"(accumulate), "r"(0u)
+      "l"(desc_a), "l"(desc_b), "r"(tc5_instr_desc()), "r"(accumulate), "r"(0u)
       : "memory");
 }
 // 32 lanes x 32 consecutive columns: thread t of the warp gets row (quadrant base + t)
@@ -279,7 +264,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
             const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
             for (int kk = 0; kk < ks_here; kk++) {
               const int ks = st * TC5_KS_PER_STAGE + kk;
-              tc_mma_i8(d_addr, tc_smem_desc(a_addr + kk * TC5_TILE), tc_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
+              tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
             }
             tc_commit(&S->empty[stage]);                              // frees the A stage when these MMAs have completed
             if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }

@@ -36,6 +36,23 @@ TC5_HD uint32_t tc5_limb4(const uint32_t (&r)[4], int l) {
   return ((r[0] >> sh) & 127u) | (((r[1] >> sh) & 127u) << 8) | (((r[2] >> sh) & 127u) << 16) | (((r[3] >> sh) & 127u) << 24);
 }
 
+// ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp; cross-checked against those structs by
+// tests/cpp/tc5_desc_check.cu)
+// shared-memory matrix descriptor: start address, LBO, SBO in 16-byte units, version 1 (Blackwell), SWIZZLE_NONE (0)
+TC5_HD uint64_t tc5_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // [0,14)   start address
+  d |= (uint64_t)((TC5_LBO >> 4) & 0x3FFF) << 16;       // [16,30)  leading-dimension byte offset (K halves)
+  d |= (uint64_t)((TC5_SBO >> 4) & 0x3FFF) << 32;       // [32,46)  stride byte offset (8-row groups)
+  d |= (uint64_t)1 << 46;                               // [46,48)  descriptor version
+  return d;
+}
+// instruction descriptor: D = s32, A = B = unsigned 8 bit, both K-major, dense, no saturation, M = 128, N = 128
+TC5_HD uint32_t tc5_instr_desc() {
+  return (2u << 4) /* c_format S32 */ | (0u << 7) /* a u8 */ | (0u << 10) /* b u8 */ | (0u << 15) | (0u << 16) |
+         ((uint32_t)(TC5_N >> 3) << 17) | ((uint32_t)(TC5_M >> 4) << 24);
+}
+
 // ---- database image: thread tid of the CTA of row tile mt / k-step ks handles one row and four consecutive j
 struct Tc5DbThread { int row_local, kq, ii, jp0; };
 TC5_HD Tc5DbThread tc5_db_thread(int tid, int mt, int ks) {

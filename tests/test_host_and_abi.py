@@ -56,3 +56,21 @@ def test_tcgen05_operand_images_and_epilogue_emulation(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "tc5_emul.cpp")])
     out = subprocess.check_output([exe], text=True)
     assert out.strip() == "tc5 emulation ok", out
+
+
+def test_tcgen05_descriptors_match_cutlass_bitfields(tmp_path):
+    """tests/cpp/tc5_desc_check.cu: our hand-packed instruction / shared-memory descriptors vs the vendored CUTLASS structs."""
+    import glob
+    import shutil
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    incs = [p for p in glob.glob("/opt/prime-rl/.venv/lib/python3*/site-packages/*/data/cutlass/include")
+            + glob.glob("/opt/prime-rl/.venv/lib/python3*/site-packages/*/3rdparty/cutlass/include")
+            if os.path.exists(os.path.join(p, "cute", "arch", "mma_sm100_desc.hpp"))]
+    if not (os.path.exists(nvcc) or shutil.which("nvcc")) or not incs:
+        pytest.skip("needs nvcc and a vendored CUTLASS header tree")
+    exe = str(tmp_path / "tc5_desc_check")
+    subprocess.check_call([nvcc if os.path.exists(nvcc) else "nvcc", "-std=c++17", "-I" + incs[0], "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "tc5_desc_check.cu"), "-ccbin",
+                           "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"])
+    out = subprocess.check_output([exe], text=True)
+    assert out.strip() == "descriptors ok", out
