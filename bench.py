@@ -270,7 +270,7 @@ def main():
                          "expanded queries overlaps the expansion / first dimension of the other")
     ap.add_argument("--mul-variant", type=int, default=0)
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
-                    help="0 = IMAD layout, 1 = INT8 tensor-core fragment order")
+                    help="0 = IMAD layout, 1 = INT8 tensor-core fragment order, 2 = tcgen05 tile images (experimental)")
     ap.add_argument("--fold-variant", type=int, default=1)
     ap.add_argument("--intt-variant", type=int, default=0)
     ap.add_argument("--imma-variant", type=int, default=0)
@@ -465,7 +465,9 @@ def main():
         G.set_option("profile", 0)
         k_ms = st1["multiply"] / max(st1["multiply_launches"], 1)
         db_b = d["slices"] * d["dim0"] * rows_local * POLY * 8
-        op_b = (d["dim0"] * POLY * 16 if args.db_format == 0 else 2 * POLY * ((d["dim0"] + 31) // 32) * 4 * 32 * 8)
+        op_b = (d["dim0"] * POLY * 16 if args.db_format == 0 else
+                2 * POLY * ((d["dim0"] + 31) // 32) * 4096 if args.db_format == 2 else
+                2 * POLY * ((d["dim0"] + 31) // 32) * 4 * 32 * 8)
         alg1 = db_b + op_b + d["slices"] * rows_local * 4 * POLY * 4
         pk, _src = measured_peak()
         single_roofline = {"queries_per_launch": 1, "kernel_ms": k_ms, "achieved": alg1 / (k_ms * 1e-3) / 1e9, "peak": pk,
@@ -494,13 +496,15 @@ def main():
     db_bytes = d["slices"] * d["dim0"] * rows_local * POLY * 8
     if args.db_format == 0:
         operand_bytes = nq_per_launch * d["dim0"] * POLY * 16
+    elif args.db_format == 2:   # tcgen05 tile images of the query operand: [n][z][dim0/32][4096 B], 16 queries
+        operand_bytes = 2 * POLY * ((d["dim0"] + 31) // 32) * 4096
     else:   # limb fragments of the query operand: [n][z][column tiles][dim0/32][4 limbs][32 lanes] x 8 B
         tiles = 4 if nq_per_launch > 8 else (2 if nq_per_launch > 4 else 1)
         operand_bytes = 2 * POLY * tiles * ((d["dim0"] + 31) // 32) * 4 * 32 * 8
     alg_bytes = db_bytes + operand_bytes + nq_per_launch * d["slices"] * rows_local * 4 * POLY * 4
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (mul_ms * 1e-3) / 1e9
-    kname = "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)"
+    kname = {0: "k_multiply (IMAD)", 1: "k_multiply_imma (INT8 MMA limbs)", 2: "k_multiply_tc5 (tcgen05 kind::i8 limbs)"}[args.db_format]
     roofline = {"bound": "hbm", "kernel": kname + " = multiply_reg_by_database, server.rs:155-221",
                 "queries_per_launch": nq_per_launch,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -523,7 +527,7 @@ def main():
             "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W, "queries_per_pass": per_pass,
                        "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
-                       "first_dimension_kernel": "k_multiply (IMAD)" if args.db_format == 0 else "k_multiply_imma (INT8 MMA limbs)",
+                       "first_dimension_kernel": kname,
                        "parallelism": ("rows ii mod %d, %d concurrent queries per GPU; queries expanded by the receiving rank; "
                                        "asynchronous NCCL all-gather of expanded queries and of surviving ciphertexts in %d "
                                        "waves (%d bytes received per rank per step)" % (N, B // N, W, coll_bytes))
