@@ -105,6 +105,11 @@ int b200pir_ntt_forward(b200pir_ctx* ctx, uint64_t* polys, size_t count);
 int b200pir_ntt_inverse(b200pir_ctx* ctx, uint64_t* polys, size_t count);
 /* Device-resident batch (BASELINE config #5): `count` polys of u32 [2][2048] residues, in place, stream-ordered. */
 int b200pir_ntt32_dev(b200pir_ctx* ctx, uint32_t* polys_dev, size_t count, int inverse);
+/* BASELINE config #5, poly_len = 4096 (not a size the reference's parameterisation uses, util.rs:246): the same transform
+ * definition (ntt.rs:67-113, :212-258) and table construction (ntt.rs:39-65) over the same two moduli.
+ * _dev: polys_dev = count x [2][4096] u32 on the device, in place; host variant: count x [2][4096] u64. */
+int b200pir_ntt4096_dev(b200pir_ctx* ctx, uint32_t* polys_dev, size_t count, int inverse);
+int b200pir_ntt4096(b200pir_ctx* ctx, uint64_t* polys, size_t count, int inverse);
 /* poly.rs:613-623 to_ntt / :646-663 from_ntt over `count` polys. */
 int b200pir_to_ntt(b200pir_ctx* ctx, uint64_t* out_ntt, const uint64_t* raw, size_t count);
 int b200pir_from_ntt(b200pir_ctx* ctx, uint64_t* out_raw, const uint64_t* ntt, size_t count);

@@ -439,6 +439,18 @@ int orc_dpir_transpose_expand_concat_cols_squish(uint32_t* out, const uint32_t* 
   ORC_CATCH
 }
 
+// BASELINE config #5 at poly_len = 4096: the same scalar transforms / table construction instantiated at the larger size
+// (the reference's parameterisation stops at 2048, util.rs:246; both moduli are 1 mod 8192)
+int orc_ntt4096(uint64_t* polys, size_t count, int inverse) {
+  ORC_TRY
+  static const Params p4k = params_init(4096, {268369921ULL, 249561089ULL}, 6.4, 2, 256, 20, 4, 8, 8, 8, true, 6, 2, 1, 8192, 0);
+  for (size_t i = 0; i < count; i++) {
+    if (inverse) ntt_inverse_scalar(p4k, polys + i * 2 * 4096);
+    else ntt_forward_scalar(p4k, polys + i * 2 * 4096);
+  }
+  ORC_CATCH
+}
+
 // CPU-baseline switch: 1 = AVX2 transforms everywhere ntt_forward / ntt_inverse are called (bit-identical to the scalar ones)
 int orc_use_avx2_ntt(int on) {
 #if defined(__AVX2__)

@@ -98,6 +98,31 @@ def ntt_sweep(batch_log2=16):
     return out
 
 
+def ntt4096_sweep(batch_log2=16):
+    """BASELINE config #5, poly_len = 4096 (opt-in: `python scripts/bench_kernels.py ntt4096`)."""
+    kw = dict(n=2, nu_1=6, nu_2=2, p=256, q2_bits=20, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1,
+              db_item_size=8192, version=0)
+    G = S.Params(**kw)
+    G.set_stream(torch.cuda.current_stream().cuda_stream)
+    count = 1 << batch_log2
+    x = torch.randint(0, 249561089, (count * 2 * 4096,), dtype=torch.int32, device="cuda")
+    import oracle_lib as O
+    small = x[: 4 * 2 * 4096].cpu().numpy().astype(np.uint32).astype(np.uint64)
+    ref = small.copy()
+    O._ck(O.LIB.orc_ntt4096(O._p64(ref), 4, 0))
+    chk = small.copy()
+    S.ntt4096(G, chk)
+    out = {"kernel": "ntt32 batch", "polys": count, "poly_len": 4096, "moduli": 2, "spot_check_ok": bool(np.array_equal(chk, ref))}
+    fn = LIB.b200pir_ntt4096_dev
+    for name, inv in (("forward", 0), ("inverse", 1)):
+        ms = timed(lambda: check(fn(G._h, x.data_ptr(), count, inv)), 5)
+        bytes_ = 2 * count * 2 * 4096 * 4
+        out[name] = {"ms": ms, "polys_per_s": count / ms * 1e3, "GB/s_u32": bytes_ / ms / 1e6,
+                     "GB/s_u64_equiv": 2 * bytes_ / ms / 1e6, "frac_of_measured_hbm_peak_u32": bytes_ / ms / 1e6 / PEAK}
+    G.close()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["dpir_small", "ntt"]
     for w in which:
@@ -107,3 +132,5 @@ if __name__ == "__main__":
             print(json.dumps(dpir(20, 4096)), flush=True)
         elif w == "ntt":
             print(json.dumps(ntt_sweep()), flush=True)
+        elif w == "ntt4096":
+            print(json.dumps(ntt4096_sweep()), flush=True)

@@ -10,6 +10,9 @@ echo "== tcgen05 probe (raw accumulators vs layout hypotheses)"
 timeout 180 python scripts/tc5_probe.py 2>&1 | tail -12
 echo "== tcgen05 parity tests"
 B200PIR_TEST_TC5=1 timeout 600 python -m pytest tests/test_gpu_tcgen05.py -x -q 2>&1 | tail -6
+echo "== 4096-point NTT (config #5)"
+B200PIR_TEST_NTT4K=1 timeout 300 python -m pytest tests/test_gpu_ntt4096.py -x -q 2>&1 | tail -3
+timeout 300 python scripts/bench_kernels.py ntt ntt4096 2>&1 | cut -c1-400
 echo "== bench: format 1 (8 / 16 per pass) vs format 2"
 for args in "--db-format 1 --queries-per-pass 8" "--db-format 1 --queries-per-pass 16" "--db-format 2 --queries-per-pass 16"; do
   timeout 300 python bench.py --no-cpu-baseline $args > gpurun_out/bringup_bench.json 2> gpurun_out/bringup_bench.err

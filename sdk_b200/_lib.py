@@ -50,6 +50,8 @@ def _load():
         "b200pir_ntt_forward": (C.c_int, [vp, u64p, C.c_size_t]),
         "b200pir_ntt_inverse": (C.c_int, [vp, u64p, C.c_size_t]),
         "b200pir_ntt32_dev": (C.c_int, [vp, u32p, C.c_size_t, C.c_int]),
+        "b200pir_ntt4096_dev": (C.c_int, [vp, u32p, C.c_size_t, C.c_int]),
+        "b200pir_ntt4096": (C.c_int, [vp, u64p, C.c_size_t, C.c_int]),
         "b200pir_to_ntt": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
         "b200pir_from_ntt": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
         "b200pir_multiply_reg_by_database": (C.c_int, [vp, vp, C.c_uint64, u64p, u64p]),

@@ -58,8 +58,7 @@ uint64_t min_primitive_root(uint64_t degree, uint64_t q) {
   return best;
 }
 // tables of ntt.rs:39-65 as (W, W') pairs
-void build_tables(uint64_t q, std::vector<Twiddle>& fwd, std::vector<Twiddle>& inv) {
-  const int N = NTT_N, LG = NTT_LOG_N;
+void build_tables(uint64_t q, std::vector<Twiddle>& fwd, std::vector<Twiddle>& inv, int N = NTT_N, int LG = NTT_LOG_N) {
   uint64_t root = min_primitive_root(2 * N, q), iroot = invmod(root, q);
   fwd.assign(N, Twiddle{0, 0});
   inv.assign(N, Twiddle{0, 0});
@@ -125,6 +124,7 @@ struct b200pir_ctx {
   int q1_bits;
   DevParams dp;
   DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1
+  DevBuf<Twiddle> d_tw4k;    // same for poly_len 4096 (config #5 sweep), built on first use
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 16, profile = 0;  // max_group: queries per database pass (IMAD path: <= 4)
@@ -932,6 +932,50 @@ int b200pir_ntt32_dev(b200pir_ctx* c, uint32_t* polys_dev, size_t count, int inv
   if (!c || !polys_dev) throw Error(B200PIR_E_BADARG, "null argument");
   Guard gd(c);
   launch_ntt32(c->dp, polys_dev, count, inverse != 0, c->stream);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
+// ---- poly_len = 4096 transforms (BASELINE config #5; not part of the reference's parameterisation, util.rs:246)
+namespace {
+const Twiddle* tables_4k(b200pir_ctx* c) {
+  if (!c->d_tw4k.p) {
+    const int N = 4096, LG = 12;
+    std::vector<Twiddle> all;
+    for (int n = 0; n < 2; n++) {
+      std::vector<Twiddle> f, i;
+      build_tables(c->dp.q[n], f, i, N, LG);
+      all.insert(all.end(), f.begin(), f.end());
+      all.insert(all.end(), i.begin(), i.end());
+    }
+    c->d_tw4k.alloc(all.size());
+    B200_CUDA(cudaMemcpy(c->d_tw4k.p, all.data(), all.size() * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  }
+  return c->d_tw4k.p;
+}
+}  // namespace
+int b200pir_ntt4096_dev(b200pir_ctx* c, uint32_t* polys_dev, size_t count, int inverse) {
+  API_BEGIN
+  if (!c || !polys_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  launch_ntt32_4k(c->dp.q[0], c->dp.q[1], tables_4k(c), polys_dev, count, inverse != 0, c->stream);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_ntt4096(b200pir_ctx* c, uint64_t* polys, size_t count, int inverse) {
+  API_BEGIN
+  if (!c || (!polys && count)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  if (count == 0) return 0;
+  const size_t words = count * 2 * 4096;
+  DevBuf<uint64_t> wide(words);
+  DevBuf<uint32_t> nar(words);
+  B200_CUDA(cudaMemcpyAsync(wide.p, polys, words * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_narrow(nar.p, wide.p, words, c->stream);
+  launch_ntt32_4k(c->dp.q[0], c->dp.q[1], tables_4k(c), nar.p, count, inverse != 0, c->stream);
+  launch_widen(wide.p, nar.p, words, c->stream);
+  B200_CUDA(cudaMemcpyAsync(polys, wide.p, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
   API_END
 }

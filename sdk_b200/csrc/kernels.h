@@ -23,6 +23,8 @@ void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inve
 // ntt32 in place
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s);
 // poly.rs:613-638 to_ntt: raw u64 -> ntt32 (reduce mod q_n, forward NTT)
+// poly_len = 4096 (config #5 only): polys ntt32 [count][2][4096]; tw = {fwd0, inv0, fwd1, inv1} x 4096 entries
+void launch_ntt32_4k(uint32_t q0, uint32_t q1, const Twiddle* tw, uint32_t* polys, size_t count, bool inverse, cudaStream_t s);
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s);
 // `batches` groups of `count` polynomials, groups out_stride (u32) / raw_stride (u64) words apart, in one launch
 void launch_to_ntt_strided(const DevParams& P, uint32_t* out, size_t out_stride, const uint64_t* raw, size_t raw_stride,

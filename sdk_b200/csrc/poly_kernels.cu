@@ -8,6 +8,7 @@
 // and pack (:429-468): it is written once (digits_mac) and fused with the surrounding inverse
 // transforms, automorphisms and CRT lifts so intermediates never leave the SM.
 #include "kernels.h"
+#include "ntt_core4096.cuh"
 
 namespace b200pir {
 
@@ -228,6 +229,28 @@ __global__ void __launch_bounds__(256) k_ntt32(DevParams P, uint32_t* polys, int
     grp_ntt_inv(g, x);
 #pragma unroll
     for (int a = 0; a < 8; a++) p[a * 256 + g.tid] = x[a];
+  }
+}
+// BASELINE config #5, poly_len = 4096: one 512-thread CTA per single-modulus transform, all twiddles through L1
+// (tables of 4096 (W, W') pairs per modulus and direction, built like the 2048 ones).  ntt32 layout [poly][n][4096].
+__global__ void __launch_bounds__(NTT4K_THREADS)
+k_ntt32_4k(uint32_t q0, uint32_t q1, const Twiddle* __restrict__ tw /* fwd0, inv0, fwd1, inv1 */, uint32_t* polys, int inverse) {
+  __shared__ __align__(16) uint32_t sm[NTT4K_SMEM_WORDS];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const uint32_t q = n ? q1 : q0;
+  uint32_t* p = polys + ((size_t)blockIdx.x * 2 + n) * NTT4K_N;
+  const TwGlobal tab{tw + (size_t)(2 * n + (inverse ? 1 : 0)) * NTT4K_N};
+  uint32_t x[8];
+  if (!inverse) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a] = p[a * NTT4K_THREADS + tid];
+    ntt4k_forward_group(tid, x, sm, tab, q, CtaSync());
+    st8(p + tid * 8, x);
+  } else {
+    ld8(x, p + tid * 8);
+    ntt4k_inverse_group(tid, x, sm, tab, q, CtaSync());
+#pragma unroll
+    for (int a = 0; a < 8; a++) p[a * NTT4K_THREADS + tid] = x[a];
   }
 }
 // u64 ABI words (ntt.rs:68 / :213 operate on &mut [u64]); values are truncated to 32 bits exactly as
@@ -1085,6 +1108,9 @@ void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inve
 }
 void launch_ntt32(const DevParams& P, uint32_t* polys, size_t count, bool inverse, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_ntt32<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, polys, inverse ? 1 : 0);
+}
+void launch_ntt32_4k(uint32_t q0, uint32_t q1, const Twiddle* tw, uint32_t* polys, size_t count, bool inverse, cudaStream_t s) {
+  if (count) ++g_kernel_launches, k_ntt32_4k<<<dim3((unsigned)count, 2), NTT4K_THREADS, 0, s>>>(q0, q1, tw, polys, inverse ? 1 : 0);
 }
 void launch_to_ntt(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t count, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_to_ntt<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, out, raw, 0, 0);

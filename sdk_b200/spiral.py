@@ -209,6 +209,13 @@ def ntt_inverse(params, operand_overall):
     check(LIB.b200pir_ntt_inverse(params._h, _ptr(operand_overall), operand_overall.size // (CRT_COUNT * POLY_LEN)))
 
 
+def ntt4096(params, operand_overall, inverse=False):
+    """BASELINE config #5: the transforms of ntt.rs at poly_len = 4096, in place over [2][4096] u64 polynomials."""
+    if operand_overall.size % (CRT_COUNT * 4096):
+        raise ValueError("operand must hold whole [2][4096] polynomials")
+    check(LIB.b200pir_ntt4096(params._h, _ptr(operand_overall), operand_overall.size // (CRT_COUNT * 4096), 1 if inverse else 0))
+
+
 # ---- lib/spiral-rs/src/poly.rs
 def to_ntt(params, raw):
     """poly.rs:613-623 (PolyMatrixRaw -> PolyMatrixNTT, any shape flattened)."""

@@ -74,3 +74,11 @@ def test_tcgen05_descriptors_match_cutlass_bitfields(tmp_path):
                            "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"])
     out = subprocess.check_output([exe], text=True)
     assert out.strip() == "descriptors ok", out
+
+
+def test_cooperative_ntt4096_emulation_matches_oracle(tmp_path):
+    exe = str(tmp_path / "ntt_core4096_emul")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "ntt_core4096_emul.cpp")])
+    out = subprocess.check_output([exe], text=True)
+    assert out.strip() == "OK", out
