@@ -55,7 +55,8 @@ int b200pir_ctx_synchronize(b200pir_ctx* ctx);
  * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments,
  * 2 = tcgen05 tile images — experimental, see tc5_kernels.cu), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
- * "expand_variant" (0 = default everywhere); "expand_pair_min_ctas" (expansion rounds with at least this many active
+ * "expand_variant" (0 = default everywhere); "sparse_fold" (1 = fold like lib/server's sparse server,
+ * compute/fold.rs:15-65: an all-zero ciphertext short-cuts the external product; 0 = spiral-rs's dense fold, default); "expand_pair_min_ctas" (expansion rounds with at least this many active
  * ciphertexts use the paired kernel, default 592);
  * unknown keys -> B200PIR_E_BADARG */
 int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);

@@ -486,6 +486,9 @@ int orc_ntt_avx2(void* h, uint64_t* polys, size_t count, int inverse) {
   ORC_CATCH
 }
 
+// 1: process_query uses lib/server's fold (all-zero ciphertext shortcut, lib/server/src/compute/fold.rs:37-43)
+int orc_set_sparse_fold(int on) { g_sparse_fold = on != 0; return 0; }
+
 // CPU-baseline switch: 1 = AVX2 first-dimension kernel inside process_query (returns 0 when not compiled with AVX2)
 int orc_use_avx2_multiply(int on) {
 #if defined(__AVX2__)

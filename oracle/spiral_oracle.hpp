@@ -36,6 +36,7 @@ namespace orc {
 
 // set by the CPU-baseline legs of bench.py: use the AVX2 first-dimension kernel inside process_query
 static bool g_use_avx2_multiply = false;
+static bool g_sparse_fold = false;        // process_query folds like lib/server (compute/fold.rs:15-65) instead of spiral-rs (server.rs:388-427)
 
 
 typedef unsigned __int128 u128;
@@ -1134,7 +1135,7 @@ inline std::vector<uint8_t> process_query(const Params& p, const PublicParameter
       std::memcpy(m.data.data(), inter.data() + i * 4 * N, 4 * N * 8);
       from_ntt(p, inter_raw[i], m);
     }
-    fold_ciphertexts(p, inter_raw, v_folding, v_folding_neg);
+    fold_ciphertexts(p, inter_raw, v_folding, v_folding_neg, g_sparse_fold);   // lib/server twin: compute/fold.rs shortcut
     v_ct_all[it] = inter_raw[0];
   }
   std::vector<PolyMatrix> v_packed;

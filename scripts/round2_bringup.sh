@@ -10,6 +10,8 @@ echo "== tcgen05 probe (raw accumulators vs layout hypotheses)"
 timeout 180 python scripts/tc5_probe.py 2>&1 | tail -12
 echo "== tcgen05 parity tests"
 B200PIR_TEST_TC5=1 timeout 600 python -m pytest tests/test_gpu_tcgen05.py -x -q 2>&1 | tail -6
+echo "== sparse server fold"
+B200PIR_TEST_SPARSE_FOLD=1 timeout 300 python -m pytest tests/test_gpu_sparse_fold.py -x -q 2>&1 | tail -3
 echo "== 4096-point NTT (config #5)"
 B200PIR_TEST_NTT4K=1 timeout 300 python -m pytest tests/test_gpu_ntt4096.py -x -q 2>&1 | tail -3
 timeout 300 python scripts/bench_kernels.py ntt ntt4096 2>&1 | cut -c1-400

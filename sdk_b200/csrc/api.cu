@@ -132,6 +132,7 @@ struct b200pir_ctx {
   int intt_variant = 0;
   int expand_variant = 0;        // wide rounds: 0 paired + residue pipeline (3 CTAs/SM), 2 paired single kernel; 1: never paired
   long pair_min_ctas = 592;      // 4 x 148 SMs
+  int sparse_fold = 0;           // 1: lib/server's fold (all-zero ciphertext shortcut, compute/fold.rs:37-43); 0: spiral-rs dense fold
   int imma_variant = 0;          // 0: cp.async-pipelined kernel for 5..8 queries per pass, 1: load-then-use kernel
   int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 16 queries)
@@ -141,6 +142,7 @@ struct b200pir_ctx {
   size_t ws_queries = 0, ws_rows = 0;
   DevBuf<uint64_t> w_query;      // [Q][2][2048] raw
   DevBuf<uint32_t> w_v;          // [Q][2^g][2][2][2048]
+  DevBuf<uint32_t> w_zflags;     // all-zero flags of the current fold round's ciphertexts ("sparse_fold")
   DevBuf<uint32_t> w_xr;         // [Q][num_in][2][2048] residues of row 0 (paired expansion rounds)
   DevBuf<uint4> w_qdev;          // [Q][dim0][2048]
   DevBuf<uint32_t> w_vfold, w_vfold_neg;   // [Q][nu_2][2][2t][2][2048]
@@ -345,9 +347,14 @@ const uint32_t* run_fold_res(b200pir_ctx* c, uint32_t* a, uint32_t* b, size_t ba
   int k = k0;
   uint32_t* src = a;
   uint32_t* dst = b;
+  uint32_t* zero_flags = nullptr;                      // lib/server's fold shortcut (fold.rs:37-43) when "sparse_fold" is set
+  if (c->sparse_fold) {
+    c->w_zflags.ensure(batch * num);
+    zero_flags = c->w_zflags.p;
+  }
   for (size_t half = num / 2; half >= 1; half /= 2, k--) {
     launch_fold_res(c->dp, src, dst, batch, batch_stride, (int)half, vfold + (size_t)k * mat, c->fold_words(),
-                    slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, c->stream);
+                    slices_per_query, (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, zero_flags, c->stream);
     std::swap(src, dst);
   }
   return src;
@@ -604,6 +611,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "fold_variant") c->fold_variant = (int)value;
   else if (k == "intt_variant") c->intt_variant = (int)value;
   else if (k == "imma_variant") c->imma_variant = (int)value;
+  else if (k == "sparse_fold") c->sparse_fold = value != 0;
   else if (k == "expand_variant") c->expand_variant = (int)value;
   else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
   else if (k == "db_format") { if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be 0, 1 or 2"); c->db_format = (int)value; }
@@ -1065,7 +1073,7 @@ int b200pir_fold_ciphertexts(b200pir_ctx* c, uint64_t* v_cts, size_t num, const 
   B200_CUDA(cudaMemcpyAsync(cts.p, v_cts, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
   B200_CUDA(cudaMemcpyAsync(wide.p, v_folding, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
   launch_narrow(vf.p, wide.p, wide.n, c->stream);
-  if (v_folding_neg) {
+  if (v_folding_neg && !c->sparse_fold) {
     // general path: honours an arbitrary v_folding_neg exactly as server.rs:405-425 does
     DevBuf<uint32_t> vfn(c->fold_words());
     B200_CUDA(cudaMemcpyAsync(wide.p, v_folding_neg, wide.n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1074,12 +1082,16 @@ int b200pir_fold_ciphertexts(b200pir_ctx* c, uint64_t* v_cts, size_t num, const 
   } else {
     // fast path (what process_query uses): v_folding_neg = get_v_folding_neg(v_folding) implied.
     // Round results are copied back so every slot ends up as the reference's in-place loop leaves it.
+    // With "sparse_fold" set this is lib/server's fold (compute/fold.rs:15-65): v_folding_neg is then taken to be
+    // get_v_folding_neg(v_folding), which is what that server passes (lib/server/src/server.rs).
     DevBuf<uint32_t> a(num * 4 * POLY), b(num * 4 * POLY);
+    DevBuf<uint32_t> zflags;
+    if (c->sparse_fold) zflags.alloc(num);
     launch_raw_to_res(c->dp, a.p, cts.p, num * 2, c->stream);
     int k = dims - 1;
     for (size_t half = num / 2; half >= 1; half /= 2, k--) {
       launch_fold_res(c->dp, a.p, b.p, 1, num * 4 * POLY, (int)half, vf.p + (size_t)k * mat, c->fold_words(), 1,
-                      (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, c->stream);
+                      (int)c->hp.t_gsw, c->bits_gsw, c->fold_variant, zflags.p, c->stream);
       B200_CUDA(cudaMemcpyAsync(a.p, b.p, half * 4 * POLY * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     launch_res_to_raw(c->dp, cts.p, a.p, num * 2, c->stream);

@@ -385,7 +385,25 @@ k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const ui
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
-           const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits) {
+           const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
+           const uint32_t* __restrict__ zero_flags /* null, or [batch][2*half]: 1 = ciphertext is all zero */) {
+  if (zero_flags) {
+    // lib/server/src/compute/fold.rs:37-43 (the sparse server's fold): an all-zero first operand is replaced by the
+    // second one, an all-zero second operand leaves the first one as it is; no external product in either case
+    const int bz = blockIdx.x / half, iz = blockIdx.x % half;
+    const uint32_t fa = zero_flags[(size_t)bz * 2 * half + iz], fb = zero_flags[(size_t)bz * 2 * half + half + iz];
+    if (fa | fb) {
+      const uint32_t* src = in + (size_t)bz * batch_stride + (size_t)((fa ? half : 0) + iz) * 4 * POLY;
+      uint32_t* dst = out + (size_t)bz * batch_stride + (size_t)iz * 4 * POLY;
+#pragma unroll
+      for (int rho = 0; rho < 2; rho++) {
+        uint32_t x[8];
+        ld8_ro(x, src + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8);
+        st8(dst + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8, x);
+      }
+      return;
+    }
+  }
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* sm0 = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
@@ -475,6 +493,22 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
     co[(0 * 2 + g.n) * POLY + z] = addmod(y0[a], __ldg(ci + (0 * 2 + g.n) * POLY + z), q);
     co[(1 * 2 + g.n) * POLY + z] = addmod(y1[a], __ldg(ci + (1 * 2 + g.n) * POLY + z), q);
   }
+}
+
+// flags[b][idx] = 1 iff ciphertext idx of batch b (residue form, 4 x 2048 words) is all zero  (fold.rs:6-13 is_all_zeros:
+// the CRT-lifted polynomial is zero exactly when every residue is)
+__global__ void __launch_bounds__(256)
+k_ct_zero_flags(const uint32_t* __restrict__ cts, size_t batch_stride, int per_batch, uint32_t* __restrict__ flags) {
+  const int b = blockIdx.x / per_batch, idx = blockIdx.x % per_batch;
+  const uint4* p = reinterpret_cast<const uint4*>(cts + (size_t)b * batch_stride + (size_t)idx * 4 * POLY);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint4 v = __ldg(p + k * 256 + threadIdx.x);
+    acc |= v.x | v.y | v.z | v.w;
+  }
+  const int any = __syncthreads_or(acc != 0);
+  if (threadIdx.x == 0) flags[blockIdx.x] = any ? 0u : 1u;
 }
 
 // neg[k][r][c] = (q_n - C[k][r][c]) + G[r][c]   with G[i][i + 2j] = 2^{bits*j}  (gadget.rs:11-32)
@@ -1128,7 +1162,7 @@ void launch_res_to_raw(const DevParams& P, uint64_t* out, const uint32_t* res, s
 }
 void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size_t batch, size_t batch_stride, int half,
                      const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
-                     int variant, cudaStream_t s) {
+                     int variant, uint32_t* zero_flags, cudaStream_t s) {
   if (batch == 0 || half == 0) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1136,14 +1170,20 @@ void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size
     cudaFuncSetAttribute(k_fold_res<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
     attr_set = true;
   }
+  if (zero_flags) {            // scratch of batch * 2 * half words: recomputed every round, as the reference re-tests every step
+    ++g_kernel_launches;
+    k_ct_zero_flags<<<(unsigned)(batch * 2 * half), 256, 0, s>>>(in, batch_stride, 2 * half, zero_flags);
+  }
   ++g_kernel_launches;
   // variant 1: 3 CTAs per SM (80 registers, a few spills) instead of 2 (128 registers)
   if (variant == 1)
     k_fold_res<3><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
-                                                                              c_batch_stride, slices_per_query, t_gsw, bits);
+                                                                              c_batch_stride, slices_per_query, t_gsw, bits,
+                                                                              zero_flags);
   else
     k_fold_res<2><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
-                                                                              c_batch_stride, slices_per_query, t_gsw, bits);
+                                                                              c_batch_stride, slices_per_query, t_gsw, bits,
+                                                                              zero_flags);
 }
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);

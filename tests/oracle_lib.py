@@ -255,8 +255,15 @@ class Params:
         _ck(LIB.orc_encode(self.hp, _p8(out), C.byref(ln), _p64(packed_raw)))
         return out[: ln.value].copy()
 
-    def process_query(self, pp, query, db, dump=False):
-        """query: dict(ct=...) or dict(v_buf=..., v_ct=...)."""
+    def process_query(self, pp, query, db, dump=False, sparse_fold=False):
+        """query: dict(ct=...) or dict(v_buf=..., v_ct=...).  sparse_fold: fold like lib/server (compute/fold.rs:15-65)."""
+        LIB.orc_set_sparse_fold(1 if sparse_fold else 0)
+        try:
+            return self._process_query(pp, query, db, dump)
+        finally:
+            LIB.orc_set_sparse_fold(0)
+
+    def _process_query(self, pp, query, db, dump=False):
         out = np.zeros(self.response_bytes() + 16, dtype=np.uint8)
         ln = C.c_size_t(0)
         d = {}

@@ -130,3 +130,46 @@ def test_oracle_reproduces_golden_fixtures():
     assert gold["seed_client"] == GC.GOLDEN_SEED_CLIENT and gold["seed_db"] == GC.GOLDEN_SEED_DB
     for case in GC.GOLDEN_CASES:
         assert GC.oracle_record(case) == gold["cases"][case], case
+
+
+def test_sparse_server_fold_shortcut_semantics():
+    # lib/server/src/compute/fold.rs:37-43: an all-zero first operand is replaced by the second, an all-zero second operand
+    # leaves the first untouched; with no all-zero ciphertext the sparse fold is the dense fold
+    P = O.Params.named("T")
+    cl = O.Client(P, 77)
+    pp = cl.generate_keys()
+    q = cl.generate_query(5)
+    _, vf = P.expand_query(pp, q["ct"])
+    vfn = P.get_v_folding_neg(vf)
+    rng = np.random.default_rng(8)
+    num = 4
+    cts = rng.integers(0, P.modulus, num * 2 * P.N, dtype=np.uint64).reshape(num, 2 * P.N)
+    dims = 2
+    mat = 4 * P.t_gsw * P.W
+    vf2, vfn2 = vf[: dims * mat], vfn[: dims * mat]
+    assert np.array_equal(P.fold_ciphertexts(cts, vf2, vfn2, sparse=True), P.fold_ciphertexts(cts, vf2, vfn2))
+    z = cts.copy()
+    z[0] = 0                                   # pair (0, 2): first operand zero -> slot 0 becomes ct 2
+    z[3] = 0                                   # pair (1, 3): second operand zero -> slot 1 stays ct 1
+    out = P.fold_ciphertexts(z, vf2, vfn2, sparse=True).reshape(num, 2 * P.N)
+    one_round = np.stack([z[2], z[1]])         # what round 1 leaves in slots 0, 1
+    ref = P.fold_ciphertexts(one_round, vf2[:mat], vfn2[:mat]).reshape(2, 2 * P.N)   # round 2 is a normal external product
+    assert np.array_equal(out[0], ref[0])
+    assert not np.array_equal(out[0], P.fold_ciphertexts(z, vf2, vfn2).reshape(num, 2 * P.N)[0])
+
+
+def test_sparse_database_decodes_with_the_sparse_server_fold():
+    # a database with whole second-dimension rows absent: populated items still decode under lib/server's fold
+    P = O.Params.named("T")
+    cl = O.Client(P, 78)
+    pp = cl.generate_keys()
+    db = P.generate_db(0xABCD).reshape(P.slices, P.N, P.num_per, P.dim0).copy()
+    db[:, :, 1::2, :] = 0                       # every odd row ii empty
+    db = db.reshape(-1)
+    for idx in (0, 2 * 7, P.num_per * 3 + 4):   # items in even rows (item index = j * num_per + ii)
+        q = cl.generate_query(idx)
+        dense = P.process_query(pp, q, db)
+        sparse = P.process_query(pp, q, db, sparse_fold=True)
+        assert not np.array_equal(dense, sparse)
+        assert np.array_equal(cl.decode_response(sparse), P.db_plain_item(0xABCD, idx))
+        assert np.array_equal(cl.decode_response(dense), P.db_plain_item(0xABCD, idx))
