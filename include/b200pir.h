@@ -77,6 +77,10 @@ int b200pir_db_upload(b200pir_ctx* ctx, b200pir_db* db, const uint64_t* words, s
  * u64 stream of the whole database (slices*dim0*num_per*2048 words, the layout b200pir_db_upload takes); it is streamed
  * to the GPU through a staging buffer. */
 int b200pir_db_load_file(b200pir_ctx* ctx, b200pir_db* db, const char* path);
+/* load_db_from_seek (server.rs:277-357; lib/server/src/db/loading.rs:192-247): `path` is the RAW database, item i at byte
+ * i*db_item_size; chunk c of an item = bytes_per_chunk bytes from i*db_item_size + c*bytes_per_chunk, clipped at the end of
+ * the file; conversion (recenter, NTT, pack) on the GPU.  logp == 8 only. */
+int b200pir_db_load_raw_file(b200pir_ctx* ctx, b200pir_db* db, const char* path);
 /* One preprocessed item polynomial: 2048 packed words (lib/server/src/db/loading.rs:34-41 pack_ntt_poly,
  * :317-359 update_item_raw -> db.upsert(inst_trial*num_items + db_idx)); item_idx = j*num_per + ii. */
 int b200pir_db_upsert_item(b200pir_ctx* ctx, b200pir_db* db, uint64_t slice, uint64_t item_idx, const uint64_t* poly);

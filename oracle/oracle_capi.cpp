@@ -415,6 +415,12 @@ int orc_update_item_raw(void* h, const uint8_t* data, size_t len, uint64_t* out)
   ORC_CATCH
 }
 
+int orc_load_db_from_bytes(void* h, const uint8_t* file, size_t len, uint64_t* db) {
+  ORC_TRY
+  load_db_from_bytes(*(Params*)h, file, len, db);
+  ORC_CATCH
+}
+
 // ---- DoublePIR
 int orc_dpir_matvec_packed(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t rows, size_t cols) {
   ORC_TRY

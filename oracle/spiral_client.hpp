@@ -484,4 +484,27 @@ inline void update_item_raw(const Params& p, const uint8_t* data, size_t len, u6
   }
 }
 
+// lib/spiral-rs/src/server.rs:277-357 load_item_from_seek + load_db_from_seek (twin: lib/server/src/db/loading.rs:192-247) over
+// an in-memory image of the file: item i, chunk c = instance * n^2 + trial starts at byte i * db_item_size + c * bytes_per_chunk
+// and is bytes_per_chunk long, clipped at the end of the file (NOT at the end of the item: when db_item_size is not a
+// multiple of the chunk count the last chunk of an item runs into the next item, as in the reference).  logp == 8 here, so
+// read_arbitrary_bits(data, i * 8, 8) is byte i.  db: [instance][trial][z][ii][j], packed lo | hi << 32.
+inline void load_db_from_bytes(const Params& p, const uint8_t* file, size_t len, u64* db) {
+  if (log2_ceil(p.pt_modulus) != 8) throw std::runtime_error("load_item_from_seek: only logp == 8 is restated");
+  const size_t chunks = p.instances * p.n * p.n, bpc = p.bytes_per_chunk(), N = p.poly_len;
+  if (bpc > N) throw std::runtime_error("chunk longer than poly_len");                 // server.rs:292
+  const size_t dim0 = (size_t)1 << p.db_dim_1, num_per = (size_t)1 << p.db_dim_2, num_items = dim0 * num_per;
+#pragma omp parallel for schedule(dynamic)
+  for (size_t idx = 0; idx < chunks * num_items; idx++) {
+    const size_t c = idx / num_items, i = idx % num_items, ii = i % num_per, j = i / num_per;
+    const size_t pos = i * p.db_item_size + c * bpc;
+    const size_t got = pos < len ? std::min(bpc, len - pos) : 0;
+    PolyMatrix item = raw_zero(p, 1, 1);
+    for (size_t k = 0; k < got; k++) item.data[k] = file[pos + k];
+    for (size_t z = 0; z < N; z++) item.data[z] = recenter_mod(item.data[z], p.pt_modulus, p.modulus);
+    PolyMatrix nt = to_ntt_alloc(p, item);
+    for (size_t z = 0; z < N; z++) db[((c * N + z) * num_per + ii) * dim0 + j] = nt.data[z] | (nt.data[N + z] << 32);
+  }
+}
+
 }  // namespace orc

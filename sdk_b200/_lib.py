@@ -39,6 +39,7 @@ def _load():
         "b200pir_db_upload_slice": (C.c_int, [vp, vp, C.c_uint64, u64p, C.c_size_t]),
         "b200pir_db_upload": (C.c_int, [vp, vp, u64p, C.c_size_t]),
         "b200pir_db_load_file": (C.c_int, [vp, vp, C.c_char_p]),
+        "b200pir_db_load_raw_file": (C.c_int, [vp, vp, C.c_char_p]),
         "b200pir_db_upsert_item": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, u64p]),
         "b200pir_db_update_item_raw": (C.c_int, [vp, vp, C.c_uint64, u8p, C.c_size_t]),
         "b200pir_db_fill_synthetic": (C.c_int, [vp, vp, C.c_uint64]),

@@ -796,6 +796,60 @@ int b200pir_db_update_item_raw(b200pir_ctx* c, b200pir_db* db, uint64_t db_idx, 
   API_END
 }
 
+// load_db_from_seek (lib/spiral-rs/src/server.rs:277-357; lib/server/src/db/loading.rs:192-247): `path` is the raw database,
+// item i at byte i * db_item_size.  Chunk c of item i is the bytes_per_chunk bytes at i * db_item_size + c * bytes_per_chunk,
+// clipped at the end of the FILE (as the reference's read does), each byte one plaintext coefficient; items past the end
+// of the file are zero polynomials.  Conversion (recenter, NTT, pack) and placement run on the GPU, `group` items per launch.
+int b200pir_db_load_raw_file(b200pir_ctx* c, b200pir_db* db, const char* path) {
+  API_BEGIN
+  if (!c || !path) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  const auto& hp = c->hp;
+  if (hp.p != 256) throw Error(B200PIR_E_UNSUPPORTED, "load_item_from_seek is restated for logp == 8 only");
+  const size_t chunks = (size_t)c->slices;
+  const size_t bpc = (hp.db_item_size + chunks - 1) / chunks;                // params.bytes_per_chunk()
+  if (bpc > (size_t)POLY) throw Error(B200PIR_E_SHAPE, "bytes_per_chunk exceeds poly_len");     // server.rs:292
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } file{fopen(path, "rb")};
+  if (!file.f) throw Error(B200PIR_E_BADARG, std::string("cannot open ") + path);
+  if (fseeko(file.f, 0, SEEK_END)) throw Error(B200PIR_E_BADARG, "cannot seek in the database file");
+  const off_t fbytes = ftello(file.f);
+  if (fbytes < 0) throw Error(B200PIR_E_BADARG, "cannot size the database file");
+  const size_t flen = (size_t)fbytes;
+  const size_t num_items = (size_t)c->dim0 * c->num_per;
+  const size_t group = 64;                                                    // items converted per launch
+  std::vector<uint8_t> host(group * chunks * bpc);
+  DevBuf<uint8_t> bucket(group * chunks * bpc);
+  DevBuf<uint64_t> polys(group * chunks * POLY);
+  for (size_t i0 = 0; i0 < num_items; i0 += group) {
+    const size_t cnt = std::min(group, num_items - i0);
+    std::fill(host.begin(), host.end(), 0);
+    for (size_t k = 0; k < cnt; k++)
+      for (size_t ch = 0; ch < chunks; ch++) {
+        const size_t pos = (i0 + k) * hp.db_item_size + ch * bpc;
+        const size_t want = pos < flen ? std::min(bpc, flen - pos) : 0;
+        if (want && (fseeko(file.f, (off_t)pos, SEEK_SET) || fread(host.data() + (k * chunks + ch) * bpc, 1, want, file.f) != want))
+          throw Error(B200PIR_E_SHAPE, "short read from the database file");
+      }
+    B200_CUDA(cudaMemcpyAsync(bucket.p, host.data(), cnt * chunks * bpc, cudaMemcpyHostToDevice, c->stream));
+    launch_item_from_bytes(c->dp, bucket.p, (int)(cnt * chunks), (int)bpc, hp.p, polys.p, c->stream);
+    for (size_t k = 0; k < cnt; k++) {
+      const size_t idx = i0 + k;
+      const int ii = (int)(idx % c->num_per), j = (int)(idx / c->num_per);
+      if (ii % db->shard.count != db->shard.index) continue;                  // row lives on another GPU
+      for (size_t s = 0; s < chunks; s++) {
+        const uint64_t* poly = polys.p + (k * chunks + s) * POLY;
+        if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)s, ii / db->shard.count, j, poly, c->stream);
+        else if (db->format == 2) launch_db_upsert_tc5(db->T, db->t.p, (int)s, ii / db->shard.count, j, poly, c->stream);
+        else launch_db_upsert_frag(db->F, db->f.p, (int)s, ii / db->shard.count, j, poly, c->stream);
+      }
+    }
+    B200_CUDA(cudaStreamSynchronize(c->stream));                              // `host` is refilled next
+  }
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+
 int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
   API_BEGIN
   if (!c) throw Error(B200PIR_E_BADARG, "null ctx");

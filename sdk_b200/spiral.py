@@ -116,6 +116,13 @@ class Database:
         check(LIB.b200pir_db_load_file(params._h, self._h, str(path).encode()))
         return self
 
+    @classmethod
+    def from_raw_file(cls, params, path, fmt=None, shard_index=0, shard_count=1):
+        """load_db_from_seek (server.rs:320-357): raw item bytes, item i at byte i * db_item_size."""
+        self = cls(params, shard_index=shard_index, shard_count=shard_count, fmt=fmt)
+        check(LIB.b200pir_db_load_raw_file(params._h, self._h, str(path).encode()))
+        return self
+
     def upload_slice(self, slice_idx, words):
         check(LIB.b200pir_db_upload_slice(self.params._h, self._h, slice_idx, _ptr(words), words.size))
 

@@ -297,6 +297,13 @@ class Params:
         _ck(LIB.orc_query_deserialize(self.hp, _p8(data), C.c_size_t(data.size), _p64(ct)))
         return ct
 
+    def load_db_from_bytes(self, data):
+        """load_db_from_seek (server.rs:320-357) over an in-memory file image -> db words."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        db = np.zeros(self.slices * self.dim0 * self.num_per * self.N, dtype=np.uint64)
+        _ck(LIB.orc_load_db_from_bytes(self.hp, _p8(data), C.c_size_t(data.size), _p64(db)))
+        return db
+
     def generate_db(self, seed):
         db = np.zeros(self.slices * self.dim0 * self.num_per * self.N, dtype=np.uint64)
         _ck(LIB.orc_generate_db(self.hp, C.c_uint64(seed), _p64(db)))

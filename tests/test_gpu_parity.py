@@ -778,3 +778,30 @@ def test_database_loaded_from_file_equals_uploaded_database(fmt, tmp_path):
     with pytest.raises(S.B200PirError):
         S.Database.from_file(G, tmp_path / "missing.bin", fmt=fmt)
     G.set_option("db_format", 0)
+
+
+# ------------------------------------------------------------------ raw database file (load_db_from_seek, server.rs:277-357)
+@pytest.mark.parametrize("fmt,shrink", [(1, 0), (0, 2)])
+def test_database_loaded_from_raw_file_matches_oracle(fmt, shrink, tmp_path):
+    """shrink = 2: db_item_size not a multiple of the chunk count, so an item's last chunk reads into the next item."""
+    S = _gpu()
+    kw = dict(O.PARAM_SETS["T"])
+    kw["db_item_size"] -= shrink
+    P = O.Params(**kw)
+    G = S.Params(**kw)
+    rng = np.random.default_rng(33)
+    total = P.dim0 * P.num_per
+    raw = rng.integers(0, 256, total * P.db_item_size - 3000, dtype=np.uint8)        # truncated last item
+    path = tmp_path / "raw.bin"
+    raw.tofile(str(path))
+    ref_db = P.load_db_from_bytes(raw)
+    gdb = S.Database.from_raw_file(G, path, fmt=fmt)
+    G.set_option("db_format", 0)
+    v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
+         | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
+    slice_words = P.dim0 * P.num_per * P.N
+    for s in range(P.slices):
+        ref = P.multiply_reg_by_database(ref_db[s * slice_words:(s + 1) * slice_words], v)
+        assert np.array_equal(S.multiply_reg_by_database(G, gdb, s, v), ref), (fmt, shrink, s)
+    gdb.close()
+    G.close()

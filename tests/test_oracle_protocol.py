@@ -173,3 +173,31 @@ def test_sparse_database_decodes_with_the_sparse_server_fold():
         assert not np.array_equal(dense, sparse)
         assert np.array_equal(cl.decode_response(sparse), P.db_plain_item(0xABCD, idx))
         assert np.array_equal(cl.decode_response(dense), P.db_plain_item(0xABCD, idx))
+
+
+def test_load_db_from_seek_restatement():
+    # server.rs:277-357: raw file -> database words.  (i) With db_item_size a multiple of the chunk count every item equals
+    # what update_item_raw (loading.rs:317-359) builds from the same bytes; (ii) otherwise the last chunk of an item runs
+    # into the next item's bytes, as the reference's seek + read does; (iii) items past the end of the file are zero.
+    P = O.Params.named("T")
+    rng = np.random.default_rng(12)
+    total = P.dim0 * P.num_per
+    raw = rng.integers(0, 256, total * P.db_item_size - 5000, dtype=np.uint8)      # short file: the last item is truncated
+    db = P.load_db_from_bytes(raw).reshape(P.slices, P.N, P.num_per, P.dim0)
+    padded = np.concatenate([raw, np.zeros(5000, dtype=np.uint8)])
+    for idx in (0, 1, 77, total - 1):
+        polys = P.update_item_raw(padded[idx * P.db_item_size:(idx + 1) * P.db_item_size]).reshape(P.slices, P.N)
+        ii, j = idx % P.num_per, idx // P.num_per
+        assert np.array_equal(db[:, :, ii, j], polys), idx
+    kw = dict(P.kw)
+    kw["db_item_size"] = P.db_item_size - 2                                          # 4 chunks of ceil((size)/4) bytes overlap
+    P2 = O.Params(**kw)
+    assert P2.bytes_per_chunk * P2.slices > P2.db_item_size
+    raw2 = rng.integers(0, 256, total * P2.db_item_size, dtype=np.uint8)
+    db2 = P2.load_db_from_bytes(raw2).reshape(P2.slices, P2.N, P2.num_per, P2.dim0)
+    idx = 5
+    bpc = P2.bytes_per_chunk
+    chunks = [raw2[idx * P2.db_item_size + c * bpc: idx * P2.db_item_size + (c + 1) * bpc] for c in range(P2.slices)]
+    assert chunks[-1].size == bpc                                                     # reaches into item idx + 1
+    polys = P2.update_item_raw(np.concatenate(chunks)).reshape(P2.slices, P2.N)
+    assert np.array_equal(db2[:, :, idx % P2.num_per, idx // P2.num_per], polys)
