@@ -6,13 +6,16 @@ over one batch of `--batch` synthetic queries against the HBM-resident database.
 
   * `value`     : queries/s with the queries already resident in HBM (device-timed, CUDA events,
                   barrier + synchronize on both sides, max over ranks)
-  * `e2e`       : the same metric through the C-ABI call with HOST buffers (pinned): the H2D copy of
-                  the query ciphertexts and the D2H read of the response bytes are inside the timed region
+  * `e2e`       : the same metric through the reference-facing C-ABI call b200pir_process_query_bytes with HOST buffers
+                  (pinned): `batch` serialized queries (Query::serialize wire format, 16 416 bytes each) in, response
+                  bytes out; deserialization (ChaCha20 seed expansion), H2D and D2H are inside the timed region
   * `roofline`  : the dominant kernel (multiply_reg_by_database, server.rs:155-221), algorithmic bytes
                   per launch / its CUDA-event duration measured live in the timed region, against the
                   measured HBM peak of MEASURED_PEAKS.json
   * `cpu_baseline` / `--impl reference` : the CPU restatement of the reference (oracle/, "port": no Rust
-                  toolchain exists in the image) on the host cores, on a bounded sample
+                  toolchain exists in the image) on the host cores: FULL process_query calls on the same parameter set
+                  (measured, one query at a time as the reference processes them), with the bounded-sample extrapolation
+                  of round 1 beside it
 
 Workloads: N=1 -> S8 = 2^17 Spiral items x 8 KiB = 2^20 x 1 KiB records, 1 GiB of
 plaintext = 8 GiB HBM-resident.  N>1 (strong scaling) -> the SAME database with its second-dimension rows
@@ -231,17 +234,63 @@ def cpu_process_query_sample(kw, threads=None, sample_rows=64):
     return est, cores, sample
 
 
+class CpuFullQuery:
+    """The oracle's process_query (CPU restatement of the reference, AVX2 + OpenMP) on the FULL parameter set: one call = one
+    query against the whole database, exactly what the reference's /private-read handler does per request.  The database
+    is a host array of the right size (a random block tiled: the computation is data-oblivious)."""
+
+    def __init__(self, kw, threads=None):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import numpy as np
+        import oracle_lib as O
+        self.O, self.np = O, np
+        self.simd = "AVX2 first dimension" if O.LIB.orc_use_avx2_multiply(1) else "scalar first dimension"
+        self.simd += " and transforms" if O.LIB.orc_use_avx2_ntt(1) else ", scalar transforms"
+        rng = np.random.default_rng(7)
+        self.P = O.Params(**kw)
+        self.pp = synthetic_pp(kw, rng)
+        self.q = dict(ct=rng.integers(0, self.P.modulus, 2 * POLY, dtype=np.uint64))
+        words = self.P.slices * self.P.dim0 * self.P.num_per * POLY
+        block = min(words, 1 << 22)
+        blk = (rng.integers(0, Q0, block, dtype=np.uint64) | (rng.integers(0, Q1, block, dtype=np.uint64) << np.uint64(32)))
+        self.db = np.tile(blk, words // block) if words > block else blk
+        self.db_bytes = self.db.nbytes
+        ncpu = os.cpu_count() or 1
+        if threads:
+            O.LIB.orc_set_num_threads(int(threads))
+        else:
+            # pick the thread count that serves the CPU path best (all logical CPUs often lose to one thread per core)
+            best = None
+            for t in sorted({ncpu, max(ncpu // 2, 1)}, reverse=True):
+                O.LIB.orc_set_num_threads(t)
+                dt = self.one()
+                if best is None or dt < best[0]:
+                    best = (dt, t)
+            O.LIB.orc_set_num_threads(best[1])
+        self.cores = int(O.LIB.orc_num_threads())
+
+    def one(self):
+        t0 = time.perf_counter()
+        self.P.process_query(self.pp, self.q, self.db)
+        return time.perf_counter() - t0
+
+    def sample(self, n):
+        return ("oracle process_query (%s, OpenMP, %d threads): %d full quer%s against the whole %.2f GiB database, one at a "
+                "time (measured, not extrapolated)" % (self.simd, self.cores, n, "y" if n == 1 else "ies", self.db_bytes / 2**30))
+
+
 def run_reference_arm(args, kw, workload_name, rank, world):
     if rank != 0:
         return
+    cpu = CpuFullQuery(kw)
     per_step = []
-    est = cores = sample = None
     for i in range(args.warmup + args.steps):
-        est, cores, sample = cpu_process_query_sample(kw, sample_rows=32)
+        dt = cpu.one()                       # a step = one full process_query on the host cores
         if i >= args.warmup:
-            per_step.append(est)
+            per_step.append(dt)
     sec = sum(per_step) / len(per_step)
     qps = 1.0 / sec
+    cores, sample = cpu.cores, cpu.sample(len(per_step))
     out = {
         "impl": "reference", "metric": "PIR server queries/sec (Spiral process_query)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -269,16 +318,17 @@ def main():
                     help="N > 1: each rank's queries are processed in this many waves so that the all-gather of one wave's "
                          "expanded queries overlaps the expansion / first dimension of the other")
     ap.add_argument("--mul-variant", type=int, default=0)
-    ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "1")),
-                    help="0 = IMAD layout, 1 = INT8 tensor-core fragment order, 2 = tcgen05 tile images (experimental)")
+    ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "-1")),
+                    help="-1 = the library's choice (tcgen05 tile images wherever supported), 0 = IMAD layout, "
+                         "1 = mma.sync fragment order, 2 = tcgen05 tile images")
     ap.add_argument("--fold-variant", type=int, default=1)
     ap.add_argument("--intt-variant", type=int, default=0)
     ap.add_argument("--imma-variant", type=int, default=0)
     ap.add_argument("--expand-variant", type=int, default=0)
     ap.add_argument("--queries-per-pass", type=int, default=None,
-                    help="queries per database pass (1, 2, 4, 8 or 16).  Default 8: the first dimension stays near the HBM "
-                         "roof.  16 is +2.6%% q/s on one GPU (profiles/bench_r01_final2_qpp16.json) but slower on 1/8 row "
-                         "shards, where a CTA's share of the database is no larger than the query operand it stages")
+                    help="queries per database pass (1, 2, 4, 8 or 16).  Default: 16 on the tcgen05 path (the pass stays "
+                         "HBM-bound), 8 on the mma.sync path (its 16-query pass is bound by the legacy tensor pipe)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the concurrent-queries sweep (Q = 1, 32, 128; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
@@ -339,11 +389,12 @@ def main():
     G.set_option("intt_variant", args.intt_variant)
     G.set_option("imma_variant", args.imma_variant)
     G.set_option("expand_variant", args.expand_variant)
+    gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=None if args.db_format < 0 else args.db_format)
+    args.db_format = gdb.info()["format"]
     if args.queries_per_pass is None:
-        args.queries_per_pass = 8
+        args.queries_per_pass = 16 if args.db_format == 2 else 8
     per_pass = min(args.queries_per_pass, 16 if B >= 16 else (8 if B >= 8 else (4 if B >= 4 else (2 if B >= 2 else 1))))
     G.set_option("batch", per_pass)
-    gdb = S.Database(G, shard_index=rank if N > 1 else 0, shard_count=N, fmt=args.db_format)
     gdb.fill_synthetic(0xB1755)
     rng = np.random.default_rng(20260923)
     pp = synthetic_pp(kw, rng)
@@ -355,6 +406,12 @@ def main():
     h_q = torch.empty(q_words, dtype=torch.int64).pin_memory()
     h_q.numpy().view(np.uint64)[:] = rng.integers(0, modulus, q_words, dtype=np.uint64)
     h_out = torch.empty((B // N) * rb, dtype=torch.uint8).pin_memory()
+    # wire-format queries (Query::serialize, client.rs:279-301: 32-byte seed || row 1 of ct) for the e2e leg
+    qb = G.query_bytes
+    h_qbytes = torch.empty((B // N) * qb, dtype=torch.uint8).pin_memory()
+    qv = h_qbytes.numpy().reshape(B // N, qb)
+    qv[:, :32] = rng.integers(0, 256, (B // N, 32), dtype=np.uint8)
+    qv[:, 32:] = rng.integers(0, modulus, (B // N, (qb - 32) // 8), dtype=np.uint64).view(np.uint8).reshape(B // N, qb - 32)
     d_q = h_q.cuda(non_blocking=False)
     d_out = torch.zeros((B // N) * rb, dtype=torch.uint8, device="cuda")
     rows_local = d["num_per"] // N
@@ -404,7 +461,8 @@ def main():
     def step_e2e():
         if N == 1:
             n = C.c_size_t(0)
-            check(LIB.b200pir_process_query_batch(G._h, gdb._h, gpp._h, h_q.data_ptr(), B, h_out.data_ptr(), C.byref(n)))
+            check(LIB.b200pir_process_query_bytes(G._h, gdb._h, gpp._h, h_qbytes.data_ptr(), B * qb, B, h_out.data_ptr(),
+                                                  C.byref(n)))
         else:
             d_q.copy_(h_q, non_blocking=True)
             step_dev()
@@ -420,7 +478,6 @@ def main():
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    G.set_option("profile", 2)
     launches0 = LIB.b200pir_kernel_launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -437,6 +494,12 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = LIB.b200pir_kernel_launches() - launches0
     ms_total = ev0.elapsed_time(ev1)
+    # per-stage / per-kernel times come from a SEPARATE pass of the same steps with per-stage CUDA events on
+    # (the timed region above is un-instrumented)
+    G.set_option("profile", 2)
+    for _ in range(args.steps):
+        step_dev()
+    barrier()
     stage = G.last_stage_ms()
     G.set_option("profile", 0)
     if dist is not None:
@@ -472,6 +535,27 @@ def main():
         pk, _src = measured_peak()
         single_roofline = {"queries_per_launch": 1, "kernel_ms": k_ms, "achieved": alg1 / (k_ms * 1e-3) / 1e9, "peak": pk,
                            "unit": "GB/s", "frac": alg1 / (k_ms * 1e-3) / 1e9 / pk, "algorithmic_bytes_per_launch": alg1}
+
+    # ---- concurrent-queries sweep (Q in {1, 8, 32, 128} in flight), device-resident, N == 1 only
+    sweep = None
+    if N == 1 and not args.steps_only and not args.no_sweep:
+        sweep = {}
+        for Q in (8, 32, 128):
+            dq = torch.from_numpy(rng.integers(0, modulus, Q * 2 * POLY, dtype=np.uint64).view(np.int64)).cuda()
+            do = torch.zeros(Q * rb, dtype=torch.uint8, device="cuda")
+            reps = max(2, min(args.steps, 256 // Q))
+            for _ in range(2):
+                check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, dq.data_ptr(), Q, do.data_ptr()))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, dq.data_ptr(), Q, do.data_ptr()))
+            e1.record()
+            torch.cuda.synchronize()
+            sweep["Q%d" % Q] = {"queries_per_s": Q * reps * 1e3 / e0.elapsed_time(e1), "ms_per_batch": e0.elapsed_time(e1) / reps}
+            del dq, do
+        sweep["Q1"] = {"queries_per_s": 1e3 / single_ms, "ms_per_batch": single_ms}
 
     # ---- end to end (host buffers, copies inside the timed region)
     e2e_steps = 0 if args.steps_only else args.steps
@@ -516,8 +600,19 @@ def main():
         cpu = None
         if N == 1 and not args.no_cpu_baseline:
             try:
-                est, cores, sample = cpu_process_query_sample(kw)
-                cpu = {"value": 1.0 / est, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+                full = CpuFullQuery(kw)
+                times = [full.one() for _ in range(3)]
+                sec = sorted(times)[1]                                   # median of three full queries
+                cpu = {"value": 1.0 / sec, "unit": "queries/s", "cores": full.cores, "kind": "port",
+                       "sample": full.sample(3) + "; median", "full_query_s": times}
+                threads = full.cores
+                del full
+                est, _cores, sample = cpu_process_query_sample(kw, threads=threads)
+                cpu["extrapolated_value"] = 1.0 / est
+                cpu["extrapolated_sample"] = sample
+                if single_ms:
+                    # like for like: one query at a time on both sides (the reference has no batching)
+                    cpu["gpu_single_query_vs_cpu"] = (1e3 / single_ms) / cpu["value"]
             except Exception as e:      # the oracle is only a reported baseline; never fail the bench on it
                 cpu = {"value": None, "unit": "queries/s", "cores": None, "kind": "port", "sample": "failed: %r" % (e,)}
         out = {
@@ -533,11 +628,16 @@ def main():
                                        "waves (%d bytes received per rank per step)" % (N, B // N, W, coll_bytes))
                        if N > 1 else "single GPU",
                        "l2": "inputs larger than L2 (database %.1f GiB per GPU streamed every step)" % (db_bytes / 2**30)},
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * 2 * POLY * 8,
-                    "d2h_bytes_per_step": B * rb},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": (B * qb) if N == 1 else B * 2 * POLY * 8,
+                    "d2h_bytes_per_step": B * rb,
+                    "call": "b200pir_process_query_bytes (Query::deserialize + process_query, wire-format queries)" if N == 1
+                            else "three-phase device entry points around NCCL all-gathers, query ciphertexts copied from pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
             "single_query_latency_ms": single_ms, "single_query_roofline": single_roofline,
+            "concurrent_queries_sweep": sweep,
+            "timed_region": "un-instrumented; stage_ms_per_step and roofline.kernel_ms come from a separate pass of the same steps "
+                            "with per-stage CUDA events",
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -52,8 +52,8 @@ void b200pir_ctx_destroy(b200pir_ctx* ctx);
 int b200pir_ctx_set_stream(b200pir_ctx* ctx, void* cuda_stream);
 int b200pir_ctx_synchronize(b200pir_ctx* ctx);
 /* knobs: "mul_variant" (kernel tiling), "batch" (max queries per database pass: 1, 2, 4, 8 or 16;
- * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: 0 = IMAD, 1 = INT8 MMA fragments,
- * 2 = tcgen05 tile images — experimental, see tc5_kernels.cu), "profile" (0 off, 1 per call,
+ * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: -1 = automatic (default): 2 wherever the
+ * tcgen05 kernel supports the geometry, else 1; 0 = IMAD, 1 = mma.sync INT8 fragments, 2 = tcgen05 tile images, tc5_kernels.cu), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
  * "expand_variant" (0 = default everywhere); "sparse_fold" (1 = fold like lib/server's sparse server,
  * compute/fold.rs:15-65: an all-zero ciphertext short-cuts the external product; 0 = spiral-rs's dense fold, default); "expand_pair_min_ctas" (expansion rounds with at least this many active
@@ -91,6 +91,9 @@ int b200pir_db_update_item_raw(b200pir_ctx* ctx, b200pir_db* db, uint64_t db_idx
 /* Synthetic database generated on the GPU: plaintext coefficient = splitmix64(seed, ((slice*items+item)*2048+z)) % p,
  * then recenter_mod / NTT / pack as generate_random_db_and_get_item does (server.rs:223-275). */
 int b200pir_db_fill_synthetic(b200pir_ctx* ctx, b200pir_db* db, uint64_t seed);
+/* What `db` is: its layout (the "db_format" it was created with, resolved when that was -1), the second-dimension rows
+ * this GPU holds, and its size in HBM.  Any out pointer may be NULL. */
+int b200pir_db_info(b200pir_db* db, int* format, uint64_t* local_rows, uint64_t* hbm_bytes);
 
 /* ---- public parameters: replaces &PublicParameters (client.rs:146-152), all matrices in NTT form ---- */
 /* v_packing: num_packing x (n+1) x t_conv ; v_expansion_left: g x 2 x t_exp_left ;

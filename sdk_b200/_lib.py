@@ -43,6 +43,7 @@ def _load():
         "b200pir_db_upsert_item": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, u64p]),
         "b200pir_db_update_item_raw": (C.c_int, [vp, vp, C.c_uint64, u8p, C.c_size_t]),
         "b200pir_db_fill_synthetic": (C.c_int, [vp, vp, C.c_uint64]),
+        "b200pir_db_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "b200pir_pp_create": (C.c_int, [vp, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
         "b200pir_pp_create_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
         "b200pir_query_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, u64p]),

@@ -10,12 +10,27 @@
 #include <memory>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace b200pir;
 
-namespace b200pir { thread_local unsigned long long g_kernel_launches = 0; }
+namespace b200pir {
+thread_local unsigned long long g_kernel_launches = 0;
+
+void opt_in_smem_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;      // (kernel, device) pairs already opted in
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kernel, dev})) return;
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({kernel, dev});
+}
+}  // namespace b200pir
 
 namespace {
 
@@ -134,7 +149,8 @@ struct b200pir_ctx {
   long pair_min_ctas = 592;      // 4 x 148 SMs
   int sparse_fold = 0;           // 1: lib/server's fold (all-zero ciphertext shortcut, compute/fold.rs:37-43); 0: spiral-rs dense fold
   int imma_variant = 0;          // 0: cp.async-pipelined kernel for 5..8 queries per pass, 1: load-then-use kernel
-  int db_format = 0;             // format given to databases created from now on: 0 = IMAD layout, 1 = INT8 MMA fragments
+  int db_format = -1;            // format given to databases created from now on: -1 = automatic (2 where the tcgen05 kernel
+                                 // supports the geometry, else 1), 0 = IMAD layout, 1 = mma.sync fragments, 2 = tcgen05 tile images
   DevBuf<uint2> w_qf;            // B operand of the IMMA path (one group of <= 16 queries)
   DevBuf<uint8_t> w_qt;          // B operand of the tcgen05 path (tile images, 16 queries)
   int sm_count = 0;
@@ -614,7 +630,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "sparse_fold") c->sparse_fold = value != 0;
   else if (k == "expand_variant") c->expand_variant = (int)value;
   else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
-  else if (k == "db_format") { if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be 0, 1 or 2"); c->db_format = (int)value; }
+  else if (k == "db_format") { if (value < -1 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be -1 (automatic), 0, 1 or 2"); c->db_format = (int)value; }
   else if (k == "profile") {
     if (value < 0 || value > 2) throw Error(B200PIR_E_BADARG, "profile must be 0, 1 or 2");
     c->profile = (int)value;
@@ -644,9 +660,9 @@ int b200pir_db_create(b200pir_ctx* c, uint64_t shard_index, uint64_t shard_count
   db->ctx = c;
   db->shard = Shard{(int)shard_index, (int)shard_count};
   db->rows = c->num_per / (int)shard_count;
-  db->format = c->db_format;
   db->F = make_imma_geom(c->dim0, db->rows);
   db->T = make_tc5_geom(c->dim0, db->rows);
+  db->format = c->db_format >= 0 ? c->db_format : (tc5_supported(db->T) ? 2 : 1);
   if (db->format == 0) {
     size_t cells = (size_t)c->slices * db->slice_cells();
     db->d.alloc(cells);
@@ -850,6 +866,14 @@ int b200pir_db_load_raw_file(b200pir_ctx* c, b200pir_db* db, const char* path) {
   API_END
 }
 
+int b200pir_db_info(b200pir_db* db, int* format, uint64_t* local_rows, uint64_t* hbm_bytes) {
+  API_BEGIN
+  if (!db) throw Error(B200PIR_E_BADARG, "null db");
+  if (format) *format = db->format;
+  if (local_rows) *local_rows = (uint64_t)db->rows;
+  if (hbm_bytes) *hbm_bytes = (uint64_t)(db->d.n * sizeof(uint4) + db->f.n * sizeof(uint4) + db->t.n);
+  API_END
+}
 int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
   API_BEGIN
   if (!c) throw Error(B200PIR_E_BADARG, "null ctx");

@@ -489,14 +489,10 @@ void launch_multiply_imma(const DevParams& P, const ImmaGeom& F, const uint4* db
   const size_t smem = (size_t)ntiles * F.ks * 128 * sizeof(uint2);
   const size_t smem8 = smem + (size_t)8 * IMMA_STAGES * 128 * sizeof(uint4);
   const size_t smem16 = smem + (size_t)8 * IMMA_STAGES16 * 128 * sizeof(uint4);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_multiply_imma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(k_multiply_imma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute((k_multiply_imma8<2, IMMA_STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    cudaFuncSetAttribute((k_multiply_imma8<4, IMMA_STAGES16>), cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    attr_set = true;
-  }
+  opt_in_smem(k_multiply_imma<1>, 96 * 1024);
+  opt_in_smem(k_multiply_imma<2>, 96 * 1024);
+  opt_in_smem((k_multiply_imma8<2, IMMA_STAGES>), 112 * 1024);
+  opt_in_smem((k_multiply_imma8<4, IMMA_STAGES16>), 224 * 1024);
   ++g_kernel_launches;
   if (ntiles == 4) {
     if (smem16 > 224 * 1024) throw Error(-2, "imma multiply: dim0 too large for 16 queries per pass");
@@ -517,11 +513,7 @@ template <int PP>
 static void launch_intt_tiled(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,
                               int nq, int slices, cudaStream_t s) {
   const size_t smem = (size_t)(PP * POLY + 2 * NTT_SMEM_WORDS) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_intt_from_zmajor_tiled<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  opt_in_smem(k_intt_from_zmajor_tiled<PP>, (int)smem);
   k_intt_from_zmajor_tiled<PP><<<dim3(F.rows * 2 / PP, 2, nq * slices), 256, smem, s>>>(P, F, in_zm, in_stride, out, slices);
 }
 void launch_intt_from_zmajor(const DevParams& P, const ImmaGeom& F, const uint32_t* in_zm, size_t in_stride, uint32_t* out,

@@ -17,6 +17,13 @@ static const int POLY = 2048;
 // number of kernels this library has launched from the calling thread (bench.py reports it)
 extern thread_local unsigned long long g_kernel_launches;
 
+// Opt a kernel in to more than 48 KiB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device only, so
+// the opt-in is remembered per (kernel, device): one process may drive several GPUs (one context per GPU) from several host
+// threads.  Thread-safe.
+void opt_in_smem_impl(const void* kernel, int bytes);
+template <typename K>
+inline void opt_in_smem(K* kernel, int bytes) { opt_in_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
+
 // ---- generic transforms (K3/K4 of SURVEY §2.3)
 // u64 ABI format [poly][n][z]  <->  in place forward / inverse NTT (ntt.rs:67-113 / :212-258)
 void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s);

@@ -441,11 +441,7 @@ void launch_db_synth(const DevParams& P, const MulGeom& G, Shard sh, uint4* db_d
   if (ctas == 0) return;
   if (ctas > 0x7fffffffULL) throw Error(-2, "db_synth: grid too large");
   const size_t smem = (size_t)(2 * NTT_SMEM_WORDS + 4 * POLY) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_db_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  opt_in_smem(k_db_synth, (int)smem);
   ++g_kernel_launches;
   k_db_synth<<<(unsigned)ctas, 512, smem, s>>>(P, G, sh, db_dev, seed, pt_modulus, slice_begin);
 }

@@ -1164,12 +1164,8 @@ void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size
                      const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
                      int variant, uint32_t* zero_flags, cudaStream_t s) {
   if (batch == 0 || half == 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_fold_res<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
-    cudaFuncSetAttribute(k_fold_res<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemFold);
-    attr_set = true;
-  }
+  opt_in_smem(k_fold_res<2>, (int)kDynSmemFold);
+  opt_in_smem(k_fold_res<3>, (int)kDynSmemFold);
   if (zero_flags) {            // scratch of batch * 2 * half words: recomputed every round, as the reference re-tests every step
     ++g_kernel_launches;
     k_ct_zero_flags<<<(unsigned)(batch * 2 * half), 256, 0, s>>>(in, batch_stride, 2 * half, zero_flags);
@@ -1214,32 +1210,20 @@ void launch_expand_scalar(const DevParams& P, uint32_t* v, size_t v_stride, int 
   k_expand_scalar<<<dim3(grid1d(total, 256), nq), 256, 0, s>>>(P, v, v_stride, num_in, neg1_r);
 }
 void launch_expand_round(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
-    attr_set = true;
-  }
+  opt_in_smem(k_expand_round, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_expand_round<<<dim3((unsigned)(2 * R.num_in), nq), CTA, kDynSmemBig, s>>>(P, v, v_stride, R);
 }
 void launch_expand_round_pair(const DevParams& P, uint32_t* v, size_t v_stride, int nq, const ExpandRound& R,
                               const uint32_t* neg1_r, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_expand_round_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
-    attr_set = true;
-  }
+  opt_in_smem(k_expand_round_pair, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_expand_round_pair<<<dim3((unsigned)R.num_in, nq), CTA, kDynSmemBig, s>>>(P, v, v_stride, R, neg1_r);
 }
 void launch_expand_round_res(const DevParams& P, uint32_t* v, size_t v_stride, uint32_t* xr, size_t xr_stride, int nq,
                              const ExpandRound& R, const uint32_t* neg1_r, cudaStream_t s) {
   const size_t smem = (size_t)2 * NTT_SMEM_WORDS * 4 + (size_t)POLY * 8 + (size_t)HI_TW * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_expand_round_res<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  opt_in_smem(k_expand_round_res<3>, (int)smem);
   g_kernel_launches += 2;
   k_expand_intt<<<dim3((unsigned)R.num_in, 2, nq), 256, 0, s>>>(P, v, v_stride, xr, xr_stride, R);
   k_expand_round_res<3><<<dim3((unsigned)R.num_in, 2, nq), 256, smem, s>>>(P, v, v_stride, xr, xr_stride, R, neg1_r);
@@ -1254,11 +1238,7 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride,
                          int nq, int count, int idx_factor, int idx_offset, const uint32_t* v_conv, int t_gsw,
                          int t_conv, int bits_conv, cudaStream_t s) {
   if (count == 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_regev_to_gsw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
-    attr_set = true;
-  }
+  opt_in_smem(k_regev_to_gsw, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_regev_to_gsw<<<dim3((unsigned)(count * t_gsw), nq), CTA, kDynSmemBig, s>>>(P, v_gsw, gsw_stride, v, v_stride,
                                                                                idx_factor, idx_offset, v_conv, t_gsw,
@@ -1268,11 +1248,7 @@ template <int ROWS>
 static void launch_pack_t(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded,
                           size_t ct_stride, size_t in_q_stride, int nq, const uint32_t* v_packing, int instances,
                           int t_conv, int bits_conv, int version, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_pack<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBig);
-    attr_set = true;
-  }
+  opt_in_smem(k_pack<ROWS>, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_pack<ROWS><<<dim3((unsigned)(instances * (ROWS - 1)), nq), CTA, kDynSmemBig, s>>>(
       P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, v_packing, t_conv, bits_conv, version);

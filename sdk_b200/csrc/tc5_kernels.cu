@@ -1,10 +1,9 @@
 // First dimension on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) — database format 2.
 //
-// STATUS: compiles for sm_100a; NOT yet run on a GPU (written after this round's GPU budget was spent).  Nothing selects
-// this path by default (`db_format` 2 must be requested explicitly) and its parity tests are gated behind
-// B200PIR_TEST_TC5=1 until they have passed on hardware.  The arithmetic is the one already proven bit-exact on the
-// legacy mma.sync path (imma_kernels.cu): 28-bit residues as four 7-bit limbs, exact s32 accumulation, recombination
-// with 2^{7s} and Barrett.
+// STATUS: validated on a B200 (raw accumulators match the assumed TMEM layout, parity tests bit-exact against the oracle,
+// tests/test_gpu_tcgen05.py); the default database format wherever the geometry is supported.  The arithmetic is the one
+// of the mma.sync path (imma_kernels.cu): 28-bit residues as four 7-bit limbs, exact s32 accumulation, recombination with
+// powers of 2^7 and one Barrett reduction per output word.
 //
 // multiply_reg_by_database (lib/spiral-rs/src/server.rs:155-221) for one NTT coordinate z and modulus n is the integer
 // GEMM  C[ii][(query,row)] = sum_j A[ii][j] * B[j][(query,row)] mod q_n.  Here both operands carry their limb index as
@@ -15,8 +14,9 @@
 //     K       = 32 values of j per instruction (kind::i8), dim0 / 32 instructions per tile
 //     D[M][N] = sum_j a_l(ii, j) * b_m(j, col)  < dim0 * 2^14 <= 2^24        (exact in s32)
 //
-// The epilogue reads a row of D from TMEM (lane = M index), folds the four m-limbs of every column in registers, reduces,
-// shifts by 7 l, and adds the four l-limbs, which sit in four adjacent lanes, with two shuffles.
+// The epilogue (tc5_layout.cuh) reads a row of D from TMEM (lane = M index), folds the four m-limbs of every column with shifts,
+// weights the 47-bit sum with 2^{7l} mod q in two wide multiply-adds, reduce-scatters over the four l-limb lanes of a row
+// (two shuffle rounds) and finishes with one 32-bit Barrett per stored word.
 //
 // Operand images.  Both operands are stored in global memory as exact images of the shared-memory tiles the MMA reads
 // (canonical K-major, no swizzle: 8-row x 16-byte core matrices, LBO = 128 B between the two K halves, SBO = 256 B
@@ -25,7 +25,8 @@
 //     dbT[slice][n][z][mt][ks][4096 B]      (mt: 32 rows, ks: 32 values of j)     == 8 bytes per database word, as before
 //     qT [n][z][ks][4096 B]                 (16 queries)
 // One persistent CTA per SM walks the (n, z) pairs; warp 0 = bulk-copy producer, warp 1 = MMA issuer (one thread),
-// warps 2..5 = epilogue (one per TMEM lane quadrant).  Pipelines: A ring (full/empty mbarriers), double-buffered B operand
+// warps 2..9 = epilogue (two per TMEM lane quadrant, 64 accumulator columns each: two warps per scheduler hide the latency
+// of the TMEM loads, shuffles and wide multiplies).  Pipelines: A ring (full/empty mbarriers), double-buffered B operand
 // (bfull/bempty), double-buffered accumulator in TMEM (tfull/tempty).
 #include "kernels.h"
 #include <cstdio>
@@ -38,8 +39,9 @@ namespace {
 
 constexpr int TC5_KS_PER_STAGE = 4;                     // k-steps per A stage
 constexpr int TC5_STAGE_BYTES = TC5_KS_PER_STAGE * TC5_TILE;   // 16 KiB
-constexpr int TC5_STAGES = 5;
-constexpr int TC5_THREADS = 192;                        // 6 warps
+constexpr int TC5_STAGES = 6;                           // 96 KiB of database tiles in flight per SM
+constexpr int TC5_EPI_WARPS = 8;
+constexpr int TC5_THREADS = 64 + 32 * TC5_EPI_WARPS;    // producer warp, MMA warp, epilogue warps
 constexpr int TC5_TMEM_COLS = 256;                      // two accumulator buffers of 128 columns
 constexpr int TC5_DBG_TILES = 4;
 
@@ -204,7 +206,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
     for (int s = 0; s < TC5_STAGES; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&S->bfull[b], 1); mbar_init(&S->bempty[b], 1);
-      mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], 4);
+      mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], TC5_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -275,15 +277,14 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
+    // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
+    const int quad = warp & 3, colhalf = (warp - 2) >> 2;
     const int l = tc5_lane_limb(lane);                                // database limb held by this lane
-    const uint32_t q0 = P.q[0], q1 = P.q[1];
     int it = 0, tile_no = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
       const int n = item & 1, z = item >> 1;
-      const uint32_t q = n ? q1 : q0;
-      const uint64_t cr1 = n ? P.cr1[1] : P.cr1[0];
+      const uint32_t q = n ? P.q[1] : P.q[0];
+      const Tc5Weights W = tc5_lane_weights(l, q);
       for (int t = 0; t < tiles_per_item; t++, tile_no++) {
         const int slice = slice_begin + t / T.mt, mt = t % T.mt;
         const int ab = tile_no & 1;
@@ -291,8 +292,9 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
         tc_fence_after();
         const int ii = mt * 32 + tc5_lane_row(quad, lane);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * TC5_N;
-#pragma unroll 1
-        for (int chunk = 0; chunk < 4; chunk++) {                     // 32 TMEM columns = 8 GEMM columns = 4 queries
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {                              // 32 TMEM columns = 8 GEMM columns = 4 queries
+          const int chunk = colhalf * 2 + ch;
           uint32_t v[32];
           tc_ld32(taddr + chunk * 32, v);
           tc_wait_ld();
@@ -300,29 +302,26 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
 #pragma unroll
             for (int c = 0; c < 32; c++) dbg[((size_t)tile_no * TC5_M + quad * 32 + lane) * TC5_N + chunk * 32 + c] = v[c];
           }
-          uint64_t tot[8];
+          uint64_t part[8], send4[4], keep4[4], send2[2], keep2[2];
 #pragma unroll
-          for (int c = 0; c < 8; c++) {
-            uint64_t u = tc5_fold_column(v + 4 * c, l, cr1, q);       // < 2^49
-            u += shfl_xor_u64(u, 1);
-            u += shfl_xor_u64(u, 2);                                  // all four limb lanes hold the sum (< 2^51)
-            tot[c] = u;
-          }
+          for (int c = 0; c < 8; c++) part[c] = tc5_lane_partial(v + 4 * c, W.w, W.wp);   // < 2^53
+          tc5_rs_select_a(l, part, send4, keep4);
+#pragma unroll
+          for (int i = 0; i < 4; i++) keep4[i] += shfl_xor_u64(send4[i], 2);
+          tc5_rs_select_b(l, keep4, send2, keep2);
+#pragma unroll
+          for (int i = 0; i < 2; i++) keep2[i] += shfl_xor_u64(send2[i], 1);              // columns 2l, 2l+1 over all four limbs, < 2^55
           // lane l stores query 4*chunk + l (both ciphertext rows = GEMM columns 2l, 2l+1 of this chunk)
-          uint64_t e = tot[0], o = tot[1];
-#pragma unroll
-          for (int c = 1; c < 4; c++)
-            if (l == c) { e = tot[2 * c]; o = tot[2 * c + 1]; }
           const int qi = tc5_lane_query(chunk, lane);
           if (qi < nq && ii < T.rows) {
-            uint2 r = make_uint2(tc5_barrett(e, cr1, q), tc5_barrett(o, cr1, q));
+            uint2 r = make_uint2(tc5_barrett57(keep2[0], W.mu, q), tc5_barrett57(keep2[1], W.mu, q));
             uint32_t* dst = out_zm + (size_t)qi * out_stride + ((((size_t)slice * 2 + n) * POLY + z) * T.rows + ii) * 2;
             *reinterpret_cast<uint2*>(dst) = r;
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S->tempty[ab]);                   // this quadrant has drained the accumulator
+        if (lane == 0) mbar_arrive(&S->tempty[ab]);                   // this warp has drained its part of the accumulator
       }
     }
   }
@@ -361,11 +360,7 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
   if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
   if (!tc5_supported(T)) throw Error(-2, "tcgen05 multiply: dim0 too large for one CTA's shared memory");
   const size_t smem = tc5_smem_bytes(T);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_multiply_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
+  opt_in_smem(k_multiply_tc5, 227 * 1024);
   ++g_kernel_launches;
   const int grid = sm_count > 0 ? (sm_count < 2 * POLY ? sm_count : 2 * POLY) : 148;
   // bring-up aid (scripts/tc5_probe.py): B200PIR_TC5_DUMP=<file> receives the raw s32 accumulators D[M][N] of the first

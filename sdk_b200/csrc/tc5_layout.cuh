@@ -81,23 +81,52 @@ TC5_HD void tc5_query_store(uint8_t* tile, int q, int r, int k, uint32_t value) 
 }
 
 // ---- epilogue: TMEM lane = M index; a warp owns the quadrant `quad` (32 lanes), a chunk is 32 consecutive columns
+// (8 GEMM columns x 4 query limbs m).  Lane (row, l) holds D[4 row + l][4 col + m] = sum_j a_l(row, j) b_m(j, col) < 2^24.
+// The residue is  sum_{l,m} D_{l,m} 2^{7(l+m)} mod q:
+//   1. per lane and column: s = sum_m D_{l,m} 2^{7m} (< 2^47, shifts and adds), split at bit 23 and weighted with
+//      w_l = 2^{7l} mod q, w'_l = 2^{7l+23} mod q:  P = (s mod 2^23) w_l + (s >> 23) w'_l  < 2^53   (two wide multiply-adds)
+//   2. reduce-scatter over the four limb lanes of a row (xor 2, then xor 1): lane l ends with the sums (< 2^55) of the two
+//      columns 2l, 2l+1 it stores = both ciphertext rows of query 4 chunk + l
+//   3. one Barrett reduction per stored word, with 32-bit operations (tc5_barrett57).
 TC5_HD int tc5_lane_row(int quad, int lane) { return quad * 8 + (lane >> 2); }     // row_local of this lane
 TC5_HD int tc5_lane_limb(int lane) { return lane & 3; }
 TC5_HD int tc5_lane_query(int chunk, int lane) { return chunk * 4 + (lane & 3); }  // the query this lane stores
-TC5_HD uint32_t tc5_barrett(uint64_t x, uint64_t cr1, uint32_t q) {                // == barrett64 (common.cuh)
+struct Tc5Weights { uint32_t w, wp, mu; };
+TC5_HD Tc5Weights tc5_lane_weights(int l, uint32_t q) {
+  Tc5Weights W;
+  W.w = (uint32_t)((1ull << (7 * l)) % q);
+  W.wp = (uint32_t)((1ull << (7 * l + 23)) % q);
+  W.mu = (uint32_t)((1ull << 58) / q);                                             // q > 2^27, so mu < 2^31
+  return W;
+}
+// x mod q for x < 2^57 and 2^27 < q < 2^28: quotient estimate floor((x >> 26) mu / 2^32) is the true quotient or one less
+// (x/2^58 + 2^26/q < 1), so the remainder estimate lies in [0, 2q) and its low 32 bits suffice.
+TC5_HD uint32_t tc5_barrett57(uint64_t x, uint32_t mu, uint32_t q) {
+  const uint32_t a = (uint32_t)(x >> 26);
 #if defined(__CUDA_ARCH__)
-  const uint64_t t = __umul64hi(x, cr1);
+  const uint32_t qh = __umulhi(a, mu);
 #else
-  const uint64_t t = (uint64_t)(((unsigned __int128)x * cr1) >> 64);
+  const uint32_t qh = (uint32_t)(((uint64_t)a * mu) >> 32);
 #endif
-  const uint32_t r = (uint32_t)(x - t * (uint64_t)q);
+  const uint32_t r = (uint32_t)x - qh * q;
   const uint32_t r2 = r - q;
   return r < r2 ? r : r2;
 }
-// the four m-limb partial sums of one GEMM column -> this lane's contribution (before the two shuffles over l)
-TC5_HD uint64_t tc5_fold_column(const uint32_t* v4, int l, uint64_t cr1, uint32_t q) {
-  const uint64_t s = (uint64_t)v4[0] + ((uint64_t)v4[1] << 7) + ((uint64_t)v4[2] << 14) + ((uint64_t)v4[3] << 21);   // < 2^46
-  return (uint64_t)tc5_barrett(s, cr1, q) << (7 * l);                                                              // < 2^49
+// step 1 for one GEMM column: v4 = the four m-limb accumulators of this lane
+TC5_HD uint64_t tc5_lane_partial(const uint32_t* v4, uint32_t w, uint32_t wp) {
+  const uint32_t a = v4[0] + (v4[1] << 7), b = v4[2] + (v4[3] << 7);               // < 2^32 each (D < 2^24)
+  const uint64_t s = (uint64_t)a + ((uint64_t)b << 14);                            // < 2^47
+  return (uint64_t)((uint32_t)s & 0x7FFFFFu) * w + (uint64_t)(uint32_t)(s >> 23) * wp;
+}
+// step 2, first exchange (partner = lane ^ 2): lanes with limb bit 1 clear keep columns 0..3 and send 4..7, the others the
+// opposite; second exchange (partner = lane ^ 1): of the four kept columns, lanes with limb bit 0 clear keep the first two.
+TC5_HD void tc5_rs_select_a(int l, const uint64_t (&P)[8], uint64_t (&send)[4], uint64_t (&keep)[4]) {
+  const bool up = (l & 2) != 0;
+  for (int i = 0; i < 4; i++) { send[i] = up ? P[i] : P[4 + i]; keep[i] = up ? P[4 + i] : P[i]; }
+}
+TC5_HD void tc5_rs_select_b(int l, const uint64_t (&K)[4], uint64_t (&send)[2], uint64_t (&keep)[2]) {
+  const bool odd = (l & 1) != 0;
+  for (int i = 0; i < 2; i++) { send[i] = odd ? K[i] : K[2 + i]; keep[i] = odd ? K[2 + i] : K[i]; }
 }
 
 }  // namespace b200pir

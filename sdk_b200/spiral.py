@@ -91,14 +91,18 @@ class Database:
     """The `db: &[u64]` argument of process_query, resident in HBM."""
 
     def __init__(self, params, shard_index=0, shard_count=1, fmt=None):
-        """fmt: 0 = IMAD layout (single-query HBM roofline kernel), 1 = INT8 tensor-core fragment order
-        (batched queries), 2 = tcgen05 tile images (experimental: not yet validated on hardware);
-        None = the context's current "db_format" option."""
+        """fmt: 0 = IMAD layout (CUDA-core kernel, at most 4 queries per pass), 1 = mma.sync fragment order,
+        2 = tcgen05 tile images (16 queries per pass); None = the context's "db_format" option (default -1 = automatic:
+        2 wherever the tcgen05 kernel supports the geometry, else 1).  An explicit fmt applies to this database only."""
         self.params = params
         h = C.c_void_p()
         if fmt is not None:
             params.set_option("db_format", fmt)
-        check(LIB.b200pir_db_create(params._h, shard_index, shard_count, C.byref(h)))
+        try:
+            check(LIB.b200pir_db_create(params._h, shard_index, shard_count, C.byref(h)))
+        finally:
+            if fmt is not None:
+                params.set_option("db_format", -1)
         self._h = h
         self.shard_index, self.shard_count = shard_index, shard_count
 
@@ -138,6 +142,12 @@ class Database:
 
     def fill_synthetic(self, seed):
         check(LIB.b200pir_db_fill_synthetic(self.params._h, self._h, seed))
+
+    def info(self):
+        """{"format": resolved layout (0, 1 or 2), "local_rows": second-dimension rows on this GPU, "hbm_bytes": size}"""
+        f, r, b = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        check(LIB.b200pir_db_info(self._h, C.byref(f), C.byref(r), C.byref(b)))
+        return {"format": f.value, "local_rows": r.value, "hbm_bytes": b.value}
 
     def close(self):
         if getattr(self, "_h", None):

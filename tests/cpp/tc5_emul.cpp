@@ -2,7 +2,7 @@
 // tc5_kernels.cu): the operand images are built by running the per-thread functions for every thread, the MMA is replaced
 // by the DEFINITION of the canonical K-major no-swizzle shared-memory layout (byte (row, k) of an operand tile at
 // (row/8)*SBO + (k/16)*LBO + (row%8)*16 + k%16; D[M][N] += A[M][k] * B[N][k]; accumulator row M in TMEM lane M), and the
-// epilogue runs lane by lane with the two xor-shuffles emulated.  Result compared with sum_j a*b mod q in 128-bit
+// epilogue runs lane by lane with the two shuffle rounds of its reduce-scatter emulated.  Result compared with sum_j a*b mod q in 128-bit
 // arithmetic.  This checks every index / limb / lane computation that is ours; what it cannot check is that the hardware
 // reads the descriptors the way the layout definition says.
 #include "../../sdk_b200/csrc/tc5_layout.cuh"
@@ -78,22 +78,31 @@ int main() {
         }
         for (int quad = 0; quad < 4; quad++)
           for (int chunk = 0; chunk < 4; chunk++) {
-            uint64_t u[32][8];
+            // step 1: per lane and GEMM column, the weighted partial sum; then the reduce-scatter of the kernel with both
+            // shuffle rounds emulated (every lane computes send/keep, then reads its partner's send)
+            uint64_t part[32][8], send4[32][4], keep4[32][4], send2[32][2], keep2[32][2];
+            Tc5Weights W[32];
             for (int lane = 0; lane < 32; lane++) {
               const uint32_t* v = reinterpret_cast<const uint32_t*>(&D[(size_t)(quad * 32 + lane) * TC5_N + chunk * 32]);
-              for (int c = 0; c < 8; c++) u[lane][c] = tc5_fold_column(v + 4 * c, tc5_lane_limb(lane), cr1, q);
-            }
-            for (int c = 0; c < 8; c++) {                            // u += shfl_xor(u, 1); u += shfl_xor(u, 2)
-              uint64_t t1[32], t2[32];
-              for (int lane = 0; lane < 32; lane++) t1[lane] = u[lane][c] + u[lane ^ 1][c];
-              for (int lane = 0; lane < 32; lane++) t2[lane] = t1[lane] + t1[lane ^ 2];
-              for (int lane = 0; lane < 32; lane++) u[lane][c] = t2[lane];
+              W[lane] = tc5_lane_weights(tc5_lane_limb(lane), q);
+              for (int c = 0; c < 8; c++) {
+                part[lane][c] = tc5_lane_partial(v + 4 * c, W[lane].w, W[lane].wp);
+                if (part[lane][c] >> 53) { if (bad < 5) printf("partial sum bound exceeded\n"); bad++; }
+              }
+              tc5_rs_select_a(tc5_lane_limb(lane), part[lane], send4[lane], keep4[lane]);
             }
             for (int lane = 0; lane < 32; lane++) {
-              const int l = tc5_lane_limb(lane), qi = tc5_lane_query(chunk, lane), ii = mt * 32 + tc5_lane_row(quad, lane);
+              uint64_t k[4];
+              for (int i = 0; i < 4; i++) k[i] = keep4[lane][i] + send4[lane ^ 2][i];
+              tc5_rs_select_b(tc5_lane_limb(lane), k, send2[lane], keep2[lane]);
+            }
+            for (int lane = 0; lane < 32; lane++) {
+              const int qi = tc5_lane_query(chunk, lane), ii = mt * 32 + tc5_lane_row(quad, lane);
               if (qi >= nq || ii >= rows) continue;
               for (int r = 0; r < 2; r++) {
-                const uint32_t got = tc5_barrett(u[lane][2 * l + r], cr1, q);
+                const uint64_t tot = keep2[lane][r] + send2[lane ^ 1][r];
+                if (tot >> 55) { if (bad < 5) printf("column sum bound exceeded\n"); bad++; }
+                const uint32_t got = tc5_barrett57(tot, W[lane].mu, q);
                 u128 ref = 0;
                 for (int j = 0; j < dim0; j++) ref += (u128)a[(size_t)ii * dim0 + j] * b[((size_t)qi * 2 + r) * dim0 + j];
                 if (got != (uint32_t)(ref % q)) { if (bad < 5) printf("mismatch trial %d n %d row %d query %d r %d\n", trial, n, ii, qi, r); bad++; }
@@ -101,6 +110,18 @@ int main() {
             }
           }
       }
+    }
+  }
+  // tc5_barrett57 against % on random and extreme inputs below 2^57
+  for (int n = 0; n < 2; n++) {
+    const uint32_t q = Q[n], mu = tc5_lane_weights(0, q).mu;
+    for (int i = 0; i < 2000000; i++) {
+      uint64_t x = rng() >> 7;
+      if (i < 64) x = ((uint64_t)1 << 57) - 1 - i;
+      else if (i < 128) x = (uint64_t)q * (i - 64) + (i & 1 ? q - 1 : 0);
+      else if (i < 4096) x = (uint64_t)q * (rng() >> 36) - (i & 3);
+      x &= ((uint64_t)1 << 57) - 1;
+      if (tc5_barrett57(x, mu, q) != (uint32_t)(x % q)) { if (bad < 5) printf("barrett57 mismatch at %llu mod %u\n", (unsigned long long)x, q); bad++; }
     }
   }
   printf(bad ? "tc5 emulation: %d mismatches\n" : "tc5 emulation ok%.0d\n", bad);

@@ -1,18 +1,13 @@
 """BASELINE config #5 at poly_len = 4096: the 512-thread cooperative transform (sdk_b200/csrc/ntt_core4096.cuh) against the
 oracle's scalar transforms instantiated at 4096.  The pass logic is already checked thread by thread on the CPU
-(tests/cpp/ntt_core4096_emul.cpp, part of the CPU suite); the kernel wrapper was written after the round's GPU budget
-ended, so this file is opt-in (B200PIR_TEST_NTT4K=1) until it has passed on a B200."""
-import os
-
+(tests/cpp/ntt_core4096_emul.cpp, part of the CPU suite)."""
 import numpy as np
 import pytest
 
 import oracle_lib as O
 from test_gpu_parity import setup_case, Q0, Q1
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200PIR_TEST_NTT4K") != "1",
-                                 reason="4096-point kernel not yet validated on hardware (set B200PIR_TEST_NTT4K=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_ntt4096_forward_inverse_match_oracle():

@@ -475,7 +475,7 @@ def test_e2e_params_full_size_bytes_and_decode(name):
 def test_imma_multiply_and_process_query_match_oracle(name):
     S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
     fdb = S.Database.from_words(G, db, fmt=1)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     rng = np.random.default_rng(14)
     v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
          | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
@@ -516,7 +516,7 @@ def test_imma_multiply_and_process_query_match_oracle(name):
     f2.fill_synthetic(SEED_DB)
     assert np.array_equal(S.multiply_reg_by_database(G, f2, P.slices - 1, v), S.multiply_reg_by_database(G, fdb, P.slices - 1, v))
     f3 = S.Database(G, fmt=1)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     sl = db[:slice_words].reshape(P.N, P.num_per, P.dim0)
     items = [0, 5, P.dim0 * P.num_per - 1, 33 % (P.dim0 * P.num_per)]
     sparse = np.zeros_like(sl)
@@ -548,7 +548,7 @@ def test_imma_multiply_many_tiles_long_k():
     G.close()
 
 
-@pytest.mark.parametrize("name,world,fmt", [("T0", 2, 1), ("T0", 4, 0), ("T1", 2, 1)])
+@pytest.mark.parametrize("name,world,fmt", [("T0", 2, 1), ("T0", 4, 0), ("T1", 2, 1), ("T0", 2, 2), ("T1", 2, 2)])
 def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
     """bench.py's N>1 flow on one GPU: every "rank" expands its own queries, expanded queries are concatenated
     (all-gather), every rank runs first dimension + local fold for ALL queries on its row shard, survivors are
@@ -580,7 +580,7 @@ def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
         shards.append(sh)
         check(LIB.b200pir_first_dim_fold_dev(G._h, sh._h, qexp.data_ptr(), vf.data_ptr(), total,
                                              gathered.data_ptr() + r * total * P.slices * ct_words * 4))
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     out = torch.zeros(total * G.response_bytes, dtype=torch.uint8, device="cuda")
     for r in range(world):          # phase 3
         check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, gathered.data_ptr(), world, total, r * per_rank, per_rank,
@@ -596,14 +596,14 @@ def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
 
 
 # ------------------------------------------------------------------ /write path: raw bucket bytes -> HBM (lib/server db/loading.rs)
-@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
 def test_update_item_raw_bytes_roundtrip(fmt):
     """update_item_raw (loading.rs:317-359) on the GPU == oracle's packed item polynomials, and a private read of the
     written items returns the written bytes (what e2e-tests/tests/simple.ts checks through the HTTP server)."""
     S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
     rng = np.random.default_rng(21)
     wdb = S.Database(G, fmt=fmt)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     sparse = np.zeros((P.slices, P.N, P.num_per, P.dim0), dtype=np.uint64)
     written = {}
     for idx, nbytes in ((7, P.db_item_size), (200, 100), (P.dim0 * P.num_per - 1, 1), (31, 0)):
@@ -635,7 +635,7 @@ def test_update_item_raw_bytes_roundtrip(fmt):
 
 # ------------------------------------------------------------------ degenerate second dimension (server.rs:554-577, :394-396)
 @pytest.mark.parametrize("nu_2", [0, 1])
-@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
 def test_small_second_dimension(nu_2, fmt):
     S = _gpu()
     kw = dict(O.PARAM_SETS["T"])
@@ -740,7 +740,7 @@ def test_cuda_path_reproduces_golden_fixtures(case):
     assert GC.sha(db) == gold["db_sha256"]
     G = S.Params(expand_queries=expand, **P.kw)
     gpp = S.PublicParameters(G, pp["pack"], pp.get("left"), pp.get("right"), pp.get("conv"))
-    for fmt in (1, 0):
+    for fmt in (2, 1, 0):
         gdb = S.Database.from_words(G, db, fmt=fmt)
         for (idx, q), g in zip(queries, gold["queries"]):
             assert idx == g["idx"]
@@ -754,13 +754,13 @@ def test_cuda_path_reproduces_golden_fixtures(case):
 
 
 # ------------------------------------------------------------------ preprocessed database file (server.rs:373-386)
-@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
 def test_database_loaded_from_file_equals_uploaded_database(fmt, tmp_path):
     S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
     path = tmp_path / "db.bin"
     db.tofile(str(path))                                   # native-endian u64 stream, what load_file reads
     fdb = S.Database.from_file(G, path, fmt=fmt)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     rng = np.random.default_rng(31)
     v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
          | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
@@ -777,11 +777,11 @@ def test_database_loaded_from_file_equals_uploaded_database(fmt, tmp_path):
         S.Database.from_file(G, short, fmt=fmt)
     with pytest.raises(S.B200PirError):
         S.Database.from_file(G, tmp_path / "missing.bin", fmt=fmt)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
 
 
 # ------------------------------------------------------------------ raw database file (load_db_from_seek, server.rs:277-357)
-@pytest.mark.parametrize("fmt,shrink", [(1, 0), (0, 2)])
+@pytest.mark.parametrize("fmt,shrink", [(1, 0), (0, 2), (2, 1)])
 def test_database_loaded_from_raw_file_matches_oracle(fmt, shrink, tmp_path):
     """shrink = 2: db_item_size not a multiple of the chunk count, so an item's last chunk reads into the next item."""
     S = _gpu()
@@ -796,7 +796,7 @@ def test_database_loaded_from_raw_file_matches_oracle(fmt, shrink, tmp_path):
     raw.tofile(str(path))
     ref_db = P.load_db_from_bytes(raw)
     gdb = S.Database.from_raw_file(G, path, fmt=fmt)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
          | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
     slice_words = P.dim0 * P.num_per * P.N

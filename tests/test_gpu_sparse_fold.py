@@ -1,17 +1,12 @@
 """The sparse server's fold (lib/server/src/compute/fold.rs:15-65: all-zero ciphertext shortcut) on the GPU, option
-"sparse_fold" — against the oracle's restatement.  Written after the round's GPU budget ended, so opt-in
-(B200PIR_TEST_SPARSE_FOLD=1) until it has passed on hardware; the default (dense, spiral-rs) fold is unaffected."""
-import os
-
+"sparse_fold" — against the oracle's restatement.  The default (dense, spiral-rs) fold is unaffected."""
 import numpy as np
 import pytest
 
 import oracle_lib as O
 from test_gpu_parity import setup_case, SEED_DB
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200PIR_TEST_SPARSE_FOLD") != "1",
-                                 reason="sparse fold not yet validated on hardware (set B200PIR_TEST_SPARSE_FOLD=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_stage_level_sparse_fold_matches_oracle():
@@ -45,7 +40,7 @@ def test_process_query_on_sparse_database_matches_sparse_server(fmt):
     sdb[:, :, 1::2, :] = 0                      # every odd second-dimension row empty
     sdb = sdb.reshape(-1)
     gs = S.Database.from_words(G, sdb, fmt=fmt)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     idxs = [0, 14, P.num_per * 3 + 4, 7]        # the last one targets an empty row
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     G.set_option("sparse_fold", 1)

@@ -1,26 +1,21 @@
 """Parity of the tcgen05 first dimension (database format 2, sdk_b200/csrc/tc5_kernels.cu) against the oracle.
 
-The kernel was written after the round's GPU budget was spent and has not run on hardware yet, so these tests are
-opt-in: set B200PIR_TEST_TC5=1 (and run them under `timeout`, e.g. `timeout 300 python -m pytest tests/test_gpu_tcgen05.py`).
-Once they pass on a B200 the gate goes away and format 2 becomes selectable by bench.py."""
-import os
-
+First run on a B200 at the start of round 2 (gpurun_out/round2_bringup.log: raw accumulators match the assumed TMEM
+layout, 6/6 parity tests green); format 2 is now the default database format and these tests run with every `-m gpu`."""
 import numpy as np
 import pytest
 
 import oracle_lib as O
 from test_gpu_parity import setup_case, SEED_DB, Q0, Q1
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200PIR_TEST_TC5") != "1",
-                                 reason="tcgen05 path not yet validated on hardware (set B200PIR_TEST_TC5=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("name", ["T", "T1", "T0"])
 def test_tc5_multiply_matches_oracle(name):
     S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
     tdb = S.Database.from_words(G, db, fmt=2)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     rng = np.random.default_rng(21)
     v = (rng.integers(0, Q0, P.dim0 * 2 * P.N, dtype=np.uint64)
          | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
@@ -37,7 +32,7 @@ def test_tc5_multiply_matches_oracle(name):
 def test_tc5_process_query_batches():
     S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
     tdb = S.Database.from_words(G, db, fmt=2)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     idxs = [0, 3, P.dim0 * P.num_per - 1, 17, 5, 9, 2, 11, 1, 30, 6, 7, 64, 100, 250, 12, 99, 180, 201]     # 16 + 3
     qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
     out = S.process_query_batch(G, gpp, qs, tdb)
@@ -55,12 +50,12 @@ def test_tc5_synthetic_and_upsert_equal_bulk_upload():
          | (rng.integers(0, Q1, P.dim0 * 2 * P.N, dtype=np.uint64) << np.uint64(32)))
     t2 = S.Database(G, fmt=2)
     t2.fill_synthetic(SEED_DB)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     assert np.array_equal(S.multiply_reg_by_database(G, t2, P.slices - 1, v), S.multiply_reg_by_database(G, gdb, P.slices - 1, v))
     slice_words = P.dim0 * P.num_per * P.N
     sl = db[:slice_words].reshape(P.N, P.num_per, P.dim0)
     t3 = S.Database(G, fmt=2)
-    G.set_option("db_format", 0)
+    G.set_option("db_format", -1)
     items = [0, 5, P.dim0 * P.num_per - 1, 33 % (P.dim0 * P.num_per)]
     sparse = np.zeros_like(sl)
     for it in items:
