@@ -4,6 +4,7 @@
 // point either runs on the GPU or returns an error.
 #include "../../include/b200pir.h"
 #include "kernels.h"
+#include "ntt_tables.hpp"
 #include <cstdio>
 #include <algorithm>
 #include <cmath>
@@ -36,62 +37,8 @@ namespace {
 
 thread_local std::string g_last_error;
 
-// ---------------------------------------------------------------- host-side number theory
-// (independent re-derivation of Params::init, params.rs:224-296; the oracle is never linked here)
-typedef unsigned __int128 u128;
-uint64_t mulmod(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)((u128)a * b % m); }
-uint64_t powmod(uint64_t a, uint64_t e, uint64_t m) {
-  uint64_t r = 1 % m;
-  a %= m;
-  while (e) { if (e & 1) r = mulmod(r, a, m); a = mulmod(a, a, m); e >>= 1; }
-  return r;
-}
-uint64_t invmod(uint64_t a, uint64_t m) {    // m prime or gcd(a,m)=1
-  __int128 r0 = a % m, r1 = m, s0 = 1, s1 = 0;
-  while (r1 != 0) { __int128 q = r0 / r1, t = r0 - q * r1; r0 = r1; r1 = t; t = s0 - q * s1; s0 = s1; s1 = t; }
-  if (r0 != 1) throw Error(B200PIR_E_BADARG, "invmod: not invertible");
-  s0 %= (__int128)m;
-  if (s0 < 0) s0 += m;
-  return (uint64_t)s0;
-}
-unsigned bitrev(unsigned x, int bits) {
-  unsigned r = 0;
-  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
-  return r;
-}
-// minimal primitive 2N-th root (number_theory.rs:14-55)
-uint64_t min_primitive_root(uint64_t degree, uint64_t q) {
-  if ((q - 1) % degree) throw Error(B200PIR_E_BADARG, "modulus is not NTT friendly");
-  uint64_t quot = (q - 1) / degree, root = 0;
-  for (uint64_t c = 2; c < 4096; c++) {
-    uint64_t r = powmod(c, quot, q);
-    if (powmod(r, degree / 2, q) == q - 1) { root = r; break; }
-  }
-  if (!root) throw Error(B200PIR_E_BADARG, "no primitive root found");
-  uint64_t gsq = mulmod(root, root, q), cur = root, best = root;
-  for (uint64_t i = 0; i < degree; i++) { if (cur < best) best = cur; cur = mulmod(cur, gsq, q); }
-  return best;
-}
-// tables of ntt.rs:39-65 as (W, W') pairs
-void build_tables(uint64_t q, std::vector<Twiddle>& fwd, std::vector<Twiddle>& inv, int N = NTT_N, int LG = NTT_LOG_N) {
-  uint64_t root = min_primitive_root(2 * N, q), iroot = invmod(root, q);
-  fwd.assign(N, Twiddle{0, 0});
-  inv.assign(N, Twiddle{0, 0});
-  auto fill = [&](std::vector<Twiddle>& t, uint64_t r, bool halve) {
-    uint64_t power = r;
-    std::vector<uint64_t> v(N, 0);
-    for (int i = 1; i < N; i++) { v[bitrev(i, LG)] = power; power = mulmod(power, r, q); }
-    v[0] = 1;
-    for (int i = 0; i < N; i++) {
-      uint64_t w = v[i];
-      if (halve) w = (w & 1) ? (w + q) >> 1 : w >> 1;          // div2_uint_mod, arith.rs:78-89
-      t[i].w = (uint32_t)w;
-      t[i].wp = (uint32_t)((w << 32) / q);                      // scale_powers_u32, ntt.rs:29-37
-    }
-  };
-  fill(fwd, root, false);
-  fill(inv, iroot, true);
-}
+using b200pir::tables::build_tables;
+using b200pir::tables::invmod;
 uint64_t log2_ceil_u64(uint64_t a) { return (uint64_t)std::ceil(std::log2((double)a)); }
 int bits_per(int t) {                        // gadget.rs:3-9 with modulus_log2 = 56
   if (t == 56) return 1;
@@ -138,7 +85,7 @@ struct b200pir_ctx {
   uint64_t q2, q1, setup_bytes, query_bytes, response_bytes;
   int q1_bits;
   DevParams dp;
-  DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1
+  DevBuf<Twiddle> d_tw;      // fwd0, inv0, fwd1, inv1, inv_lz0, inv_lz1
   DevBuf<Twiddle> d_tw4k;    // same for poly_len 4096 (config #5 sweep), built on first use
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
@@ -515,7 +462,8 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
   if (hp.version > 1) throw Error(B200PIR_E_BADARG, "unknown version");
   if (hp.p < 2 || (hp.p & (hp.p - 1)) || hp.p > (1u << 20)) throw Error(B200PIR_E_BADARG, "p must be a power of two <= 2^20");
   for (uint64_t t : {hp.t_gsw, hp.t_conv, hp.t_exp_left, hp.t_exp_right})
-    if (t < 2 || t > 56) throw Error(B200PIR_E_UNSUPPORTED, "gadget dimensions must be in 2..56");
+    if (t < 3 || t > 56)   // t = 2 would mean 29-bit digits: above q, outside the transforms' input range (and no parameter
+      throw Error(B200PIR_E_UNSUPPORTED, "gadget dimensions must be in 3..56");   // set of the reference uses it)
   if (hp.db_item_size == 0) hp.db_item_size = hp.instances * hp.n * hp.n * 2048 * log2_ceil_u64(hp.p) / 8;
   c->dim0 = 1 << hp.nu_1;
   c->num_per = 1 << hp.nu_2;
@@ -552,15 +500,20 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
   std::vector<Twiddle> f0, i0, f1, i1;
   build_tables(q0, f0, i0);
   build_tables(q1m, f1, i1);
-  c->d_tw.alloc(4 * POLY);
+  std::vector<Twiddle> l0, l1;                                     // relaxed-range inverse tables (ntt_core.cuh "lz")
+  b200pir::tables::build_inverse_table_lz(q0, l0);
+  b200pir::tables::build_inverse_table_lz(q1m, l1);
+  c->d_tw.alloc(6 * POLY);
+  B200_CUDA(cudaMemcpy(c->d_tw.p + 4 * POLY, l0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(c->d_tw.p + 5 * POLY, l1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p, f0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p + POLY, i0.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p + 2 * POLY, f1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(c->d_tw.p + 3 * POLY, i1.data(), POLY * sizeof(Twiddle), cudaMemcpyHostToDevice));
   {
-    std::vector<Twiddle> lo(2 * 2 * 64);
-    for (int i = 0; i < 64; i++) { lo[(0 * 2 + 0) * 64 + i] = f0[i]; lo[(0 * 2 + 1) * 64 + i] = i0[i];
-                                   lo[(1 * 2 + 0) * 64 + i] = f1[i]; lo[(1 * 2 + 1) * 64 + i] = i1[i]; }
+    std::vector<Twiddle> lo(2 * 3 * 64);                           // [n][forward, inverse, relaxed-range inverse][64]
+    for (int i = 0; i < 64; i++) { lo[(0 * 3 + 0) * 64 + i] = f0[i]; lo[(0 * 3 + 1) * 64 + i] = i0[i]; lo[(0 * 3 + 2) * 64 + i] = l0[i];
+                                   lo[(1 * 3 + 0) * 64 + i] = f1[i]; lo[(1 * 3 + 1) * 64 + i] = i1[i]; lo[(1 * 3 + 2) * 64 + i] = l1[i]; }
     upload_poly_constants(lo.data());
     upload_mul_constants(lo.data());
     upload_imma_constants(lo.data());
@@ -573,6 +526,8 @@ int b200pir_ctx_create(const b200pir_params* params, int device, b200pir_ctx** o
   dp.cr1_mod = (uint64_t)(((u128)1 << 64) / dp.modulus);
   dp.q1_inv_mod_q0 = (uint32_t)invmod(q1m % q0, q0);
   dp.fwd[0] = c->d_tw.p; dp.inv[0] = c->d_tw.p + POLY; dp.fwd[1] = c->d_tw.p + 2 * POLY; dp.inv[1] = c->d_tw.p + 3 * POLY;
+  dp.inv_lz[0] = c->d_tw.p + 4 * POLY; dp.inv_lz[1] = c->d_tw.p + 5 * POLY;
+  dp.mu58[0] = (uint32_t)(((uint64_t)1 << 58) / q0); dp.mu58[1] = (uint32_t)(((uint64_t)1 << 58) / q1m);
   // v_neg1 (params.rs:98-107): NTT of -(X^{N - 2^i})
   {
     std::vector<uint32_t> h((size_t)NTT_LOG_N * 2 * POLY, 0);

@@ -19,6 +19,8 @@ struct DevParams {
   uint32_t q1_inv_mod_q0;      // Garner constant for the CRT lift
   const Twiddle* fwd[2];       // [n] -> 2048 (W, W') forward, bit-reversed table order (ntt.rs:39-65)
   const Twiddle* inv[2];       // inverse (pre-halved) tables
+  const Twiddle* inv_lz[2];    // inverse tables of the relaxed-range transform (un-halved, 1/N in the last stage; ntt_tables.hpp)
+  uint32_t mu58[2];            // floor(2^58 / q_n): 32-bit Barrett for values < 2^57 (barrett57)
 };
 
 // x mod q for any 64-bit x  (== arith.rs:122-134 barrett_raw_u64)
@@ -27,6 +29,14 @@ __device__ __forceinline__ uint32_t barrett64(uint64_t x, uint64_t cr1, uint32_t
   uint64_t r = x - t * (uint64_t)q;
   uint32_t r32 = (uint32_t)r;                 // r < 2q < 2^32
   return ntt_min(r32, r32 - q);
+}
+// x mod q for x < 2^57 (2^27 < q < 2^28) with 32-bit operations: the quotient estimate floor((x >> 26) mu / 2^32), mu =
+// floor(2^58 / q), is the true quotient or one less (x / 2^58 + 2^26 / q < 1), so the remainder estimate lies in [0, 2q)
+// and its low 32 bits suffice.  One IMAD.HI + one IMAD instead of a 64 x 64 -> high multiply.
+__device__ __forceinline__ uint32_t barrett57(uint64_t x, uint32_t mu, uint32_t q) {
+  const uint32_t qh = __umulhi((uint32_t)(x >> 26), mu);
+  const uint32_t r = (uint32_t)x - qh * q;
+  return ntt_min(r, r - q);
 }
 // x mod q (56-bit q) for any 64-bit x
 __device__ __forceinline__ uint64_t barrett64_big(uint64_t x, uint64_t cr1, uint64_t q) {
@@ -43,7 +53,7 @@ __device__ __forceinline__ uint32_t addmod(uint32_t a, uint32_t b, uint32_t q) {
 // representative), computed with Garner's formula instead of the 128-bit Barrett.
 __device__ __forceinline__ uint64_t crt_compose(uint32_t x, uint32_t y, const DevParams& P) {
   uint32_t d = x >= y ? x - y : x + P.q[0] - y;          // y < q1 < q0
-  uint32_t m = barrett64((uint64_t)d * P.q1_inv_mod_q0, P.cr1[0], P.q[0]);
+  uint32_t m = barrett57((uint64_t)d * P.q1_inv_mod_q0, P.mu58[0], P.q[0]);       // d, q1^-1 < q0 < 2^28: product < 2^56
   return (uint64_t)y + (uint64_t)P.q[1] * m;
 }
 // gadget digit k of a raw coefficient (gadget.rs:34-60)

@@ -335,7 +335,7 @@ k_multiply_imma8(DevParams P, ImmaGeom F, const uint4* __restrict__ dbf, const u
   cp_async_wait<0>();
 }
 
-__constant__ Twiddle c_tw_lo_imma[2][2][64];
+__constant__ Twiddle c_tw_lo_imma[2][3][64];
 struct TwConstI {
   int n, dir;
   __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_imma[n][dir][i]; }
@@ -378,7 +378,7 @@ k_intt_from_zmajor(DevParams P, ImmaGeom F, const uint32_t* __restrict__ in_zm, 
   uint32_t x[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) x[k] = __ldg(src + (size_t)(tid * 8 + k) * F.rows * 2);
-  ntt_inverse_group(tid, x, sm, TwConstI{n, 1}, TwGlobalI{n ? P.inv[1] : P.inv[0]}, q, SyncI());
+  ntt_inverse_group_nh(tid, x, sm, TwConstI{n, 2}, TwGlobalI{n ? P.inv_lz[1] : P.inv_lz[0]}, q, SyncI());
   uint32_t* dst = out + ((((size_t)qs * F.rows + ii) * 2 + r) * 2 + n) * POLY;
 #pragma unroll
   for (int a = 0; a < 8; a++) dst[a * 256 + tid] = x[a];
@@ -419,8 +419,8 @@ k_intt_from_zmajor_tiled(DevParams P, ImmaGeom F, const uint32_t* __restrict__ i
     for (int p = 0; p < PP; p++) polybuf[p * POLY + z] = v[p];
   }
   __syncthreads();
-  const TwConstI lo{n, 1};
-  const TwGlobalI hi{n ? P.inv[1] : P.inv[0]};
+  const TwConstI lo{n, 2};                               // relaxed-range inverse (ntt_core.cuh "lz"): inputs are canonical residues
+  const TwGlobalI hi{n ? P.inv_lz[1] : P.inv_lz[0]};
 #pragma unroll 1
   for (int p = 0; p < PP; p += 2) {
     uint32_t x0[8], x1[8];
@@ -429,7 +429,7 @@ k_intt_from_zmajor_tiled(DevParams P, ImmaGeom F, const uint32_t* __restrict__ i
       x0[k] = polybuf[p * POLY + tid * 8 + k];
       x1[k] = polybuf[(p + 1) * POLY + tid * 8 + k];
     }
-    ntt_inverse_group2(tid, x0, x1, sm0, sm1, lo, hi, q, SyncI());
+    ntt_inverse_group2_nh(tid, x0, x1, sm0, sm1, lo, hi, q, SyncI());
     const int f0 = p0 + p, f1 = p0 + p + 1;               // flattened (row, ct_row)
     uint32_t* d0 = out + ((((size_t)qs * F.rows + (f0 >> 1)) * 2 + (f0 & 1)) * 2 + n) * POLY;
     uint32_t* d1 = out + ((((size_t)qs * F.rows + (f1 >> 1)) * 2 + (f1 & 1)) * 2 + n) * POLY;
@@ -456,7 +456,7 @@ inline unsigned grid1d(size_t total, int block) { return (unsigned)((total + blo
 }  // namespace
 
 void upload_imma_constants(const Twiddle* lo) {
-  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_imma, lo, sizeof(Twiddle) * 2 * 2 * 64));
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_imma, lo, sizeof(Twiddle) * 2 * 3 * 64));
 }
 size_t imma_db_cells(const ImmaGeom& F, int slices) {
   return (size_t)slices * 2 * POLY * F.mt * F.ks * 4 * 32;

@@ -45,8 +45,8 @@ void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, 
 void launch_raw_to_res(const DevParams& P, uint32_t* out, const uint64_t* raw, size_t polys, cudaStream_t s);
 void launch_res_to_raw(const DevParams& P, uint64_t* out, const uint32_t* res, size_t polys, cudaStream_t s);
 // twiddle entries 0..63 of every (modulus, direction) -> constant bank of the poly kernels' module
-void upload_poly_constants(const Twiddle* lo /* [2][2][64] */);
-void upload_mul_constants(const Twiddle* lo /* [2][2][64] */);
+void upload_poly_constants(const Twiddle* lo /* [2][3][64]: forward, inverse, relaxed-range inverse */);
+void upload_mul_constants(const Twiddle* lo /* [2][3][64]: forward, inverse, relaxed-range inverse */);
 // format converters for the C ABI (u64 [n][z] words < 2^32  <->  ntt32)
 void launch_widen(uint64_t* out, const uint32_t* in, size_t words, cudaStream_t s);
 void launch_narrow(uint32_t* out, const uint64_t* in, size_t words, cudaStream_t s);

@@ -19,7 +19,7 @@ namespace b200pir {
 
 namespace {
 
-__constant__ Twiddle c_tw_lo_mul[2][2][64];
+__constant__ Twiddle c_tw_lo_mul[2][3][64];
 struct TwConstM {
   int n, dir;
   __device__ __forceinline__ Twiddle operator()(int i) const { return c_tw_lo_mul[n][dir][i]; }
@@ -196,7 +196,7 @@ k_db_synth(DevParams P, MulGeom G, Shard sh, uint4* db, uint64_t seed, uint64_t 
       uint64_t v = splitmix64_at(seed, base + a * 256 + tid) % pt;
       x[a] = (v > pt / 2) ? (uint32_t)(q - (uint32_t)(pt - v)) : (uint32_t)v;     // recenter_mod, then mod q_n
     }
-    ntt_forward_group(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());
+    ntt_forward_group_lz<NTT_OUT_CANON>(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());   // inputs canonical
 #pragma unroll
     for (int k = 0; k < 8; k++) cell[(tid * 8 + k) * 4 + jb * 2 + n] = x[k];
   }
@@ -223,7 +223,7 @@ k_item_from_bytes(DevParams P, const uint8_t* __restrict__ bucket, int pt_len, u
     const uint64_t v = i < pt_len ? (uint64_t)src[i] : 0;
     x[a] = (v > pt / 2) ? (uint32_t)(q - (uint32_t)(pt - v)) : (uint32_t)v;       // recenter_mod, then mod q_n
   }
-  ntt_forward_group(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());
+  ntt_forward_group_lz<NTT_OUT_CANON>(tid, x, ntt_smem + n * NTT_SMEM_WORDS, TwConstM{n, 0}, TwGlobalM{n ? P.fwd[1] : P.fwd[0]}, q, S());   // inputs canonical
 #pragma unroll
   for (int k = 0; k < 8; k++) halves[n][tid * 8 + k] = x[k];
   __syncthreads();
@@ -387,7 +387,7 @@ void launch_dpir_transpose_expand(uint32_t* out, const uint32_t* a, size_t rows,
                                                                            out_rows, out_cols);
 }
 void upload_mul_constants(const Twiddle* lo) {
-  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_mul, lo, sizeof(Twiddle) * 2 * 2 * 64));
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo_mul, lo, sizeof(Twiddle) * 2 * 3 * 64));
 }
 void launch_multiply(const DevParams& P, const MulGeom& G, const uint4* db_dev, const uint4* q_dev, uint32_t* out,
                      int slice_begin, int slice_count, int nq, size_t q_stride, size_t out_stride, int variant,

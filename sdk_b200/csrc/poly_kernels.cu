@@ -19,7 +19,7 @@ constexpr int HI_TW = NTT_N - 64;       // twiddle table entries 64..2047 (passe
 
 // Table entries 0..63 (passes A and B) of every (modulus, direction) live in the constant bank: the
 // index is thread-uniform (pass A) or warp-uniform (pass B), so they cost no load/store-unit traffic.
-__constant__ Twiddle c_tw_lo[2][2][64];     // [n][0 = forward, 1 = inverse][index]
+__constant__ Twiddle c_tw_lo[2][3][64];     // [n][0 = forward, 1 = inverse][index]
 
 struct TwConst {
   int n, dir;
@@ -64,6 +64,7 @@ struct Grp {
   uint64_t cr1;
   const Twiddle* fwd;   // global tables
   const Twiddle* inv;
+  const Twiddle* inv_lz; // relaxed-range inverse table (ntt_core.cuh "lz")
   uint32_t* smem;       // this group's NTT exchange buffer (NTT_SMEM_WORDS)
   uint32_t* smem2;      // second buffer for paired transforms (null when the kernel has none)
   const Twiddle* fwd_hi_sm;   // shared copy of fwd[64..], or null
@@ -81,6 +82,7 @@ __device__ __forceinline__ Grp make_grp(const DevParams& P, uint32_t* ntt_smem) 
   g.cr1 = g.n ? P.cr1[1] : P.cr1[0];
   g.fwd = g.n ? P.fwd[1] : P.fwd[0];
   g.inv = g.n ? P.inv[1] : P.inv[0];
+  g.inv_lz = g.n ? P.inv_lz[1] : P.inv_lz[0];
   g.smem = ntt_smem + g.n * NTT_SMEM_WORDS;
   g.smem2 = nullptr;
   g.fwd_hi_sm = nullptr;
@@ -95,6 +97,7 @@ __device__ __forceinline__ Grp make_grp_single(const DevParams& P, uint32_t* ntt
   g.cr1 = n ? P.cr1[1] : P.cr1[0];
   g.fwd = n ? P.fwd[1] : P.fwd[0];
   g.inv = n ? P.inv[1] : P.inv[0];
+  g.inv_lz = n ? P.inv_lz[1] : P.inv_lz[0];
   g.smem = ntt_smem;
   g.smem2 = nullptr;
   g.fwd_hi_sm = nullptr;
@@ -109,13 +112,15 @@ __device__ __forceinline__ void stage_fwd_twiddles(Grp& g, Twiddle* dst) {
   g.fwd_hi_sm = dst;
 }
 // SM = true: the kernel staged the forward hi-table with stage_fwd_twiddles()
+// canonical forward transform of inputs < 4q (the old per-butterfly-corrected transform's input contract, which
+// to_ntt_no_reduce's callers rely on), canonical inverse transform of inputs < 2q: relaxed-range versions (ntt_core.cuh "lz")
 template <bool SM>
 __device__ __forceinline__ void grp_ntt_fwd(const Grp& g, uint32_t (&x)[8]) {
-  if (SM) ntt_forward_group(g.tid, x, g.smem, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
-  else ntt_forward_group(g.tid, x, g.smem, TwConst{g.n, 0}, TwGlobal{g.fwd}, g.q, CtaSync());
+  if (SM) ntt_forward_group_lz<NTT_OUT_CANON, true>(g.tid, x, g.smem, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+  else ntt_forward_group_lz<NTT_OUT_CANON, true>(g.tid, x, g.smem, TwConst{g.n, 0}, TwGlobal{g.fwd}, g.q, CtaSync());
 }
 __device__ __forceinline__ void grp_ntt_inv(const Grp& g, uint32_t (&x)[8]) {
-  ntt_inverse_group(g.tid, x, g.smem, TwConst{g.n, 1}, TwGlobal{g.inv}, g.q, CtaSync());
+  ntt_inverse_group_nh(g.tid, x, g.smem, TwConst{g.n, 2}, TwGlobal{g.inv_lz}, g.q, CtaSync());
 }
 
 // contiguous-layout load/store of 8 ntt32 words (two 16-byte accesses)
@@ -140,9 +145,18 @@ __device__ __forceinline__ void acc_reduce(uint64_t (&acc)[ROWS][8], const Grp& 
     for (int k = 0; k < 8; k++) acc[r][k] = barrett64(acc[r][k], g.cr1, g.q);
 }
 
+// digit k of a raw coefficient; bits == 8 (the common t = 8): digit k is byte k, and since the values are <= q < 2^56 byte 7
+// is a zero byte to fill the upper three bytes with — one PRMT instead of two funnel shifts and a mask
+__device__ __forceinline__ uint32_t gadget_digit_fast(uint64_t v, int k, int bits, uint64_t mask) {
+  if (bits == 8) return __byte_perm((uint32_t)v, (uint32_t)(v >> 32), 0x7770u | (uint32_t)k);
+  return gadget_digit(v, k, bits, mask);
+}
+
 // acc[r][.] += sum_k  C[r][col0 + k*col_step] (.) NTT(digit_k(v))     (pointwise, this group's modulus)
 // v[a] = raw coefficient at index a*256 + tid (strided layout).  c0 points at element (row 0, first
 // column) of this group's modulus, offset by tid*8.  `cnt` counts products held per accumulator.
+// Relaxed-range forward transforms (ntt_core.cuh "lz"): digits are < 2^19 < 2q (gadget dimensions >= 3), the outputs
+// (< 16q < 2^32) go straight into the 64-bit accumulators: products < 2^60, at most 16 per accumulator between reductions.
 template <int ROWS, bool SM>
 __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
                                            int bits, const uint32_t* c0, size_t col_step, size_t row_step,
@@ -157,11 +171,12 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
       uint32_t x0[8], x1[8];
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        x0[a] = gadget_digit(v[a], k, bits, mask);
-        x1[a] = gadget_digit(v[a], k + 1, bits, mask);
+        x0[a] = gadget_digit_fast(v[a], k, bits, mask);
+        x1[a] = gadget_digit_fast(v[a], k + 1, bits, mask);
       }
-      // lazy outputs (< 4q < 2^30): products < 2^58, so at most 63 of them fit one 64-bit accumulator
-      ntt_forward_group2<false>(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+      ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+      if (cnt + 2 > 16) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+      cnt += 2;
       const uint32_t* c = c0 + (size_t)k * col_step;
 #pragma unroll
       for (int r = 0; r < ROWS; r++) {
@@ -173,16 +188,17 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
 #pragma unroll
         for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
       }
-      cnt += 2;
-      if (cnt >= 60) { acc_reduce<ROWS>(acc, g); cnt = 1; }
     }
   }
 #pragma unroll 1
   for (; k < ndig; k++) {
     uint32_t x[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) x[a] = gadget_digit(v[a], k, bits, mask);
-    grp_ntt_fwd<SM>(g, x);
+    for (int a = 0; a < 8; a++) x[a] = gadget_digit_fast(v[a], k, bits, mask);
+    if (SM) ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x, g.smem, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
+    else ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x, g.smem, TwConst{g.n, 0}, TwGlobal{g.fwd}, g.q, CtaSync());
+    if (cnt + 1 > 16) { acc_reduce<ROWS>(acc, g); cnt = 1; }
+    cnt += 1;
     const uint32_t* c = c0 + (size_t)k * col_step;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
@@ -191,7 +207,6 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
 #pragma unroll
       for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x[e] * cv[e];
     }
-    if (++cnt >= 60) { acc_reduce<ROWS>(acc, g); cnt = 1; }
   }
 }
 
@@ -486,6 +501,129 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
     y1[e] = barrett64(acc[1][e], g.cr1, q);
   }
   ntt_inverse_group2(g.tid, y0, y1, sm0, sm1, TwConst{g.n, 1}, TwGlobal{g.inv}, q, CtaSync());
+  uint32_t* co = out + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int z = a * 256 + g.tid;
+    co[(0 * 2 + g.n) * POLY + z] = addmod(y0[a], __ldg(ci + (0 * 2 + g.n) * POLY + z), q);
+    co[(1 * 2 + g.n) * POLY + z] = addmod(y1[a], __ldg(ci + (1 * 2 + g.n) * POLY + z), q);
+  }
+}
+
+// Digit k of vh minus digit k of vi, offset by q: in (q - 2^bits, q + 2^bits), a subset of [0, 2q) for bits <= 27 (the
+// context rejects gadget dimensions below 3, so bits <= 19) — the relaxed-range forward transform needs no more.
+// BYTE: bits == 8, where digit k is simply byte k; the values are < 2^56, so byte 7 serves as the zero filler.
+template <bool BYTE>
+__device__ __forceinline__ uint32_t digit_diff(uint64_t vh, uint64_t vi, int k, int bits, uint64_t mask, uint32_t q) {
+  if (BYTE) {
+    const uint32_t sel = 0x7770u | (uint32_t)k;
+    return __byte_perm((uint32_t)vh, (uint32_t)(vh >> 32), sel) - __byte_perm((uint32_t)vi, (uint32_t)(vi >> 32), sel) + q;
+  }
+  return gadget_digit(vh, k, bits, mask) - gadget_digit(vi, k, bits, mask) + q;
+}
+
+// Same step as k_fold_res on the relaxed-range transforms (ntt_core.cuh "lz"): no per-butterfly range correction in the
+// forward transforms (outputs < 16q feed the 64-bit multiply-accumulate directly: 16 products of < 2^32 x < 2^28 fit),
+// no halving in the inverse transform, byte-permute digit extraction when bits_per = 8, 32-bit Barrett in the CRT lift.
+template <int MINB, bool BYTE>
+__global__ void __launch_bounds__(256, MINB)
+k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
+              const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
+              const uint32_t* __restrict__ zero_flags /* null, or [batch][2*half]: 1 = ciphertext is all zero */) {
+  if (zero_flags) {            // lib/server/src/compute/fold.rs:37-43, see k_fold_res
+    const int bz = blockIdx.x / half, iz = blockIdx.x % half;
+    const uint32_t fa = zero_flags[(size_t)bz * 2 * half + iz], fb = zero_flags[(size_t)bz * 2 * half + half + iz];
+    if (fa | fb) {
+      const uint32_t* src = in + (size_t)bz * batch_stride + (size_t)((fa ? half : 0) + iz) * 4 * POLY;
+      uint32_t* dst = out + (size_t)bz * batch_stride + (size_t)iz * 4 * POLY;
+#pragma unroll
+      for (int rho = 0; rho < 2; rho++) {
+        uint32_t x[8];
+        ld8_ro(x, src + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8);
+        st8(dst + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8, x);
+      }
+      return;
+    }
+  }
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* sm0 = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
+  Twiddle* tw = reinterpret_cast<Twiddle*>(sm1 + NTT_SMEM_WORDS);
+  Grp g = make_grp_single(P, sm0, blockIdx.y);
+  stage_fwd_twiddles(g, tw);
+  const TwConst lo{g.n, 0};
+  const TwShared hi{tw};
+  const int b = blockIdx.x / half, i = blockIdx.x % half;
+  const uint32_t* ci = in + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
+  const uint32_t* ch = in + (size_t)b * batch_stride + (size_t)(half + i) * 4 * POLY;
+  const uint32_t* C = c_pos + (size_t)(b / slices_per_query) * c_batch_stride;
+  const int cols = 2 * t_gsw;
+  const size_t row_step = (size_t)cols * 2 * POLY;
+  const uint64_t mask = (1ull << bits) - 1;
+  const uint32_t q = g.q;
+
+  uint64_t acc[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[r][e] = 0;
+  int cnt = 0;                                   // products (< 2^60 each) held by every accumulator: at most 16
+#pragma unroll 1
+  for (int rho = 0; rho < 2; rho++) {
+    uint64_t vi[8], vh[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int z = a * 256 + g.tid;
+      vi[a] = crt_compose(__ldg(ci + (rho * 2 + 0) * POLY + z), __ldg(ci + (rho * 2 + 1) * POLY + z), P);
+      vh[a] = crt_compose(__ldg(ch + (rho * 2 + 0) * POLY + z), __ldg(ch + (rho * 2 + 1) * POLY + z), P);
+    }
+    const uint32_t* c0 = C + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;       // key-matrix column of digit k: rho + 2k
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < t_gsw; k += 2) {
+      uint32_t x0[8], x1[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
+        x1[a] = digit_diff<BYTE>(vh[a], vi[a], k + 1, bits, mask, q);
+      }
+      ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
+      if (cnt + 2 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
+      cnt += 2;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        uint32_t cv[8];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)(k + 1) * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
+      }
+    }
+    if (k < t_gsw) {                            // odd t_gsw: last digit alone
+      uint32_t x0[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
+      ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, hi, q, CtaSync());
+      if (cnt + 1 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
+      cnt += 1;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        uint32_t cv[8];
+        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
+      }
+    }
+  }
+  uint32_t y0[8], y1[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    y0[e] = barrett64(acc[0][e], g.cr1, q);
+    y1[e] = barrett64(acc[1][e], g.cr1, q);
+  }
+  ntt_inverse_group2_nh(g.tid, y0, y1, sm0, sm1, TwConst{g.n, 2}, TwGlobal{g.inv_lz}, q, CtaSync());
   uint32_t* co = out + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
 #pragma unroll
   for (int a = 0; a < 8; a++) {
@@ -1134,8 +1272,8 @@ const size_t kDynSmemFold = (size_t)(2 * NTT_SMEM_WORDS) * 4 + (size_t)HI_TW * 8
 
 }  // namespace
 
-void upload_poly_constants(const Twiddle* lo /* [2][2][64] */) {
-  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo, lo, sizeof(Twiddle) * 2 * 2 * 64));
+void upload_poly_constants(const Twiddle* lo /* [2][3][64]: forward, inverse, relaxed-range inverse */) {
+  B200_CUDA(cudaMemcpyToSymbol(c_tw_lo, lo, sizeof(Twiddle) * 2 * 3 * 64));
 }
 void launch_ntt_u64(const DevParams& P, uint64_t* polys, size_t count, bool inverse, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_ntt_u64<<<dim3((unsigned)count, 2), 256, 0, s>>>(P, polys, inverse ? 1 : 0);
@@ -1171,6 +1309,20 @@ void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size
     k_ct_zero_flags<<<(unsigned)(batch * 2 * half), 256, 0, s>>>(in, batch_stride, 2 * half, zero_flags);
   }
   ++g_kernel_launches;
+  // variant 2 (default): relaxed-range transforms, 3 CTAs per SM; 3: the same at 2 CTAs per SM
+  if (variant == 2 || variant == 3) {
+    const dim3 grid((unsigned)(batch * half), 2);
+#define FOLD_LZ(MINB, BYTE)                                                                                             \
+    do {                                                                                                                \
+      opt_in_smem(k_fold_res_lz<MINB, BYTE>, (int)kDynSmemFold);                                                        \
+      k_fold_res_lz<MINB, BYTE><<<grid, 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos, c_batch_stride,  \
+                                                               slices_per_query, t_gsw, bits, zero_flags);             \
+    } while (0)
+    if (variant == 2) { if (bits == 8) FOLD_LZ(3, true); else FOLD_LZ(3, false); }
+    else { if (bits == 8) FOLD_LZ(2, true); else FOLD_LZ(2, false); }
+#undef FOLD_LZ
+    return;
+  }
   // variant 1: 3 CTAs per SM (80 registers, a few spills) instead of 2 (128 registers)
   if (variant == 1)
     k_fold_res<3><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,

@@ -37,9 +37,7 @@ namespace b200pir {
 
 namespace {
 
-constexpr int TC5_KS_PER_STAGE = 4;                     // k-steps per A stage
-constexpr int TC5_STAGE_BYTES = TC5_KS_PER_STAGE * TC5_TILE;   // 16 KiB
-constexpr int TC5_STAGES = 6;                           // 96 KiB of database tiles in flight per SM
+constexpr int TC5_RING_BYTES = 96 * 1024;               // database tiles in flight per SM (ring of KSPS-k-step stages)
 constexpr int TC5_EPI_WARPS = 8;
 constexpr int TC5_THREADS = 64 + 32 * TC5_EPI_WARPS;    // producer warp, MMA warp, epilogue warps
 constexpr int TC5_TMEM_COLS = 256;                      // two accumulator buffers of 128 columns
@@ -180,18 +178,27 @@ k_query_to_tc5(Tc5Geom T, const uint4* __restrict__ q_dev, size_t q_stride, int 
 }
 
 // ---- the multiply -----------------------------------------------------------------------------------------------------
+constexpr int TC5_MAX_STAGES = 24;
 struct Tc5Smem {
-  uint64_t full[TC5_STAGES], empty[TC5_STAGES];
+  uint64_t full[TC5_MAX_STAGES], empty[TC5_MAX_STAGES];
   uint64_t bfull[2], bempty[2];
   uint64_t tfull[2], tempty[2];
   uint32_t tmem_base;
 };
 
 // out_zm[query][slice][n][z][row][ct_row] (u32), the format of k_multiply_imma
+// KSPS = k-steps (4 KiB tiles) per ring stage.  dbg_mode (bring-up / bottleneck analysis only, B200PIR_TC5_DBG): bit 0 = the MMA
+// thread releases every stage without issuing MMAs, bit 1 = the epilogue warps release the accumulators without reading them.
+template <int KSPS>
 __global__ void __launch_bounds__(TC5_THREADS, 1)
 k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const uint8_t* __restrict__ qt,
                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count,
-               uint32_t* __restrict__ dbg /* bring-up aid: raw accumulators of CTA 0's first TC5_DBG_TILES tiles, or null */) {
+               uint32_t* __restrict__ dbg /* bring-up aid: raw accumulators of CTA 0's first TC5_DBG_TILES tiles, or null */,
+               int dbg_mode) {
+  constexpr int TC5_KS_PER_STAGE = KSPS;
+  constexpr int TC5_STAGE_BYTES = KSPS * TC5_TILE;
+  constexpr int TC5_STAGES = TC5_RING_BYTES / TC5_STAGE_BYTES;
+  static_assert(TC5_STAGES <= TC5_MAX_STAGES, "ring too long");
   extern __shared__ __align__(1024) uint8_t tc5_smem[];
   uint8_t* smem_b = tc5_smem;                                         // [2][ks][4096]
   uint8_t* smem_a = smem_b + (size_t)2 * T.ks * TC5_TILE;             // [STAGES][16 KiB]
@@ -264,6 +271,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
             mbar_wait(&S->full[stage], sphase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
+            if (dbg_mode & 1) { mbar_arrive(&S->empty[stage]); if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; } continue; }
             for (int kk = 0; kk < ks_here; kk++) {
               const int ks = st * TC5_KS_PER_STAGE + kk;
               tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
@@ -271,9 +279,11 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
             tc_commit(&S->empty[stage]);                              // frees the A stage when these MMAs have completed
             if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
           }
-          tc_commit(&S->tfull[ab]);                                   // accumulator ready for the epilogue
+          if (dbg_mode & 1) mbar_arrive(&S->tfull[ab]);
+          else tc_commit(&S->tfull[ab]);                              // accumulator ready for the epilogue
         }
-        tc_commit(&S->bempty[bb]);                                    // every MMA reading this B buffer has completed
+        if (dbg_mode & 1) mbar_arrive(&S->bempty[bb]);
+        else tc_commit(&S->bempty[bb]);                               // every MMA reading this B buffer has completed
       }
     }
   } else {
@@ -293,7 +303,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
         const int ii = mt * 32 + tc5_lane_row(quad, lane);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * TC5_N;
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {                              // 32 TMEM columns = 8 GEMM columns = 4 queries
+        for (int ch = 0; ch < ((dbg_mode & 2) ? 0 : 2); ch++) {                              // 32 TMEM columns = 8 GEMM columns = 4 queries
           const int chunk = colhalf * 2 + ch;
           uint32_t v[32];
           tc_ld32(taddr + chunk * 32, v);
@@ -338,7 +348,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
 size_t tc5_db_bytes(const Tc5Geom& T, int slices) { return (size_t)slices * 2 * POLY * T.mt * T.ks * TC5_TILE; }
 size_t tc5_query_bytes(const Tc5Geom& T) { return (size_t)2 * POLY * T.ks * TC5_TILE; }
 static size_t tc5_smem_bytes(const Tc5Geom& T) {
-  return (size_t)2 * T.ks * TC5_TILE + (size_t)TC5_STAGES * TC5_STAGE_BYTES + sizeof(Tc5Smem) + 16;
+  return (size_t)2 * T.ks * TC5_TILE + (size_t)TC5_RING_BYTES + sizeof(Tc5Smem) + 16;
 }
 bool tc5_supported(const Tc5Geom& T) { return T.dim0 % 2 == 0 && tc5_smem_bytes(T) <= 227 * 1024; }
 
@@ -360,7 +370,6 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
   if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
   if (!tc5_supported(T)) throw Error(-2, "tcgen05 multiply: dim0 too large for one CTA's shared memory");
   const size_t smem = tc5_smem_bytes(T);
-  opt_in_smem(k_multiply_tc5, 227 * 1024);
   ++g_kernel_launches;
   const int grid = sm_count > 0 ? (sm_count < 2 * POLY ? sm_count : 2 * POLY) : 148;
   // bring-up aid (scripts/tc5_probe.py): B200PIR_TC5_DUMP=<file> receives the raw s32 accumulators D[M][N] of the first
@@ -372,7 +381,16 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
     B200_CUDA(cudaMalloc(&dbg, dbg_words * 4));
     B200_CUDA(cudaMemsetAsync(dbg, 0xFF, dbg_words * 4, s));
   }
-  k_multiply_tc5<<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count, dbg);
+  static const int dbg_mode = getenv("B200PIR_TC5_DBG") ? atoi(getenv("B200PIR_TC5_DBG")) : 0;     // analysis only: wrong results
+  static const int ksps = getenv("B200PIR_TC5_KSPS") ? atoi(getenv("B200PIR_TC5_KSPS")) : 4;
+#define TC5_LAUNCH(K)                                                                                                          \
+  do {                                                                                                                         \
+    opt_in_smem(k_multiply_tc5<K>, 227 * 1024);                                                                                \
+    k_multiply_tc5<K><<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count, dbg,   \
+                                                      dbg_mode);                                                               \
+  } while (0)
+  if (ksps == 1) TC5_LAUNCH(1); else if (ksps == 2) TC5_LAUNCH(2); else if (ksps == 8) TC5_LAUNCH(8); else TC5_LAUNCH(4);
+#undef TC5_LAUNCH
   if (dump) {
     std::vector<uint32_t> host(dbg_words);
     B200_CUDA(cudaStreamSynchronize(s));

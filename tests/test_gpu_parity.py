@@ -321,6 +321,10 @@ def test_error_behaviour():
         S.Params(device=99, **P.kw)
     with pytest.raises(S.B200PirError):
         S.Database.from_words(G, np.zeros(17, dtype=np.uint64))
+    # gadget dimension 2 = 29-bit digits, above q_n: outside the transforms' input range, rejected (no reference parameter set uses it)
+    with pytest.raises(S.B200PirError) as ei:
+        S.Params(**dict(P.kw, t_gsw=2))
+    assert ei.value.code == -4          # B200PIR_E_UNSUPPORTED
 
 
 # ------------------------------------------------------------------ DoublePIR
