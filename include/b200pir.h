@@ -55,7 +55,8 @@ int b200pir_ctx_synchronize(b200pir_ctx* ctx);
  * the IMAD layout uses at most 4), "db_format" (layout of databases created afterwards: -1 = automatic (default): 2 wherever the
  * tcgen05 kernel supports the geometry, else 1; 0 = IMAD, 1 = mma.sync INT8 fragments, 2 = tcgen05 tile images, tc5_kernels.cu), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
- * "expand_variant" (0 = default everywhere); "sparse_fold" (1 = fold like lib/server's sparse server,
+ * "expand_variant" (0 = default everywhere); "coalesce" (1 = default: concurrent single-query callers
+ * share database passes, see b200pir_coalesce_stats), "sparse_fold" (1 = fold like lib/server's sparse server,
  * compute/fold.rs:15-65: an all-zero ciphertext short-cuts the external product; 0 = spiral-rs's dense fold, default); "expand_pair_min_ctas" (expansion rounds with at least this many active
  * ciphertexts use the paired kernel, default 592);
  * unknown keys -> B200PIR_E_BADARG */
@@ -152,9 +153,22 @@ int b200pir_process_query(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, cons
 /* Query::deserialize (client.rs:303-315, expand_queries only): data = seed || row 1 of ct; query_ct: PolyMatrixRaw(2,1). */
 int b200pir_query_from_bytes(b200pir_ctx* ctx, const uint8_t* data, size_t len, uint64_t* query_ct);
 /* process_query on `count` serialized queries (count x query_bytes, back to back); out: count x response_bytes.
- * Replaces Query::deserialize + process_query as lib/server's /private-read handler chains them. */
+ * Replaces Query::deserialize + process_query as lib/server's /private-read handler chains them (bin/server.rs:99-141).
+ * Both branches of Query::deserialize (client.rs:303-329): expand_queries != 0 -> seed || row 1 of ct;
+ * expand_queries == 0 (direct upload) -> seed || the odd-indexed words of v_buf || rows 1 of the nu_2 v_ct matrices, the
+ * seed-derived halves being regenerated on the GPU.  (In direct-upload mode the handler's body is setup || query: pass the
+ * first setup_bytes to b200pir_pp_create_from_bytes and the rest here.) */
 int b200pir_process_query_bytes(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* pp, const uint8_t* queries, size_t len,
                                 size_t count, uint8_t* out, size_t* out_len_each);
+/* `count` queries of DIFFERENT clients in one database pass: pps[i] = the public parameters of the client that sent query_cts[i]
+ * (host PolyMatrixRaw(2,1) each; expand_queries only); outs[i] receives response_bytes bytes.  lib/server looks the parameters up
+ * per request (bin/server.rs:113-117); the kernels take them per query. */
+int b200pir_process_queries(b200pir_ctx* ctx, b200pir_db* db, b200pir_pp* const* pps, const uint64_t* const* query_cts,
+                            size_t count, uint8_t* const* outs);
+/* Concurrent callers: b200pir_process_query and single-query b200pir_process_query_bytes calls on one context are coalesced —
+ * requests that arrive while a batch is running are served together (up to 32) in one database pass by the next caller to
+ * find the GPU free; a lone caller is served at once.  Option "coalesce" = 0 restores strictly serial calls.  Counters: */
+int b200pir_coalesce_stats(b200pir_ctx* ctx, uint64_t* batches, uint64_t* queries);
 /* `count` queries of one client in one call; the database is streamed once per group of up to 4 (IMAD layout)
  * or 16 (INT8 tensor-core layout) queries.
  * queries: count x PolyMatrixRaw(2,1); out: count x response_bytes. */

@@ -363,12 +363,21 @@ int orc_client_pp_bytes(void* c, uint8_t* out, size_t* out_len) {
   *out_len = b.size();
   ORC_CATCH
 }
-int orc_client_query_bytes(void* c, uint8_t* out, size_t* out_len) {       // the last generated (expand-mode) query
+int orc_client_query_bytes(void* c, uint8_t* out, size_t* out_len) {       // Query::serialize of the last generated query
   ORC_TRY
   Client& cl = *(Client*)c;
-  std::vector<uint8_t> b = serialize_query(cl.p, cl.last_query_ct, cl.query_seed);
+  std::vector<uint8_t> b = cl.p.expand_queries ? serialize_query(cl.p, cl.last_query_ct, cl.query_seed)
+                                               : serialize_query_direct(cl.p, cl.last_query, cl.query_seed);
   std::memcpy(out, b.data(), b.size());
   *out_len = b.size();
+  ORC_CATCH
+}
+int orc_query_deserialize_direct(void* h, const uint8_t* data, size_t len, uint64_t* v_buf, uint64_t* v_ct) {
+  ORC_TRY
+  const Params& p = *(Params*)h;
+  Query q = deserialize_query_direct(p, data, len);
+  std::memcpy(v_buf, q.v_buf.data(), q.v_buf.size() * 8);
+  store_vec(v_ct, q.v_ct);
   ORC_CATCH
 }
 int orc_pp_deserialize(void* h, const uint8_t* data, size_t len, uint64_t* pack, uint64_t* left, uint64_t* right, uint64_t* conv) {

@@ -146,6 +146,7 @@ struct Client {
   uint8_t pp_seed[32], query_seed[32];
   PublicParameters last_pp;
   PolyMatrix last_query_ct;
+  Query last_query;             // the last generated query in full (direct-upload serialization needs v_buf / v_ct)
   Client(const Params& params, u64 seed)
       : p(params), sk_gsw(raw_zero(params, params.n, 1)), sk_reg(raw_zero(params, 1, 1)),
         dg(params.noise_width), rng(seed), seeder(seed ^ 0xA5A5A5A55A5A5A5AULL) {
@@ -317,6 +318,7 @@ struct Client {
         q.v_ct.push_back(from_ntt_alloc(p, ct_gsw));
       }
     }
+    last_query = q;
     return q;
   }
   // client.rs:732-810.  Returns the decoded (instances*n) x n plaintext matrix (mod p), i.e.
@@ -456,6 +458,48 @@ inline std::vector<uint8_t> serialize_query(const Params& p, const PolyMatrix& c
   std::vector<uint8_t> out(seed, seed + 32);
   ser_matrix_excl_first_row(out, p, ct);
   return out;
+}
+// direct upload (expand_queries == false), client.rs:279-301: seed || the odd-indexed words of v_buf (extract_excl_rng_data
+// :97-105: the even-indexed ones are regenerated from the seed) || rows 1.. of every v_ct matrix
+inline std::vector<uint8_t> serialize_query_direct(const Params& p, const Query& q, const uint8_t seed[32]) {
+  std::vector<uint8_t> out(seed, seed + 32);
+  for (size_t i = 1; i < q.v_buf.size(); i += 2) {
+    const uint8_t* w = reinterpret_cast<const uint8_t*>(&q.v_buf[i]);
+    out.insert(out.end(), w, w + 8);
+  }
+  for (auto& m : q.v_ct) ser_matrix_excl_first_row(out, p, m);
+  return out;
+}
+// client.rs:316-327 with interleave_rng_data (:107-131): for every first-dimension ciphertext the row 0 polynomial is
+// q - (rng % q) per coefficient (row 1 stays zero), transformed and reoriented; its packed words are the even-indexed words
+// of v_buf, the uploaded words the odd-indexed ones.  Then the v_ct matrices, first rows from the same stream.
+inline Query deserialize_query_direct(const Params& p, const uint8_t* data, size_t len) {
+  if (len != p.query_bytes()) throw std::runtime_error("query has the wrong length");
+  if (p.expand_queries) throw std::runtime_error("expansion-mode queries are handled by deserialize_query");
+  ChaCha20Rng rng(data);
+  const size_t num_expanded = (size_t)1 << p.db_dim_1, N = p.poly_len;
+  const size_t v_buf_words = num_expanded * N;                                              // query_v_buf_bytes / 8, params.rs:184-186
+  std::vector<PolyMatrix> reg_cts;
+  for (size_t j = 0; j < num_expanded; j++) {
+    PolyMatrix sigma = raw_zero(p, 2, 1);
+    for (size_t z = 0; z < N; z++) sigma.data[z] = p.modulus - (rng.next() % p.modulus);
+    reg_cts.push_back(to_ntt_alloc(p, sigma));
+  }
+  std::vector<u64> reg_buf(num_expanded * 2 * N, 0);
+  reorient_reg_ciphertexts(p, reg_buf.data(), reg_cts);
+  Query q;
+  q.v_buf.resize(2 * v_buf_words);
+  for (size_t i = 0; i < v_buf_words; i++) {
+    q.v_buf[2 * i] = reg_buf[2 * i];
+    std::memcpy(&q.v_buf[2 * i + 1], data + 32 + 8 * i, 8);
+  }
+  size_t idx = 32 + 8 * v_buf_words;
+  for (size_t i = 0; i < p.db_dim_2; i++) {
+    PolyMatrix m = raw_zero(p, 2, 2 * p.t_gsw);
+    idx += deser_matrix_rng(p, m, data + idx, rng);
+    q.v_ct.push_back(m);
+  }
+  return q;
 }
 inline PolyMatrix deserialize_query(const Params& p, const uint8_t* data, size_t len) {   // :303-315 (expand_queries)
   if (len != p.query_bytes()) throw std::runtime_error("query has the wrong length");

@@ -16,19 +16,14 @@ except Exception as e:
 PY
 }
 {
-echo "== quick parity of the relaxed-range transforms and the new fold kernel"
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "ntt or fold or process_query or expansion or pack" 2>&1 | tail -3
-echo "== first dimension: analysis knobs"
-run "default (ksps 4)" X=1 --
-run "no MMA" B200PIR_TC5_DBG=1 --
-run "no epilogue" B200PIR_TC5_DBG=2 --
-run "copy only" B200PIR_TC5_DBG=3 --
-run "ksps 2 (8 KiB x 12)" B200PIR_TC5_KSPS=2 --
-run "ksps 8 (32 KiB x 3)" B200PIR_TC5_KSPS=8 --
-run "ksps 1 (4 KiB x 24)" B200PIR_TC5_KSPS=1 --
-echo "== fold variants"
-run "fold old 3/SM" X=1 -- --fold-variant 1
-run "fold old 2/SM" X=1 -- --fold-variant 0
+echo "== new tests"
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tcgen05.py -x -q -k "different_clients or coalesced or direct_upload or error_behaviour or wire or tc5 or expansion or golden" 2>&1 | tail -3
+echo "== first dimension: barrier wait and stage size"
+run "spin wait, ksps 4" X=1 --
+run "spin wait, ksps 8" B200PIR_TC5_KSPS=8 --
+run "spin wait, ksps 2" B200PIR_TC5_KSPS=2 --
+run "hinted wait, ksps 4" B200PIR_TC5_DBG=4 --
+run "spin wait, no epilogue" B200PIR_TC5_DBG=2 --
+run "spin wait, no MMA" B200PIR_TC5_DBG=1 --
 run "fold lz 3/SM" X=1 -- --fold-variant 2
-run "fold lz 2/SM" X=1 -- --fold-variant 3
 } 2>&1 | tee gpurun_out/gpu_exp.log

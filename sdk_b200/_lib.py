@@ -65,6 +65,8 @@ def _load():
         "b200pir_encode": (C.c_int, [vp, u64p, u8p, szp]),
         "b200pir_process_query": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u8p, szp]),
         "b200pir_process_query_batch": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, u8p, szp]),
+        "b200pir_process_queries": (C.c_int, [vp, vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),
+        "b200pir_coalesce_stats": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "b200pir_process_query_batch_dev": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, u8p]),
         "b200pir_query_stage_a_dev": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, u64p]),
         "b200pir_query_stage_b_dev": (C.c_int, [vp, vp, u64p, C.c_size_t, C.c_size_t, u8p]),

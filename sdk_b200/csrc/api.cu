@@ -10,6 +10,8 @@
 #include <cmath>
 #include <memory>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <set>
 #include <string>
@@ -115,6 +117,28 @@ struct b200pir_ctx {
   size_t folded_stride = 0;           // u32 words between consecutive (query, slice) survivors
   DevBuf<uint64_t> w_packed;     // [Q][inst][n+1][n][2048]
   DevBuf<uint8_t> w_resp;        // [Q][response_bytes]
+  // Coalescing of concurrent callers ("coalesce", default on): lib/server takes a READ lock around process_query
+  // (bin/server.rs:102), so actix workers call it concurrently.  Requests arriving while a batch runs queue up here; the
+  // thread that finds no batch in flight becomes the leader and serves everything queued (up to kCoalesceMax) in ONE
+  // database pass.  A lone caller is served immediately (no waiting window).
+  struct Pending {
+    b200pir_db* db; b200pir_pp* pp; const uint64_t* query_ct; const uint8_t* query_bytes; uint8_t* out;
+    int rc = 0; std::string err; bool done = false;
+  };
+  static constexpr size_t kCoalesceMax = 32;
+  int coalesce = 1;
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::deque<Pending*> pending;
+  bool leader_active = false;
+  unsigned long long coalesced_batches = 0, coalesced_queries = 0;
+  // per-query public parameters (PpTable, kernels.h): device arrays [4][pptab_cap] of base pointers; `multi_pps` (host array, one
+  // handle per query of the call in flight) is set by the multi-client entry points, otherwise one handle serves every query
+  DevBuf<const uint32_t*> d_pptab;
+  size_t pptab_cap = 0;
+  std::vector<const uint32_t*> h_pptab;          // what d_pptab holds (skip the upload when unchanged)
+  b200pir_pp* const* multi_pps = nullptr;
+  PpTable pp_table(b200pir_pp* pp, size_t count);
   // profiling
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -200,6 +224,27 @@ struct b200pir_pp {
   DevBuf<uint32_t> pack, left, right, conv;    // ntt32
 };
 
+PpTable b200pir_ctx::pp_table(b200pir_pp* pp, size_t count) {
+  if (count > pptab_cap) {
+    pptab_cap = std::max<size_t>(count, 16);
+    d_pptab.alloc(4 * pptab_cap);
+    h_pptab.clear();
+  }
+  std::vector<const uint32_t*> h(4 * pptab_cap, nullptr);
+  for (size_t i = 0; i < count; i++) {
+    const b200pir_pp* p = multi_pps ? multi_pps[i] : pp;
+    h[0 * pptab_cap + i] = p->pack.p;
+    h[1 * pptab_cap + i] = p->left.p;
+    h[2 * pptab_cap + i] = p->right.p ? p->right.p : p->left.p;     // unwrap_or(v_w_left), server.rs:549
+    h[3 * pptab_cap + i] = p->conv.p;
+  }
+  if (h != h_pptab) {
+    B200_CUDA(cudaMemcpyAsync(d_pptab.p, h.data(), h.size() * sizeof(const uint32_t*), cudaMemcpyHostToDevice, stream));
+    h_pptab = h;
+  }
+  return PpTable{d_pptab.p, d_pptab.p + pptab_cap, d_pptab.p + 2 * pptab_cap, d_pptab.p + 3 * pptab_cap};
+}
+
 struct b200pir_dpir {
   int device;
   cudaStream_t stream = nullptr;
@@ -245,6 +290,7 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
   const int g = c->g;
   const int stop_round = hp.nu_2 > 0 ? c->stop_round : 0;
   const int max_right = hp.nu_2 > 0 ? (int)(hp.t_gsw * hp.nu_2) : 0;
+  const PpTable T = c->pp_table(pp, (size_t)nq);
   for (int r = 0; r < g; r++) {
     const int num_in = 1 << r;
     // wide rounds: one CTA per input ciphertext produces both outputs (no scalar-multiply pass, one inverse transform);
@@ -257,15 +303,15 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
     R.fill_skipped = all_slots ? 1 : 0;
     R.t_auto = (POLY >> r) + 1;
     R.t_left = (int)hp.t_exp_left; R.bits_left = c->bits_left;
-    R.w_left = pp->left.p + (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
+    R.tab_left = T.left; R.off_left = (size_t)r * 2 * hp.t_exp_left * 2 * POLY;
     if (hp.nu_2 > 0 && c->has_right) {
       // v_w_right has stop_round+1 matrices; rounds beyond that never take the right branch for a
       // processed (even) index except r == 0 (server.rs:60-73), so clamp the pointer for safety.
       int rr = r <= c->stop_round ? r : c->stop_round;
       R.t_right = (int)hp.t_exp_right; R.bits_right = c->bits_right;
-      R.w_right = pp->right.p + (size_t)rr * 2 * hp.t_exp_right * 2 * POLY;
+      R.tab_right = T.right; R.off_right = (size_t)rr * 2 * hp.t_exp_right * 2 * POLY;
     } else {
-      R.t_right = R.t_left; R.bits_right = R.bits_left; R.w_right = R.w_left;   // unwrap_or(v_w_left), server.rs:549
+      R.t_right = R.t_left; R.bits_right = R.bits_left; R.tab_right = T.left; R.off_right = R.off_left;   // unwrap_or(v_w_left), server.rs:549
     }
     if (pair && c->expand_variant == 0) {
       const size_t xr_stride = (size_t)num_in * 2 * POLY;
@@ -287,7 +333,7 @@ void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw,
   const int factor = hp.nu_2 > 0 ? 2 : 1;
   launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
   if (hp.nu_2 > 0)
-    launch_regev_to_gsw(c->dp, v_fold, c->fold_words(), v, c->v_words(), nq, (int)hp.nu_2, 2, 1, pp->conv.p,
+    launch_regev_to_gsw(c->dp, v_fold, c->fold_words(), v, c->v_words(), nq, (int)hp.nu_2, 2, 1, c->pp_table(pp, (size_t)nq).conv,
                         (int)hp.t_gsw, (int)hp.t_conv, c->bits_conv, s);
 }
 
@@ -409,7 +455,7 @@ void run_pack_encode(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* folded, siz
   const size_t packed_words = (size_t)hp.instances * (hp.n + 1) * hp.n * POLY;
   {
     b200pir_ctx::Scope sc(c, ST_PACK);
-    launch_pack(c->dp, c->w_packed.p, packed_words, folded, ct_stride, (size_t)c->slices * ct_stride, (int)count, pp->pack.p,
+    launch_pack(c->dp, c->w_packed.p, packed_words, folded, ct_stride, (size_t)c->slices * ct_stride, (int)count, c->pp_table(pp, count).pack,
                 (int)hp.n, (int)hp.instances, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
   }
   {
@@ -583,6 +629,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "intt_variant") c->intt_variant = (int)value;
   else if (k == "imma_variant") c->imma_variant = (int)value;
   else if (k == "sparse_fold") c->sparse_fold = value != 0;
+  else if (k == "coalesce") c->coalesce = value != 0;
   else if (k == "expand_variant") c->expand_variant = (int)value;
   else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
   else if (k == "db_format") { if (value < -1 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be -1 (automatic), 0, 1 or 2"); c->db_format = (int)value; }
@@ -930,6 +977,31 @@ void deserialize_queries(b200pir_ctx* c, const uint8_t* data, size_t count, uint
     B200_CUDA(cudaMemcpyAsync(dst_dev + i * 2 * POLY + POLY, q + 32, POLY * 8, cudaMemcpyHostToDevice, c->stream));
   }
 }
+// Query::deserialize, direct-upload branch (client.rs:316-327): one serialized query -> the device-format first-dimension
+// operand (q_dev) and the NTT-form folding matrices (v_fold) of workspace slot `slot`.
+// Keystream order (interleave_rng_data :107-131, deserialize_vec_polymatrix_rng :81-93): 2048 words per first-dimension
+// ciphertext (its row 0), then the first rows (2 t_gsw polynomials) of the nu_2 GSW matrices.
+void deserialize_query_direct(b200pir_ctx* c, const uint8_t* q, size_t slot) {
+  const size_t dim0 = (size_t)c->dim0, t2 = 2 * c->hp.t_gsw, nu2 = c->hp.nu_2;
+  cudaStream_t s = c->stream;
+  // row 0 of every first-dimension ciphertext: a raw 1 x 1 "matrix" per ciphertext (row 1 of sigma stays zero and is never used)
+  DevBuf<uint64_t> sig_raw(dim0 * POLY);
+  DevBuf<uint32_t> sig_ntt(dim0 * 2 * POLY);
+  launch_chacha_first_rows(sig_raw.p, q, 0, (uint32_t)dim0, POLY, POLY, c->dp.modulus, s);
+  launch_to_ntt(c->dp, sig_ntt.p, sig_raw.p, dim0, s);
+  DevBuf<uint64_t> wire(dim0 * POLY);
+  B200_CUDA(cudaMemcpyAsync(wire.p, q + 32, dim0 * POLY * 8, cudaMemcpyHostToDevice, s));
+  launch_direct_query_to_dev(c->w_qdev.p + slot * dim0 * POLY, sig_ntt.p, wire.p, (int)dim0, s);
+  if (nu2) {
+    DevBuf<uint64_t> raw(nu2 * 2 * t2 * POLY);
+    launch_chacha_first_rows(raw.p, q, dim0 * POLY, (uint32_t)nu2, (uint32_t)(t2 * POLY), 2 * t2 * POLY, c->dp.modulus, s);
+    const uint8_t* rest = q + 32 + dim0 * POLY * 8;
+    for (size_t i = 0; i < nu2; i++)
+      B200_CUDA(cudaMemcpyAsync(raw.p + (i * 2 + 1) * t2 * POLY, rest + i * t2 * POLY * 8, t2 * POLY * 8, cudaMemcpyHostToDevice, s));
+    launch_to_ntt(c->dp, c->w_vfold.p + slot * c->fold_words(), raw.p, nu2 * 2 * t2, s);
+  }
+  B200_CUDA(cudaStreamSynchronize(s));        // the staging buffers above are freed on return
+}
 }  // namespace
 
 int b200pir_query_from_bytes(b200pir_ctx* c, const uint8_t* data, size_t len, uint64_t* query_ct) {
@@ -1214,7 +1286,7 @@ int b200pir_pack(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* v_ct, uint64_t*
   DevBuf<uint32_t> o(outp * 2 * POLY), res(nn * 4 * POLY);
   B200_CUDA(cudaMemcpyAsync(cts.p, v_ct, cts.n * 8, cudaMemcpyHostToDevice, c->stream));
   launch_raw_to_res(c->dp, res.p, cts.p, nn * 2, c->stream);
-  launch_pack(c->dp, raw.p, 0, res.p, 4 * POLY, 0, 1, pp->pack.p, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
+  launch_pack(c->dp, raw.p, 0, res.p, 4 * POLY, 0, 1, c->pp_table(pp, 1).pack, (int)hp.n, 1, (int)hp.t_conv, c->bits_conv, (int)hp.version, c->stream);
   // the reference's pack returns the NTT-form matrix (server.rs:467); the kernel already applied .raw()
   launch_to_ntt(c->dp, o.p, raw.p, outp, c->stream);
   launch_widen(wide.p, o.p, o.n, c->stream);
@@ -1289,13 +1361,100 @@ int b200pir_process_query_batch(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, 
   API_END
 }
 
+namespace {
+// `count` queries of possibly different clients in one database pass.  cts[i]: host PolyMatrixRaw(2,1), or bytes[i]: the
+// serialized query (exactly one of the two non-null per entry); outs[i]: response_bytes.  Caller holds no lock.
+void process_multi(b200pir_ctx* c, b200pir_db* db, b200pir_pp* const* pps, const uint64_t* const* cts,
+                   const uint8_t* const* bytes, size_t count, uint8_t* const* outs) {
+  Guard gd(c);
+  check_db(c, db);
+  for (size_t i = 0; i < count; i++) check_pp(c, pps[i]);
+  if (db->shard.count != 1) throw Error(B200PIR_E_BADARG, "sharded database: use the stage_a / stage_b entry points");
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "multi-client batches need expand_queries");
+  // workspace sized once for a full coalesced batch: batch sizes vary from call to call, the buffers do not
+  c->ensure_workspace(std::max(count, c->coalesce ? b200pir_ctx::kCoalesceMax : count), db->rows);
+  c->prof_reset();
+  for (size_t i = 0; i < count; i++) {
+    if (bytes && bytes[i]) deserialize_queries(c, bytes[i], 1, c->w_query.p + i * 2 * POLY);
+    else B200_CUDA(cudaMemcpyAsync(c->w_query.p + i * 2 * POLY, cts[i], 2 * POLY * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->multi_pps = pps;
+  try {
+    run_query_batch_resident(c, db, pps[0], count, c->w_resp.p);
+  } catch (...) { c->multi_pps = nullptr; throw; }
+  c->multi_pps = nullptr;
+  for (size_t i = 0; i < count; i++)
+    B200_CUDA(cudaMemcpyAsync(outs[i], c->w_resp.p + i * c->response_bytes, c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->profile == 1) c->prof_collect();
+  B200_CUDA(cudaGetLastError());
+}
+
+// one query through the combiner (see b200pir_ctx::Pending)
+int coalesced_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64_t* query_ct, const uint8_t* query_bytes,
+                    uint8_t* out) {
+  b200pir_ctx::Pending me;
+  me.db = db; me.pp = pp; me.query_ct = query_ct; me.query_bytes = query_bytes; me.out = out;
+  std::unique_lock<std::mutex> lk(c->qmu);
+  c->pending.push_back(&me);
+  while (!me.done) {
+    if (c->leader_active) { c->qcv.wait(lk); continue; }
+    // become the leader: take every queued request for the database at the head of the queue
+    c->leader_active = true;
+    std::vector<b200pir_ctx::Pending*> batch;
+    b200pir_db* bdb = c->pending.front()->db;
+    for (auto it = c->pending.begin(); it != c->pending.end() && batch.size() < b200pir_ctx::kCoalesceMax;) {
+      if ((*it)->db == bdb) { batch.push_back(*it); it = c->pending.erase(it); } else ++it;
+    }
+    lk.unlock();
+    int rc = 0;
+    std::string err;
+    try {
+      std::vector<b200pir_pp*> pps; std::vector<const uint64_t*> cts; std::vector<const uint8_t*> bys; std::vector<uint8_t*> outs;
+      for (auto* p : batch) { pps.push_back(p->pp); cts.push_back(p->query_ct); bys.push_back(p->query_bytes); outs.push_back(p->out); }
+      process_multi(c, bdb, pps.data(), cts.data(), bys.data(), batch.size(), outs.data());
+    } catch (const std::exception& e) { rc = fail(e); err = e.what(); }
+    lk.lock();
+    c->coalesced_batches++; c->coalesced_queries += batch.size();
+    for (auto* p : batch) { p->rc = rc; p->err = err; p->done = true; }
+    c->leader_active = false;
+    c->qcv.notify_all();
+  }
+  if (me.rc) g_last_error = me.err;
+  return me.rc;
+}
+}  // namespace
+
+int b200pir_process_queries(b200pir_ctx* c, b200pir_db* db, b200pir_pp* const* pps, const uint64_t* const* query_cts, size_t count,
+                            uint8_t* const* outs) {
+  API_BEGIN
+  if (!c || !pps || !query_cts || !outs) throw Error(B200PIR_E_BADARG, "null argument");
+  for (size_t i = 0; i < count; i++)
+    if (!pps[i] || !query_cts[i] || !outs[i]) throw Error(B200PIR_E_BADARG, "null entry");
+  if (count == 0) return 0;
+  process_multi(c, db, pps, query_cts, nullptr, count, outs);
+  API_END
+}
+int b200pir_coalesce_stats(b200pir_ctx* c, uint64_t* batches, uint64_t* queries) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  std::lock_guard<std::mutex> lk(c->qmu);
+  if (batches) *batches = c->coalesced_batches;
+  if (queries) *queries = c->coalesced_queries;
+  API_END
+}
+
 // process_query over the wire format: `count` serialized queries (Query::serialize, client.rs:279-301) back to back
 int b200pir_process_query_bytes(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint8_t* queries, size_t len,
                                 size_t count, uint8_t* out, size_t* out_len_each) {
   API_BEGIN
   if (!c || !out || !queries) throw Error(B200PIR_E_BADARG, "null argument");
-  if (!c->hp.expand_queries) throw Error(B200PIR_E_UNSUPPORTED, "serialized direct-upload queries are not supported");
   if (len != count * c->query_bytes) throw Error(B200PIR_E_SHAPE, "queries: expected " + std::to_string(count * c->query_bytes) + " bytes");
+  if (count == 1 && c->coalesce && c->hp.expand_queries && db && pp) {          // the /private-read handler's call: one query per request
+    const int rc = coalesced_query(c, db, pp, nullptr, queries, out);
+    if (rc == 0 && out_len_each) *out_len_each = c->response_bytes;
+    return rc;
+  }
   Guard gd(c);
   check_db(c, db);
   check_pp(c, pp);
@@ -1303,8 +1462,16 @@ int b200pir_process_query_bytes(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, 
   if (count == 0) return 0;
   c->ensure_workspace(count, db->rows);
   c->prof_reset();
-  deserialize_queries(c, queries, count, c->w_query.p);
-  run_query_batch_resident(c, db, pp, count, c->w_resp.p);
+  if (c->hp.expand_queries) {
+    deserialize_queries(c, queries, count, c->w_query.p);
+    run_query_batch_resident(c, db, pp, count, c->w_resp.p);
+  } else {
+    // direct upload (client.rs:316-327; the body lib/server's handler parses at bin/server.rs:122-137 is setup || query):
+    // every query arrives expanded; nothing to prepare beyond the deserialization
+    for (size_t i = 0; i < count; i++) deserialize_query_direct(c, queries + i * c->query_bytes, i);
+    run_first_dim_and_fold(c, db, count);
+    run_pack_encode(c, pp, c->folded, c->folded_stride, count, c->w_resp.p);
+  }
   B200_CUDA(cudaMemcpyAsync(out, c->w_resp.p, count * c->response_bytes, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
   if (c->profile == 1) c->prof_collect();
@@ -1317,8 +1484,11 @@ int b200pir_process_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const 
                           const uint64_t* v_ct, uint8_t* out, size_t* out_len) {
   if (!c) { g_last_error = "null ctx"; return B200PIR_E_BADARG; }
   if (c->hp.expand_queries) {
-    if (!query_ct) { g_last_error = "query_ct is NULL"; return B200PIR_E_BADARG; }
-    return b200pir_process_query_batch(c, db, pp, query_ct, 1, out, out_len);
+    if (!query_ct || !out || !db || !pp) { g_last_error = "null argument"; return B200PIR_E_BADARG; }
+    if (!c->coalesce) return b200pir_process_query_batch(c, db, pp, query_ct, 1, out, out_len);
+    const int rc = coalesced_query(c, db, pp, query_ct, nullptr, out);
+    if (rc == 0 && out_len) *out_len = c->response_bytes;
+    return rc;
   }
   API_BEGIN
   if (!v_buf || (!v_ct && c->hp.nu_2) || !out) throw Error(B200PIR_E_BADARG, "null argument");

@@ -39,6 +39,8 @@ void launch_to_ntt_strided(const DevParams& P, uint32_t* out, size_t out_stride,
 // client.rs:47-80: first rows of n_mats raw matrices = q - (ChaCha20 keystream u64 % q), keystream u64 index word0 onwards
 void launch_chacha_first_rows(uint64_t* raw, const uint8_t seed[32], uint64_t word0, uint32_t n_mats, uint32_t row_words,
                               uint64_t mat_words, uint64_t modulus, cudaStream_t s);
+// client.rs:316-327: regenerated row-0 transforms (ntt32 [j][n][z]) + uploaded words ([z][j]) -> q_dev (format of launch_query_to_dev)
+void launch_direct_query_to_dev(uint4* q_dev, const uint32_t* sig_ntt, const uint64_t* wire_words, int dim0, cudaStream_t s);
 // poly.rs:646-663 from_ntt: ntt32 -> raw u64 (inverse NTT both moduli + CRT lift)
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s);
 // raw u64 coefficients <-> residue form u32 [poly][n][z] (coefficient domain; the CRT lift is poly.rs:658)
@@ -134,10 +136,14 @@ void launch_folding_neg(const DevParams& P, uint32_t* out, const uint32_t* v_fol
 // launch, each covering all nq queries (grid.y).
 void launch_expand_scalar(const DevParams& P, uint32_t* v, size_t v_stride, int nq, int num_in, const uint32_t* neg1_r,
                           cudaStream_t s);
+// Public parameters are per QUERY: device arrays of base pointers (the ntt32 matrices of the client that sent query i), so one
+// launch serves concurrent queries of different clients — lib/server looks the parameters up per request (bin/server.rs:113-117).
+struct PpTable { const uint32_t* const* pack; const uint32_t* const* left; const uint32_t* const* right; const uint32_t* const* conv; };
 struct ExpandRound {
   int r, num_in, stop_round, max_bits_to_gen_right, t_auto;
-  const uint32_t* w_left;   // ntt32 [2][t_exp_left]  for this round (or null when r == 0 / unused)
-  const uint32_t* w_right;  // ntt32 [2][t_exp_right]
+  const uint32_t* const* tab_left;    // [query] -> v_expansion_left of that query's client; this round's matrix (ntt32 [2][t_exp_left])
+  const uint32_t* const* tab_right;   // starts off_left / off_right words further
+  size_t off_left, off_right;
   int t_left, t_right, bits_left, bits_right;
   int fill_skipped;         // paired kernel: also write v[i + num_in] = v[i] (.) neg1 for skipped i (stage-level parity)
 };
@@ -153,7 +159,7 @@ void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint
                      int idx_factor, cudaStream_t s);
 // server.rs:123-151: v_gsw[i] (ntt32 [2][2 t_gsw]) from v_inp[idx_factor*(i t_gsw + j) + idx_offset]
 void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride,
-                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* v_conv, int t_gsw,
+                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* const* tab_conv, int t_gsw,
                          int t_conv, int bits_conv, cudaStream_t s);
 
 // ---- packing + encoding (server.rs:429-503; lib/server compute/pack.rs)
@@ -161,7 +167,7 @@ void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride,
 // w: ntt32 packing matrices; out: raw [inst][n+1][n][2048]
 // nq queries per launch: query k reads folded + k*in_q_stride and writes out_raw + k*out_q_stride
 void launch_pack(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride,
-                 size_t in_q_stride, int nq, const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv,
+                 size_t in_q_stride, int nq, const uint32_t* const* tab_pack, int n, int instances, int t_conv, int bits_conv,
                  int version, cudaStream_t s);
 // out: nq x out_bytes; packed_raw: nq matrices packed_q_stride words apart
 void launch_encode(const DevParams& P, uint8_t* out, size_t out_bytes, const uint64_t* packed_raw, size_t packed_q_stride,

@@ -147,8 +147,9 @@ __device__ __forceinline__ void acc_reduce(uint64_t (&acc)[ROWS][8], const Grp& 
 
 // digit k of a raw coefficient; bits == 8 (the common t = 8): digit k is byte k, and since the values are <= q < 2^56 byte 7
 // is a zero byte to fill the upper three bytes with — one PRMT instead of two funnel shifts and a mask
+template <bool BYTE>
 __device__ __forceinline__ uint32_t gadget_digit_fast(uint64_t v, int k, int bits, uint64_t mask) {
-  if (bits == 8) return __byte_perm((uint32_t)v, (uint32_t)(v >> 32), 0x7770u | (uint32_t)k);
+  if (BYTE) return __byte_perm((uint32_t)v, (uint32_t)(v >> 32), 0x7770u | (uint32_t)k);
   return gadget_digit(v, k, bits, mask);
 }
 
@@ -157,10 +158,10 @@ __device__ __forceinline__ uint32_t gadget_digit_fast(uint64_t v, int k, int bit
 // column) of this group's modulus, offset by tid*8.  `cnt` counts products held per accumulator.
 // Relaxed-range forward transforms (ntt_core.cuh "lz"): digits are < 2^19 < 2q (gadget dimensions >= 3), the outputs
 // (< 16q < 2^32) go straight into the 64-bit accumulators: products < 2^60, at most 16 per accumulator between reductions.
-template <int ROWS, bool SM>
-__device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
-                                           int bits, const uint32_t* c0, size_t col_step, size_t row_step,
-                                           const Grp& g) {
+template <int ROWS, bool SM, bool BYTE>
+__device__ __forceinline__ void digits_mac_impl(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
+                                                int bits, const uint32_t* c0, size_t col_step, size_t row_step,
+                                                const Grp& g) {
   const uint64_t mask = (1ull << bits) - 1;
   int k = 0;
   if (SM) {
@@ -171,8 +172,8 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
       uint32_t x0[8], x1[8];
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        x0[a] = gadget_digit_fast(v[a], k, bits, mask);
-        x1[a] = gadget_digit_fast(v[a], k + 1, bits, mask);
+        x0[a] = gadget_digit_fast<BYTE>(v[a], k, bits, mask);
+        x1[a] = gadget_digit_fast<BYTE>(v[a], k + 1, bits, mask);
       }
       ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, g.smem, g.smem2, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
       if (cnt + 2 > 16) { acc_reduce<ROWS>(acc, g); cnt = 1; }
@@ -194,7 +195,7 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
   for (; k < ndig; k++) {
     uint32_t x[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) x[a] = gadget_digit_fast(v[a], k, bits, mask);
+    for (int a = 0; a < 8; a++) x[a] = gadget_digit_fast<BYTE>(v[a], k, bits, mask);
     if (SM) ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x, g.smem, TwConst{g.n, 0}, TwShared{g.fwd_hi_sm}, g.q, CtaSync());
     else ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x, g.smem, TwConst{g.n, 0}, TwGlobal{g.fwd}, g.q, CtaSync());
     if (cnt + 1 > 16) { acc_reduce<ROWS>(acc, g); cnt = 1; }
@@ -208,6 +209,15 @@ __device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, c
       for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x[e] * cv[e];
     }
   }
+}
+
+// one warp-uniform branch per call (not per digit): the byte-permute and the funnel-shift digit extraction as two loop bodies
+template <int ROWS, bool SM>
+__device__ __forceinline__ void digits_mac(uint64_t (&acc)[ROWS][8], int& cnt, const uint64_t (&v)[8], int ndig,
+                                           int bits, const uint32_t* c0, size_t col_step, size_t row_step,
+                                           const Grp& g) {
+  if (bits == 8) digits_mac_impl<ROWS, SM, true>(acc, cnt, v, ndig, bits, c0, col_step, row_step, g);
+  else digits_mac_impl<ROWS, SM, false>(acc, cnt, v, ndig, bits, c0, col_step, row_step, g);
 }
 
 // CRT-lift one polynomial whose two residue vectors sit in the two groups' registers (strided layout,
@@ -699,7 +709,7 @@ __global__ void __launch_bounds__(CTA, 1) k_expand_round(DevParams P, uint32_t* 
       (R.stop_round > 0 && R.r == R.stop_round && (ih & 1) && (ih / 2) >= R.max_bits_to_gen_right))
     return;
   const bool left = (R.r != 0) && ((ih & 1) == 0);
-  const uint32_t* W = left ? R.w_left : R.w_right;
+  const uint32_t* W = left ? R.tab_left[blockIdx.y] + R.off_left : R.tab_right[blockIdx.y] + R.off_right;
   const int t_exp = left ? R.t_left : R.t_right;
   const int bits = left ? R.bits_left : R.bits_right;
 
@@ -808,7 +818,7 @@ k_expand_round_pair(DevParams P, uint32_t* v, size_t v_stride, ExpandRound R, co
     return;
   }
   const bool left = (R.r != 0) && ((i & 1) == 0);
-  const uint32_t* W = left ? R.w_left : R.w_right;
+  const uint32_t* W = left ? R.tab_left[blockIdx.y] + R.off_left : R.tab_right[blockIdx.y] + R.off_right;
   const int t_exp = left ? R.t_left : R.t_right;
   const int bits = left ? R.bits_left : R.bits_right;
 
@@ -958,7 +968,7 @@ k_expand_round_res(DevParams P, uint32_t* v, size_t v_stride, const uint32_t* __
     return;
   }
   const bool left = (R.r != 0) && ((i & 1) == 0);
-  const uint32_t* W = left ? R.w_left : R.w_right;
+  const uint32_t* W = left ? R.tab_left[blockIdx.z] + R.off_left : R.tab_right[blockIdx.z] + R.off_right;
   const int t_exp = left ? R.t_left : R.t_right;
   const int bits = left ? R.bits_left : R.bits_right;
   stage_fwd_twiddles(g, tw);
@@ -1045,7 +1055,8 @@ __global__ void k_reorient(MulGeom G, uint4* q_dev, size_t q_stride, const uint3
 // server.rs:134-150.  CTA = (gsw index i, digit j).
 __global__ void __launch_bounds__(CTA, 1)
 k_regev_to_gsw(DevParams P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride, int idx_factor,
-               int idx_offset, const uint32_t* v_conv, int t_gsw, int t_conv, int bits_conv) {
+               int idx_offset, const uint32_t* const* tab_conv, int t_gsw, int t_conv, int bits_conv) {
+  const uint32_t* v_conv = tab_conv[blockIdx.y];
   v_gsw += (size_t)blockIdx.y * gsw_stride;
   v += (size_t)blockIdx.y * v_stride;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -1099,7 +1110,8 @@ k_regev_to_gsw(DevParams P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* 
 template <int ROWS>
 __global__ void __launch_bounds__(CTA, 1)
 k_pack(DevParams P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride, size_t in_q_stride,
-       const uint32_t* v_packing, int t_conv, int bits, int version) {
+       const uint32_t* const* tab_pack, int t_conv, int bits, int version) {
+  const uint32_t* v_packing = tab_pack[blockIdx.y];
   out_raw += (size_t)blockIdx.y * out_q_stride;
   folded += (size_t)blockIdx.y * in_q_stride;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -1387,32 +1399,32 @@ void launch_reorient(const MulGeom& G, uint4* q_dev, size_t q_stride, const uint
   k_reorient<<<dim3(grid1d(total, 256), nq), 256, 0, s>>>(G, q_dev, q_stride, v, v_stride, idx_factor);
 }
 void launch_regev_to_gsw(const DevParams& P, uint32_t* v_gsw, size_t gsw_stride, const uint32_t* v, size_t v_stride,
-                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* v_conv, int t_gsw,
+                         int nq, int count, int idx_factor, int idx_offset, const uint32_t* const* tab_conv, int t_gsw,
                          int t_conv, int bits_conv, cudaStream_t s) {
   if (count == 0) return;
   opt_in_smem(k_regev_to_gsw, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_regev_to_gsw<<<dim3((unsigned)(count * t_gsw), nq), CTA, kDynSmemBig, s>>>(P, v_gsw, gsw_stride, v, v_stride,
-                                                                               idx_factor, idx_offset, v_conv, t_gsw,
+                                                                               idx_factor, idx_offset, tab_conv, t_gsw,
                                                                                t_conv, bits_conv);
 }
 template <int ROWS>
 static void launch_pack_t(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded,
-                          size_t ct_stride, size_t in_q_stride, int nq, const uint32_t* v_packing, int instances,
+                          size_t ct_stride, size_t in_q_stride, int nq, const uint32_t* const* tab_pack, int instances,
                           int t_conv, int bits_conv, int version, cudaStream_t s) {
   opt_in_smem(k_pack<ROWS>, (int)kDynSmemBig);
   ++g_kernel_launches;
   k_pack<ROWS><<<dim3((unsigned)(instances * (ROWS - 1)), nq), CTA, kDynSmemBig, s>>>(
-      P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, v_packing, t_conv, bits_conv, version);
+      P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, tab_pack, t_conv, bits_conv, version);
 }
 void launch_pack(const DevParams& P, uint64_t* out_raw, size_t out_q_stride, const uint32_t* folded, size_t ct_stride,
-                 size_t in_q_stride, int nq, const uint32_t* v_packing, int n, int instances, int t_conv, int bits_conv,
+                 size_t in_q_stride, int nq, const uint32_t* const* tab_pack, int n, int instances, int t_conv, int bits_conv,
                  int version, cudaStream_t s) {
   switch (n) {
-    case 1: launch_pack_t<2>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 2: launch_pack_t<3>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 3: launch_pack_t<4>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
-    case 4: launch_pack_t<5>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, v_packing, instances, t_conv, bits_conv, version, s); break;
+    case 1: launch_pack_t<2>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, tab_pack, instances, t_conv, bits_conv, version, s); break;
+    case 2: launch_pack_t<3>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, tab_pack, instances, t_conv, bits_conv, version, s); break;
+    case 3: launch_pack_t<4>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, tab_pack, instances, t_conv, bits_conv, version, s); break;
+    case 4: launch_pack_t<5>(P, out_raw, out_q_stride, folded, ct_stride, in_q_stride, nq, tab_pack, instances, t_conv, bits_conv, version, s); break;
     default: throw Error(-2, "pack: n must be 1..4");
   }
 }

@@ -48,9 +48,33 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// Bounded wait: a protocol error must surface as a launch failure (trap), never as a hung GPU.  Each try_wait suspends
-// for at most ~1 ms (0xF4240 ns hint); 20000 tries ~ 20 s is far beyond any legitimate wait of this kernel.
+// Bounded wait: a protocol error must surface as a launch failure (trap), never as a hung GPU.  Plain try_wait in a spin loop
+// (no suspend-time hint: a hinted wait may park the thread for long quanta, and every stage hand-off of the pipeline goes
+// through one of these); the bound is on elapsed clocks (~20 s), checked every 1024 polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t tries = 0;; tries++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((tries & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 40000000000ll) asm volatile("trap;");
+    }
+  }
+}
+// the previous form (1 ms suspend-time hint per try), kept selectable for A/B measurements (dbg_mode bit 2)
+__device__ __forceinline__ void mbar_wait_hinted(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (int tries = 0; tries < 20000; tries++) {
     uint32_t done;
@@ -195,6 +219,8 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count,
                uint32_t* __restrict__ dbg /* bring-up aid: raw accumulators of CTA 0's first TC5_DBG_TILES tiles, or null */,
                int dbg_mode) {
+  const bool hinted = (dbg_mode & 4) != 0;
+#define mbar_wait(bar, par) do { if (hinted) mbar_wait_hinted(bar, par); else (mbar_wait)(bar, par); } while (0)
   constexpr int TC5_KS_PER_STAGE = KSPS;
   constexpr int TC5_STAGE_BYTES = KSPS * TC5_TILE;
   constexpr int TC5_STAGES = TC5_RING_BYTES / TC5_STAGE_BYTES;
@@ -336,6 +362,7 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
     }
   }
 
+#undef mbar_wait
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

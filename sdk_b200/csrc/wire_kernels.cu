@@ -60,4 +60,22 @@ void launch_chacha_first_rows(uint64_t* raw, const uint8_t seed[32], uint64_t wo
   B200_CUDA(cudaGetLastError());
 }
 
+// Query::deserialize, direct-upload branch (client.rs:316-327 with interleave_rng_data :107-131): the device-format first
+// dimension operand q_dev[j][z] = {row 0 mod q0, row 0 mod q1 (regenerated from the seed, transformed), low and high half of
+// the uploaded word (z, j)} — the reference's interleaved v_buf[(z dim0 + j) 2 + {0, 1}] without materialising it.
+// sig: ntt32 [j][n][z] of the regenerated row-0 polynomials; wire: the uploaded odd-indexed words, [z][j].
+__global__ void k_direct_query_to_dev(uint4* __restrict__ q_dev, const uint32_t* __restrict__ sig, const uint64_t* __restrict__ wire,
+                                      int dim0) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over dim0 * 2048, z fastest
+  if (idx >= (size_t)dim0 * 2048) return;
+  const int z = (int)(idx % 2048), j = (int)(idx / 2048);
+  const uint64_t w = wire[(size_t)z * dim0 + j];
+  q_dev[idx] = make_uint4(sig[((size_t)j * 2 + 0) * 2048 + z], sig[((size_t)j * 2 + 1) * 2048 + z], (uint32_t)w, (uint32_t)(w >> 32));
+}
+void launch_direct_query_to_dev(uint4* q_dev, const uint32_t* sig_ntt, const uint64_t* wire_words, int dim0, cudaStream_t s) {
+  const size_t total = (size_t)dim0 * 2048;
+  k_direct_query_to_dev<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q_dev, sig_ntt, wire_words, dim0);
+  g_kernel_launches++;
+}
+
 }  // namespace b200pir

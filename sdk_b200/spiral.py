@@ -328,6 +328,32 @@ def process_query_bytes(params, public_params, queries, db):
     return out.reshape(count, params.response_bytes)
 
 
+def process_queries(params, public_params_list, query_cts, db):
+    """Concurrent queries of DIFFERENT clients in one database pass: public_params_list[i] belongs to the client that sent
+    query_cts[i] (each a PolyMatrixRaw(2,1) as u64 array).  Returns [count][response_bytes]."""
+    count = len(query_cts)
+    if len(public_params_list) != count:
+        raise ValueError("one PublicParameters per query")
+    cts = [np.ascontiguousarray(q, dtype=np.uint64) for q in query_cts]
+    for q in cts:
+        if q.size != 2 * POLY_LEN:
+            raise ValueError("query ct must hold 2 x 2048 words")
+    out = np.zeros((count, params.response_bytes), dtype=np.uint8)
+    vp = C.c_void_p * count
+    pps = vp(*[pp._h for pp in public_params_list])
+    qs = vp(*[q.ctypes.data for q in cts])
+    outs = vp(*[out[i].ctypes.data for i in range(count)])
+    check(LIB.b200pir_process_queries(params._h, db._h, pps, qs, count, outs))
+    return out
+
+
+def coalesce_stats(params):
+    """(batches, queries) served through the concurrent-caller combiner of this context so far."""
+    b, q = C.c_uint64(0), C.c_uint64(0)
+    check(LIB.b200pir_coalesce_stats(params._h, C.byref(b), C.byref(q)))
+    return b.value, q.value
+
+
 def process_query_batch(params, public_params, query_cts, db):
     """`count` expanded-mode queries of one client; the database is streamed once per group."""
     count = query_cts.size // (2 * POLY_LEN)

@@ -297,6 +297,14 @@ class Params:
         _ck(LIB.orc_query_deserialize(self.hp, _p8(data), C.c_size_t(data.size), _p64(ct)))
         return ct
 
+    def query_deserialize_direct(self, data):
+        """Query::deserialize, direct-upload branch (client.rs:316-327): -> dict(v_buf, v_ct)."""
+        v_buf = np.zeros(self.dim0 * 2 * self.N, dtype=np.uint64)
+        v_ct = np.zeros(self.nu_2 * 2 * 2 * self.t_gsw * self.N, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        _ck(LIB.orc_query_deserialize_direct(self.hp, _p8(data), C.c_size_t(data.size), _p64(v_buf), _p64(v_ct)))
+        return dict(v_buf=v_buf, v_ct=v_ct)
+
     def load_db_from_bytes(self, data):
         """load_db_from_seek (server.rs:320-357) over an in-memory file image -> db words."""
         data = np.ascontiguousarray(data, dtype=np.uint8)

@@ -729,6 +729,96 @@ def test_wire_formats_deserialize_and_process(name):
     gpp2.close()
 
 
+def test_queries_of_different_clients_share_one_pass():
+    """lib/server serves each request with the public parameters of ITS client (bin/server.rs:113-117).  Two clients with
+    different keys, their queries interleaved in one b200pir_process_queries call: every response == the oracle's for that
+    client, and decodes under that client's secret key."""
+    S, P, cl_a, pp_a, db, G, gdb, gpp_a = setup_case("T")
+    cl_b = O.Client(P, 777)
+    pp_b = cl_b.generate_keys()
+    gpp_b = S.PublicParameters(G, pp_b["pack"], pp_b["left"], pp_b["right"], pp_b["conv"])
+    plan = [(cl_a, pp_a, gpp_a, 5), (cl_b, pp_b, gpp_b, 9), (cl_b, pp_b, gpp_b, 200), (cl_a, pp_a, gpp_a, 77), (cl_b, pp_b, gpp_b, 0)]
+    qs = [cl.generate_query(idx)["ct"] for cl, _, _, idx in plan]
+    out = S.process_queries(G, [g for _, _, g, _ in plan], qs, gdb)
+    for k, (cl, pp, _, idx) in enumerate(plan):
+        assert np.array_equal(out[k], P.process_query(pp, dict(ct=qs[k]), db)), k
+        assert np.array_equal(cl.decode_response(out[k]), P.db_plain_item(SEED_DB, idx))
+    gpp_b.close()
+
+
+def test_concurrent_callers_are_coalesced():
+    """lib/server calls process_query from concurrent actix workers under a read lock (bin/server.rs:102).  16 host threads
+    call b200pir_process_query on one context (two clients, alternating): identical bytes to serial calls, fewer database
+    passes than queries, and at least 3x the serial queries/s."""
+    import threading
+    import time
+    S, P, cl_a, pp_a, db, G, gdb, gpp_a = setup_case("T")
+    cl_b = O.Client(P, 4242)
+    pp_b = cl_b.generate_keys()
+    gpp_b = S.PublicParameters(G, pp_b["pack"], pp_b["left"], pp_b["right"], pp_b["conv"])
+    n = 16
+    who = [(cl_a, gpp_a) if k % 2 == 0 else (cl_b, gpp_b) for k in range(n)]
+    idxs = [(37 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
+    qs = [S.Query(ct=cl.generate_query(i)["ct"]) for (cl, _), i in zip(who, idxs)]
+    serial = [S.process_query(G, g, q, gdb).copy() for (_, g), q in zip(who, qs)]         # also warms the workspace up
+    t0 = time.perf_counter()
+    for (_, g), q in zip(who, qs):
+        S.process_query(G, g, q, gdb)
+    t_serial = time.perf_counter() - t0
+    b0, q0 = S.coalesce_stats(G)
+    got = [None] * n
+    start = threading.Barrier(n)
+
+    def worker(k):
+        start.wait()
+        got[k] = S.process_query(G, who[k][1], qs[k], gdb).copy()
+
+    best = None
+    for _ in range(3):
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(n)]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        for k in range(n):
+            assert np.array_equal(got[k], serial[k]), k
+    b1, q1 = S.coalesce_stats(G)
+    assert q1 - q0 == 3 * n and b1 - b0 < 3 * n / 2, (b1 - b0, q1 - q0)
+    for k, ((cl, _), i) in enumerate(zip(who, idxs)):
+        assert np.array_equal(cl.decode_response(got[k]), P.db_plain_item(SEED_DB, i))
+    assert t_serial / best >= 3.0, (t_serial, best)
+    gpp_b.close()
+
+
+def test_direct_upload_queries_over_the_wire():
+    """Query::deserialize's direct-upload branch (client.rs:316-327) on the GPU: the seed-derived halves of v_buf and the
+    first rows of v_ct are regenerated from the 32-byte seed; response bytes == the oracle's process_query on the generated
+    (never serialized) query, for a batch of three queries in one call; public parameters arrive serialized too
+    (the handler's body is setup || query, bin/server.rs:122-137)."""
+    S, P, _, _, db, G, gdb, _ = setup_case("T", expand=False)
+    cl = O.Client(P, 99)
+    pp = cl.generate_keys()
+    gpp = S.PublicParameters.deserialize(G, cl.pp_bytes())
+    idxs = [0, 77, P.dim0 * P.num_per - 1]
+    blobs, refs = [], []
+    for idx in idxs:
+        q = cl.generate_query(idx)
+        qb = cl.query_bytes()
+        assert qb.size == G.query_bytes
+        blobs.append(qb)
+        refs.append(P.process_query(pp, q, db))
+    out = S.process_query_bytes(G, gpp, np.concatenate(blobs), gdb)
+    for k, idx in enumerate(idxs):
+        assert np.array_equal(out[k], refs[k]), k
+        assert np.array_equal(cl.decode_response(out[k]), P.db_plain_item(SEED_DB, idx))
+    with pytest.raises((S.B200PirError, ValueError)):
+        S.process_query_bytes(G, gpp, blobs[0][:-8], gdb)
+    gpp.close()
+
+
 # ------------------------------------------------------------------ golden fixtures (tests/golden/spiral_golden.json)
 @pytest.mark.parametrize("case", ["T_expand", "T1_expand", "T0_expand", "T_direct"])
 def test_cuda_path_reproduces_golden_fixtures(case):

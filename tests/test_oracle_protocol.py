@@ -120,6 +120,24 @@ def test_wire_formats_round_trip(name):
     assert np.array_equal(P.query_deserialize(qb), q["ct"])
 
 
+def test_direct_upload_wire_format_round_trip():
+    # client.rs:939-955 no_expansion_query_serialization_is_correct (serialize . deserialize . serialize), strengthened:
+    # the deserialized query must equal the generated one word for word (the even-indexed words of v_buf and the first rows
+    # of v_ct are regenerated from the 32-byte seed), and it must still decode to the planted item
+    P = O.Params.named("T", expand_queries=False)
+    cl = O.Client(P, 717)
+    pp = cl.generate_keys()
+    idx = 23
+    q = cl.generate_query(idx)
+    qb = cl.query_bytes()
+    assert qb.size == P.query_bytes == 32 + (P.dim0 + P.nu_2 * 2 * P.t_gsw) * P.N * 8
+    q2 = P.query_deserialize_direct(qb)
+    assert np.array_equal(q2["v_buf"], q["v_buf"])
+    assert np.array_equal(q2["v_ct"], q["v_ct"])
+    db = P.generate_db(0xB1755)
+    assert np.array_equal(cl.decode_response(P.process_query(pp, q2, db)), P.db_plain_item(0xB1755, idx))
+
+
 def test_oracle_reproduces_golden_fixtures():
     # tests/golden/spiral_golden.json was frozen from this oracle after the KAT pinning; any drift shows up here
     import json
