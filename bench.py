@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--db-format", type=int, default=int(os.environ.get("B200PIR_BENCH_DB_FORMAT", "-1")),
                     help="-1 = the library's choice (tcgen05 tile images wherever supported), 0 = IMAD layout, "
                          "1 = mma.sync fragment order, 2 = tcgen05 tile images")
-    ap.add_argument("--fold-variant", type=int, default=1)
+    ap.add_argument("--fold-variant", type=int, default=2)
     ap.add_argument("--intt-variant", type=int, default=0)
     ap.add_argument("--imma-variant", type=int, default=0)
     ap.add_argument("--expand-variant", type=int, default=0)
@@ -330,6 +330,9 @@ def main():
                          "HBM-bound), 8 on the mma.sync path (its 16-query pass is bound by the legacy tensor pipe)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the concurrent-queries sweep (Q = 1, 32, 128; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="N > 1: skip the correctness check of the NCCL flow (every rank recomputes its own queries of the last step "
+                         "on an unsharded copy of the same database with the single-GPU path and compares the response bytes)")
     ap.add_argument("--steps-only", action="store_true",
                     help="profiling aid: skip the single-query latency probe and the e2e leg (clean ncu launch lists)")
     args = ap.parse_args()
@@ -573,6 +576,25 @@ def main():
         e2e_s = float(t.item())
     e2e_qps = B * e2e_steps / e2e_s
 
+    # ---- N > 1: correctness of the real multi-GPU run (the reference's model is chunked_end_to_end_test,
+    # lib/doublepir/src/doublepir/doublepir.rs:607-716: partial results combined, outcome compared).  Every rank holds the
+    # responses to ITS queries from the last step (d_out); it recomputes them on an UNSHARDED copy of the same synthetic
+    # database with the single-GPU path (itself checked against the oracle by tests/) and the bytes must be identical.
+    verified = None
+    if N > 1 and not args.no_verify:
+        step_dev()
+        torch.cuda.synchronize()
+        full = S.Database(G, shard_index=0, shard_count=1, fmt=args.db_format)
+        full.fill_synthetic(0xB1755)
+        d_ref = torch.zeros(Bl * rb, dtype=torch.uint8, device="cuda")
+        check(LIB.b200pir_process_query_batch_dev(G._h, full._h, gpp._h, d_q.data_ptr(), Bl, d_ref.data_ptr()))
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if torch.equal(d_ref, d_out) else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verified = bool(ok.item())
+        full.close()
+        del d_ref
+
     # ---- roofline of the dominant kernel (multiply_reg_by_database)
     mul_launches = max(int(stage["multiply_launches"]), 1)
     mul_ms = stage["multiply"] / mul_launches
@@ -636,6 +658,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
             "single_query_latency_ms": single_ms, "single_query_roofline": single_roofline,
             "concurrent_queries_sweep": sweep,
+            "verified": verified,
             "timed_region": "un-instrumented; stage_ms_per_step and roofline.kernel_ms come from a separate pass of the same steps "
                             "with per-stage CUDA events",
         }

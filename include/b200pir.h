@@ -213,6 +213,17 @@ unsigned long long b200pir_kernel_launches(void);
 int b200pir_dpir_create(int device, const uint32_t* a, uint64_t rows, uint64_t cols, b200pir_dpir** out);
 /* synthetic a: word(i,k) = low 30 bits of splitmix64(seed, i*cols+k) */
 int b200pir_dpir_create_synthetic(int device, uint64_t rows, uint64_t cols, uint64_t seed, b200pir_dpir** out);
+/* Offline setup (lib/doublepir/src/doublepir/doublepir.rs:76-108): h_1 = db.data * a_1 and h_2 = h_1' * a_2 as exact 8-bit limb
+ * products on the tcgen05 tensor cores (small signed left operand x 32-bit right operand, modulo 2^32), transpose / expand /
+ * concat_cols / squish as small kernels.  Host pointers.  db: l x m, entries centred in [-p/2, p/2) as wrapping u32, p <= 2^10;
+ * a1: m x n; a2: (l/x) x n; delta = params.delta(), x = db.info.x.  Outputs: db_squished l x ceil(m/3); h1_squished
+ * (n delta x) x ceil((l/x)/3); a2_t n x ((l/x) rounded up to a multiple of 3); h2 (n delta x) x n. */
+int b200pir_dpir_setup(int device, const uint32_t* db, uint64_t l, uint64_t m, const uint32_t* a1, uint64_t n, const uint32_t* a2,
+                       uint32_t p, uint64_t delta, uint64_t x, uint32_t* db_squished, uint32_t* h1_squished, uint32_t* a2_t,
+                       uint32_t* h2);
+/* `&Matrix * &Matrix` (matrix/ops.rs:169-191) on the same kernel: out (a_rows x b_cols) = a * b mod 2^32, entries of a in [-2^15, 2^15). */
+int b200pir_dpir_matmul(int device, const uint32_t* a, uint64_t a_rows, uint64_t a_cols, const uint32_t* b, uint64_t b_cols,
+                        uint32_t* out);
 void b200pir_dpir_destroy(b200pir_dpir* m);
 int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream);
 /* b: 3*cols u32 ; out: rows u32 */

@@ -456,6 +456,32 @@ int orc_dpir_transpose_expand_concat_cols_squish(uint32_t* out, const uint32_t* 
 
 // BASELINE config #5 at poly_len = 4096: the same scalar transforms / table construction instantiated at the larger size
 // (the reference's parameterisation stops at 2048, util.rs:246; both moduli are 1 mod 8192)
+// DoublePIR offline setup (doublepir.rs:76-108).  Outputs (caller-allocated): db_sq l x ceil(m/3); h1_sq (n delta x) x ceil((l/x)/3);
+// a2_t n x (l/x rounded up to a multiple of 3); h2 (n delta x) x n.
+int orc_dpir_setup(const uint32_t* db, size_t l, size_t m, const uint32_t* a1, size_t n, const uint32_t* a2, uint32_t p,
+                   size_t delta, size_t x, uint32_t* db_sq, uint32_t* h1_sq, uint32_t* a2_t, uint32_t* h2) {
+  ORC_TRY
+  dpir::Mat D(l, m), A1(m, n), A2(l / x, n);
+  std::memcpy(D.data.data(), db, l * m * 4);
+  std::memcpy(A1.data.data(), a1, m * n * 4);
+  std::memcpy(A2.data.data(), a2, (l / x) * n * 4);
+  dpir::SetupOut o = dpir::setup(D, A1, A2, p, delta, x);
+  std::memcpy(db_sq, o.db_squished.data.data(), o.db_squished.data.size() * 4);
+  std::memcpy(h1_sq, o.h1_squished.data.data(), o.h1_squished.data.size() * 4);
+  std::memcpy(a2_t, o.a2_t.data.data(), o.a2_t.data.size() * 4);
+  std::memcpy(h2, o.h2.data.data(), o.h2.data.size() * 4);
+  ORC_CATCH
+}
+int orc_dpir_mul(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t ar, size_t ac, size_t bc) {
+  ORC_TRY
+  dpir::Mat A(ar, ac), B(ac, bc);
+  std::memcpy(A.data.data(), a, ar * ac * 4);
+  std::memcpy(B.data.data(), b, ac * bc * 4);
+  dpir::Mat C = dpir::mul(A, B);
+  std::memcpy(out, C.data.data(), ar * bc * 4);
+  ORC_CATCH
+}
+
 int orc_ntt4096(uint64_t* polys, size_t count, int inverse) {
   ORC_TRY
   static const Params p4k = params_init(4096, {268369921ULL, 249561089ULL}, 6.4, 2, 256, 20, 4, 8, 8, 8, true, 6, 2, 1, 8192, 0);

@@ -17,13 +17,12 @@ PY
 }
 {
 echo "== new tests"
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tcgen05.py -x -q -k "different_clients or coalesced or direct_upload or error_behaviour or wire or tc5 or expansion or golden" 2>&1 | tail -3
-echo "== first dimension: barrier wait and stage size"
-run "spin wait, ksps 4" X=1 --
-run "spin wait, ksps 8" B200PIR_TC5_KSPS=8 --
-run "spin wait, ksps 2" B200PIR_TC5_KSPS=2 --
-run "hinted wait, ksps 4" B200PIR_TC5_DBG=4 --
-run "spin wait, no epilogue" B200PIR_TC5_DBG=2 --
-run "spin wait, no MMA" B200PIR_TC5_DBG=1 --
-run "fold lz 3/SM" X=1 -- --fold-variant 2
+timeout 900 python -m pytest tests/test_gpu_bench_config.py tests/test_gpu_tcgen05.py -x -q 2>&1 | tail -15
+echo "== first dimension with converged issue warps"
+run "ksps8 B1 A4 (default)" X=1 --
+run "ksps8 B2 A4" B200PIR_TC5_BBUFS=2 --
+run "ksps4 B1 A4" B200PIR_TC5_KSPS=4 --
+run "ksps4 B2 A2" B200PIR_TC5_KSPS=4 B200PIR_TC5_BBUFS=2 B200PIR_TC5_ABUFS=2 --
+run "no epilogue" B200PIR_TC5_DBG=2 --
+run "copy only" B200PIR_TC5_DBG=3 --
 } 2>&1 | tee gpurun_out/gpu_exp.log

@@ -78,6 +78,9 @@ def _load():
         "b200pir_dpir_create": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_create_synthetic": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_destroy": (None, [vp]),
+        "b200pir_dpir_setup": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, u32p, C.c_uint64, u32p, C.c_uint32, C.c_uint64,
+                                         C.c_uint64, u32p, u32p, u32p, u32p]),
+        "b200pir_dpir_matmul": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, u32p, C.c_uint64, u32p]),
         "b200pir_dpir_set_stream": (C.c_int, [vp, vp]),
         "b200pir_dpir_matvec_packed": (C.c_int, [vp, u32p, u32p]),
         "b200pir_dpir_matvec_packed_dev": (C.c_int, [vp, u32p, u32p, C.c_int]),

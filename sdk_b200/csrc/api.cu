@@ -92,7 +92,8 @@ struct b200pir_ctx {
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 16, profile = 0;  // max_group: queries per database pass (IMAD path: <= 4)
-  int fold_variant = 1;          // 1: k_fold_res at 3 CTAs/SM (80 registers); 0: 2 CTAs/SM (128 registers)
+  int fold_variant = 2;          // 2: relaxed-range transforms, 3 CTAs/SM (default); 3: same at 2 CTAs/SM; 4: twiddles in registers;
+                                 // 1 / 0: the per-butterfly-corrected kernel of round 1 at 3 / 2 CTAs per SM
   int intt_variant = 0;
   int expand_variant = 0;        // wide rounds: 0 paired + residue pipeline (3 CTAs/SM), 2 paired single kernel; 1: never paired
   long pair_min_ctas = 592;      // 4 x 148 SMs
@@ -1689,6 +1690,61 @@ int b200pir_dpir_create_synthetic(int device, uint64_t rows, uint64_t cols, uint
   cudaError_t e = cudaStreamSynchronize(m->stream);
   if (e != cudaSuccess) { b200pir_dpir_destroy(m); throw Error(B200PIR_E_CUDA, cudaGetErrorString(e)); }
   *out = m;
+  API_END
+}
+// doublepir.rs:76-108 setup(): both matrix products on the tensor cores (dpir_gemm.cu), the rest as small kernels.  Host pointers.
+int b200pir_dpir_setup(int device, const uint32_t* db, uint64_t l, uint64_t m, const uint32_t* a1, uint64_t n, const uint32_t* a2,
+                       uint32_t p, uint64_t delta, uint64_t x, uint32_t* db_squished, uint32_t* h1_squished, uint32_t* a2_t,
+                       uint32_t* h2) {
+  API_BEGIN
+  if (!db || !a1 || !a2 || !db_squished || !h1_squished || !a2_t || !h2) throw Error(B200PIR_E_BADARG, "null argument");
+  if (!l || !m || !n || !x || !delta || l % x) throw Error(B200PIR_E_SHAPE, "setup: l must be a positive multiple of x");
+  if (p < 2 || p > 1024) throw Error(B200PIR_E_UNSUPPORTED, "setup: p must be at most 2^10 (squish basis, database.rs:274)");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw Error(B200PIR_E_BADARG, "no such CUDA device (this library has no CPU path)");
+  B200_CUDA(cudaSetDevice(device));
+  cudaStream_t s = nullptr;
+  B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  try {
+    const size_t lx = l / x, rows1 = n * delta * x, lx3 = lx + (3 - lx % 3) % 3;
+    DevBuf<uint32_t> d_db(l * m), d_a1(m * n), d_a2(lx * n), d_h(l * n), d_hc(rows1 * lx), d_h2(rows1 * n);
+    DevBuf<uint32_t> d_dbsq(l * ((m + 2) / 3)), d_h1sq(rows1 * ((lx + 2) / 3)), d_a2t(n * lx3);
+    B200_CUDA(cudaMemcpyAsync(d_db.p, db, l * m * 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(d_a1.p, a1, m * n * 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(d_a2.p, a2, lx * n * 4, cudaMemcpyHostToDevice, s));
+    launch_dpir_gemm(d_h.p, d_db.p, d_a1.p, l, m, n, s);                                   // h_1 = db.data * a_1
+    launch_dpir_transpose_expand_concat(d_hc.p, d_h.p, l, n, p, (int)delta, x, s);        // transpose, expand, concat_cols
+    launch_dpir_gemm(d_h2.p, d_hc.p, d_a2.p, rows1, lx, n, s);                             // h_2 = h_1 * a_2
+    launch_dpir_add_squish(d_dbsq.p, d_db.p, l, m, p / 2, s);                              // db.data += p/2; db.squish()
+    launch_dpir_add_squish(d_h1sq.p, d_hc.p, rows1, lx, p / 2, s);                         // h_1 += p/2; squish
+    launch_dpir_pad_transpose(d_a2t.p, d_a2.p, lx, n, lx3, s);                             // a_2_copy
+    B200_CUDA(cudaMemcpyAsync(db_squished, d_dbsq.p, d_dbsq.n * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(h1_squished, d_h1sq.p, d_h1sq.n * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(a2_t, d_a2t.p, d_a2t.n * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(h2, d_h2.p, d_h2.n * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    B200_CUDA(cudaGetLastError());
+  } catch (...) { cudaStreamDestroy(s); throw; }
+  cudaStreamDestroy(s);
+  API_END
+}
+// &Matrix * &Matrix (matrix/ops.rs:169-191) for a left operand with small signed entries (|a| < 2^15): out = a * b mod 2^32
+int b200pir_dpir_matmul(int device, const uint32_t* a, uint64_t a_rows, uint64_t a_cols, const uint32_t* b, uint64_t b_cols,
+                        uint32_t* out) {
+  API_BEGIN
+  if (!a || !b || !out || !a_rows || !a_cols || !b_cols) throw Error(B200PIR_E_BADARG, "null or empty argument");
+  int ndev = 0;
+  B200_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw Error(B200PIR_E_BADARG, "no such CUDA device (this library has no CPU path)");
+  B200_CUDA(cudaSetDevice(device));
+  for (size_t i = 0; i < (size_t)a_rows * a_cols; i++)
+    if ((int32_t)a[i] < -32768 || (int32_t)a[i] > 32767) throw Error(B200PIR_E_UNSUPPORTED, "matmul: left operand entries must lie in [-2^15, 2^15)");
+  DevBuf<uint32_t> da(a_rows * a_cols), dbm(a_cols * b_cols), dc(a_rows * b_cols);
+  B200_CUDA(cudaMemcpy(da.p, a, da.n * 4, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(dbm.p, b, dbm.n * 4, cudaMemcpyHostToDevice));
+  launch_dpir_gemm(dc.p, da.p, dbm.p, a_rows, a_cols, b_cols, nullptr);
+  B200_CUDA(cudaMemcpy(out, dc.p, dc.n * 4, cudaMemcpyDeviceToHost));
   API_END
 }
 void b200pir_dpir_destroy(b200pir_dpir* m) {

@@ -183,4 +183,16 @@ void launch_dpir_mul_transposed(uint32_t* out, const uint32_t* a, const uint32_t
 void launch_dpir_transpose_expand(uint32_t* out, const uint32_t* a, size_t rows, size_t cols, uint64_t modulus, size_t delta,
                                   size_t concat, size_t out_rows, size_t out_cols, cudaStream_t s);
 
+// ---- DoublePIR offline setup (dpir_gemm.cu): doublepir.rs:76-108
+// c (rows x n_cols) = a (rows x k_dim, entries in [-2^15, 2^15) as wrapping u32) * b (k_dim x n_cols) mod 2^32; device pointers;
+// 8-bit limb products on the tcgen05 tensor cores (exact); synchronises the stream
+void launch_dpir_gemm(uint32_t* c, const uint32_t* a, const uint32_t* b, size_t rows, size_t k_dim, size_t n_cols, cudaStream_t s);
+// transpose + expand (contract.rs:62-78) + concat_cols (indexing.rs:82-101): h (l x n) -> out ((n delta x) x (l / x)), centred digits
+void launch_dpir_transpose_expand_concat(uint32_t* out, const uint32_t* h, size_t l, size_t n, uint32_t p, int delta, size_t x,
+                                         cudaStream_t s);
+// squish(m + add), three 10-bit values per word (squish.rs:52-70)
+void launch_dpir_add_squish(uint32_t* out, const uint32_t* m, size_t rows, size_t cols, uint32_t add, cudaStream_t s);
+// rows padded with zeros to rows3, then transposed (doublepir.rs:96-100)
+void launch_dpir_pad_transpose(uint32_t* out, const uint32_t* a, size_t rows, size_t cols, size_t rows3, cudaStream_t s);
+
 }  // namespace b200pir

@@ -535,7 +535,9 @@ __device__ __forceinline__ uint32_t digit_diff(uint64_t vh, uint64_t vi, int k, 
 // Same step as k_fold_res on the relaxed-range transforms (ntt_core.cuh "lz"): no per-butterfly range correction in the
 // forward transforms (outputs < 16q feed the 64-bit multiply-accumulate directly: 16 products of < 2^32 x < 2^28 fit),
 // no halving in the inverse transform, byte-permute digit extraction when bits_per = 8, 32-bit Barrett in the CRT lift.
-template <int MINB, bool BYTE>
+// REGTW: the forward transforms' pass C / D twiddles live in registers (TwRegsC / TwRegsD) instead of a shared-memory copy of
+// the table: 26 more registers, so it runs at 2 CTAs per SM (128 registers), with 18 KiB instead of 34 KiB of shared memory.
+template <int MINB, bool BYTE, bool REGTW>
 __global__ void __launch_bounds__(256, MINB)
 k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
               const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
@@ -560,8 +562,11 @@ k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict
   uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
   Twiddle* tw = reinterpret_cast<Twiddle*>(sm1 + NTT_SMEM_WORDS);
   Grp g = make_grp_single(P, sm0, blockIdx.y);
-  stage_fwd_twiddles(g, tw);
   const TwConst lo{g.n, 0};
+  TwRegsC rc;
+  TwRegsD rd;
+  if (REGTW) { rc.load(g.tid, TwGlobal{g.fwd}); rd.load(g.tid, TwGlobal{g.fwd}); }
+  else stage_fwd_twiddles(g, tw);
   const TwShared hi{tw};
   const int b = blockIdx.x / half, i = blockIdx.x % half;
   const uint32_t* ci = in + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
@@ -597,7 +602,8 @@ k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict
         x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
         x1[a] = digit_diff<BYTE>(vh[a], vi[a], k + 1, bits, mask, q);
       }
-      ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
+      if (REGTW) ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, rc, rd, q, CtaSync());
+      else ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
       if (cnt + 2 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
       cnt += 2;
 #pragma unroll
@@ -615,7 +621,8 @@ k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict
       uint32_t x0[8];
 #pragma unroll
       for (int a = 0; a < 8; a++) x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
-      ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, hi, q, CtaSync());
+      if (REGTW) ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, rc, rd, q, CtaSync());
+      else ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, hi, q, CtaSync());
       if (cnt + 1 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
       cnt += 1;
 #pragma unroll
@@ -1322,16 +1329,18 @@ void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size
   }
   ++g_kernel_launches;
   // variant 2 (default): relaxed-range transforms, 3 CTAs per SM; 3: the same at 2 CTAs per SM
-  if (variant == 2 || variant == 3) {
+  if (variant >= 2 && variant <= 4) {
     const dim3 grid((unsigned)(batch * half), 2);
-#define FOLD_LZ(MINB, BYTE)                                                                                             \
+#define FOLD_LZ(MINB, BYTE, REGTW)                                                                                      \
     do {                                                                                                                \
-      opt_in_smem(k_fold_res_lz<MINB, BYTE>, (int)kDynSmemFold);                                                        \
-      k_fold_res_lz<MINB, BYTE><<<grid, 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos, c_batch_stride,  \
-                                                               slices_per_query, t_gsw, bits, zero_flags);             \
+      const size_t smem = REGTW ? (size_t)(2 * NTT_SMEM_WORDS) * 4 : kDynSmemFold;                                      \
+      opt_in_smem(k_fold_res_lz<MINB, BYTE, REGTW>, (int)smem);                                                         \
+      k_fold_res_lz<MINB, BYTE, REGTW><<<grid, 256, smem, s>>>(P, in, out, batch_stride, half, c_pos, c_batch_stride,   \
+                                                              slices_per_query, t_gsw, bits, zero_flags);              \
     } while (0)
-    if (variant == 2) { if (bits == 8) FOLD_LZ(3, true); else FOLD_LZ(3, false); }
-    else { if (bits == 8) FOLD_LZ(2, true); else FOLD_LZ(2, false); }
+    if (variant == 2) { if (bits == 8) FOLD_LZ(3, true, false); else FOLD_LZ(3, false, false); }
+    else if (variant == 3) { if (bits == 8) FOLD_LZ(2, true, false); else FOLD_LZ(2, false, false); }
+    else { if (bits == 8) FOLD_LZ(2, true, true); else FOLD_LZ(2, false, true); }       // 4: twiddles in registers, 2 CTAs per SM
 #undef FOLD_LZ
     return;
   }

@@ -29,6 +29,7 @@
 // of the TMEM loads, shuffles and wide multiplies).  Pipelines: A ring (full/empty mbarriers), double-buffered B operand
 // (bfull/bempty), double-buffered accumulator in TMEM (tfull/tempty).
 #include "kernels.h"
+#include "tc5_ptx.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -37,105 +38,12 @@ namespace b200pir {
 
 namespace {
 
-constexpr int TC5_RING_BYTES = 96 * 1024;               // database tiles in flight per SM (ring of KSPS-k-step stages)
+constexpr int TC5_SMEM_BUDGET = 227 * 1024 - 1024;      // dynamic shared memory of the CTA minus barriers / alignment slack
 constexpr int TC5_EPI_WARPS = 8;
 constexpr int TC5_THREADS = 64 + 32 * TC5_EPI_WARPS;    // producer warp, MMA warp, epilogue warps
-constexpr int TC5_TMEM_COLS = 256;                      // two accumulator buffers of 128 columns
 constexpr int TC5_DBG_TILES = 4;
 
-// ---- raw PTX wrappers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-// Bounded wait: a protocol error must surface as a launch failure (trap), never as a hung GPU.  Plain try_wait in a spin loop
-// (no suspend-time hint: a hinted wait may park the thread for long quanta, and every stage hand-off of the pipeline goes
-// through one of these); the bound is on elapsed clocks (~20 s), checked every 1024 polls.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t tries = 0;; tries++) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((tries & 1023u) == 1023u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 40000000000ll) asm volatile("trap;");
-    }
-  }
-}
-// the previous form (1 ms suspend-time hint per try), kept selectable for A/B measurements (dbg_mode bit 2)
-__device__ __forceinline__ void mbar_wait_hinted(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (int tries = 0; tries < 20000; tries++) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0xF4240;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  asm volatile("trap;");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(tc5_instr_desc()), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// 32 lanes x 32 consecutive columns: thread t of the warp gets row (quadrant base + t)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
-        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
-        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
-  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
-  return ((uint64_t)hi << 32) | lo;
-}
+using namespace tc5;
 
 // ---- operand images ---------------------------------------------------------------------------------------------------
 // format 0 slice (uint4 [row][jp][z]) -> tile images.  CTA = (z, mt, ks); thread = (row_local, group of 4 values of j).
@@ -206,14 +114,22 @@ constexpr int TC5_MAX_STAGES = 24;
 struct Tc5Smem {
   uint64_t full[TC5_MAX_STAGES], empty[TC5_MAX_STAGES];
   uint64_t bfull[2], bempty[2];
-  uint64_t tfull[2], tempty[2];
+  uint64_t tfull[4], tempty[4];
   uint32_t tmem_base;
 };
+// ring stages that fit beside the query operand: the bytes in flight per SM bound the HBM bandwidth the kernel can pull
+// (latency x bandwidth = about 90 KiB per SM at 6.5 TB/s and 2 us), and a stage is out of flight while its MMAs run
+__host__ __device__ inline int tc5_ring_stages(int ks, int ksps, int bbufs) {
+  const int n = (TC5_SMEM_BUDGET - bbufs * ks * TC5_TILE) / (ksps * TC5_TILE);
+  return n > TC5_MAX_STAGES ? TC5_MAX_STAGES : n;
+}
 
 // out_zm[query][slice][n][z][row][ct_row] (u32), the format of k_multiply_imma
 // KSPS = k-steps (4 KiB tiles) per ring stage.  dbg_mode (bring-up / bottleneck analysis only, B200PIR_TC5_DBG): bit 0 = the MMA
 // thread releases every stage without issuing MMAs, bit 1 = the epilogue warps release the accumulators without reading them.
-template <int KSPS>
+// BBUFS: buffers of the query operand (2 = the next (n, z) pair's operand loads under the current pair's MMAs; 1 = its 64 KiB go
+// to the database ring instead, at the price of a reload bubble per pair).  ABUFS: accumulator buffers in TMEM (128 columns each).
+template <int KSPS, int BBUFS, int ABUFS>
 __global__ void __launch_bounds__(TC5_THREADS, 1)
 k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const uint8_t* __restrict__ qt,
                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count,
@@ -223,11 +139,11 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
 #define mbar_wait(bar, par) do { if (hinted) mbar_wait_hinted(bar, par); else (mbar_wait)(bar, par); } while (0)
   constexpr int TC5_KS_PER_STAGE = KSPS;
   constexpr int TC5_STAGE_BYTES = KSPS * TC5_TILE;
-  constexpr int TC5_STAGES = TC5_RING_BYTES / TC5_STAGE_BYTES;
-  static_assert(TC5_STAGES <= TC5_MAX_STAGES, "ring too long");
+  constexpr int TC5_TMEM_COLS = ABUFS * TC5_N;
+  const int TC5_STAGES = tc5_ring_stages(T.ks, KSPS, BBUFS);
   extern __shared__ __align__(1024) uint8_t tc5_smem[];
-  uint8_t* smem_b = tc5_smem;                                         // [2][ks][4096]
-  uint8_t* smem_a = smem_b + (size_t)2 * T.ks * TC5_TILE;             // [STAGES][16 KiB]
+  uint8_t* smem_b = tc5_smem;                                         // [BBUFS][ks][4096]
+  uint8_t* smem_a = smem_b + (size_t)BBUFS * T.ks * TC5_TILE;         // [STAGES][KSPS x 4 KiB]
   Tc5Smem* S = reinterpret_cast<Tc5Smem*>(smem_a + (size_t)TC5_STAGES * TC5_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages_per_tile = (T.ks + TC5_KS_PER_STAGE - 1) / TC5_KS_PER_STAGE;
@@ -237,10 +153,8 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC5_STAGES; s++) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
-    for (int b = 0; b < 2; b++) {
-      mbar_init(&S->bfull[b], 1); mbar_init(&S->bempty[b], 1);
-      mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], TC5_EPI_WARPS);
-    }
+    for (int b = 0; b < 2; b++) { mbar_init(&S->bfull[b], 1); mbar_init(&S->bempty[b], 1); }
+    for (int b = 0; b < 4; b++) { mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], TC5_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                                                    // TMEM allocation is owned by the MMA warp
@@ -254,63 +168,83 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
   tc_fence_after();
   const uint32_t tmem_base = S->tmem_base;
 
+  // The producer and MMA warps run their loops CONVERGED (all 32 lanes, warp-uniform values); only the asynchronous
+  // instructions themselves are issued by one elected lane.  (Issuing from inside an `if (lane == 0)` region makes every
+  // operand of UBLKCP / UTCIMMA / UTCBAR a per-thread value: ptxas then wraps each of them in an ELECT / R2UR serialisation
+  // loop, and the single MMA thread needs ~140 clocks per 64-clock MMA — measured, profiles/ncu_tc5_r02a_source.md.)
   if (warp == 0) {
-    // ===== producer: one thread issues every bulk copy =====
-    if (lane == 0) {
-      int stage = 0; uint32_t sphase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        const int n = item & 1, z = item >> 1, bb = it & 1;
-        mbar_wait(&S->bempty[bb], ((it >> 1) & 1) ^ 1);
+    // ===== producer =====
+    int stage = 0; uint32_t sphase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int n = item & 1, z = item >> 1, bb = it % BBUFS;
+      mbar_wait(&S->bempty[bb], ((it / BBUFS) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&S->bfull[bb], b_bytes);
         bulk_g2s(smem_b + (size_t)bb * b_bytes, qt + tc5_q_tile(T, n, z, 0) * TC5_TILE, b_bytes, &S->bfull[bb]);
-        for (int t = 0; t < tiles_per_item; t++) {
-          const int slice = slice_begin + t / T.mt, mt = t % T.mt;
-          const uint8_t* src = dbt + tc5_db_tile(T, slice, n, z, mt, 0) * TC5_TILE;
+      }
+      __syncwarp();
+      for (int sl = 0; sl < slice_count; sl++)
+        for (int mt = 0; mt < T.mt; mt++) {
+          const uint8_t* src = dbt + tc5_db_tile(T, slice_begin + sl, n, z, mt, 0) * TC5_TILE;
           for (int st = 0; st < stages_per_tile; st++) {
             const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
             mbar_wait(&S->empty[stage], sphase ^ 1);
-            mbar_expect_tx(&S->full[stage], (uint32_t)ks_here * TC5_TILE);
-            bulk_g2s(smem_a + (size_t)stage * TC5_STAGE_BYTES, src + (size_t)st * TC5_STAGE_BYTES, (uint32_t)ks_here * TC5_TILE,
-                     &S->full[stage]);
+            if (elect_one()) {
+              mbar_expect_tx(&S->full[stage], (uint32_t)ks_here * TC5_TILE);
+              bulk_g2s(smem_a + (size_t)stage * TC5_STAGE_BYTES, src + (size_t)st * TC5_STAGE_BYTES, (uint32_t)ks_here * TC5_TILE,
+                       &S->full[stage]);
+            }
+            __syncwarp();
             if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
           }
         }
-      }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
-      int stage = 0; uint32_t sphase = 0;
-      int it = 0, tile_no = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        const int bb = it & 1;
-        mbar_wait(&S->bfull[bb], (it >> 1) & 1);
-        const uint32_t b_addr = smem_u32(smem_b + (size_t)bb * b_bytes);
-        for (int t = 0; t < tiles_per_item; t++, tile_no++) {
-          const int ab = tile_no & 1;
-          mbar_wait(&S->tempty[ab], ((tile_no >> 1) & 1) ^ 1);
+    // ===== MMA issuer =====
+    int stage = 0; uint32_t sphase = 0;
+    int it = 0, tile_no = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      const int bb = it % BBUFS;
+      mbar_wait(&S->bfull[bb], (it / BBUFS) & 1);
+      const uint32_t b_addr = smem_u32(smem_b + (size_t)bb * b_bytes);
+      for (int t = 0; t < tiles_per_item; t++, tile_no++) {
+        const int ab = tile_no % ABUFS;
+        mbar_wait(&S->tempty[ab], ((tile_no / ABUFS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)ab * TC5_N;
+        for (int st = 0; st < stages_per_tile; st++) {
+          const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
+          mbar_wait(&S->full[stage], sphase);
           tc_fence_after();
-          const uint32_t d_addr = tmem_base + (uint32_t)ab * TC5_N;
-          for (int st = 0; st < stages_per_tile; st++) {
-            const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
-            mbar_wait(&S->full[stage], sphase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
-            if (dbg_mode & 1) { mbar_arrive(&S->empty[stage]); if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; } continue; }
-            for (int kk = 0; kk < ks_here; kk++) {
-              const int ks = st * TC5_KS_PER_STAGE + kk;
-              tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
+          if (elect_one()) {
+            if (dbg_mode & 1) mbar_arrive(&S->empty[stage]);
+            else {
+#pragma unroll
+              for (int kk = 0; kk < TC5_KS_PER_STAGE; kk++) {
+                if (kk < ks_here) {
+                  const int ks = st * TC5_KS_PER_STAGE + kk;
+                  tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
+                }
+              }
+              tc_commit(&S->empty[stage]);                            // frees the A stage when these MMAs have completed
             }
-            tc_commit(&S->empty[stage]);                              // frees the A stage when these MMAs have completed
-            if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
+        }
+        if (elect_one()) {
           if (dbg_mode & 1) mbar_arrive(&S->tfull[ab]);
           else tc_commit(&S->tfull[ab]);                              // accumulator ready for the epilogue
         }
+        __syncwarp();
+      }
+      if (elect_one()) {
         if (dbg_mode & 1) mbar_arrive(&S->bempty[bb]);
         else tc_commit(&S->bempty[bb]);                               // every MMA reading this B buffer has completed
       }
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
@@ -321,26 +255,34 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
       const int n = item & 1, z = item >> 1;
       const uint32_t q = n ? P.q[1] : P.q[0];
       const Tc5Weights W = tc5_lane_weights(l, q);
-      for (int t = 0; t < tiles_per_item; t++, tile_no++) {
-        const int slice = slice_begin + t / T.mt, mt = t % T.mt;
-        const int ab = tile_no & 1;
-        mbar_wait(&S->tfull[ab], (tile_no >> 1) & 1);
+      for (int t = 0, slice = slice_begin, mt = 0; t < tiles_per_item; t++, tile_no++, mt++) {
+        if (mt == T.mt) { mt = 0; slice++; }
+        const int ab = tile_no % ABUFS;
+        mbar_wait(&S->tfull[ab], (tile_no / ABUFS) & 1);
         tc_fence_after();
         const int ii = mt * 32 + tc5_lane_row(quad, lane);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * TC5_N;
-#pragma unroll
-        for (int ch = 0; ch < ((dbg_mode & 2) ? 0 : 2); ch++) {                              // 32 TMEM columns = 8 GEMM columns = 4 queries
-          const int chunk = colhalf * 2 + ch;
-          uint32_t v[32];
-          tc_ld32(taddr + chunk * 32, v);
+        // both 32-column chunks of this warp go to registers first, so the accumulator buffer is released after the TMEM
+        // load latency, not after the arithmetic: the MMA of a later tile never waits for epilogue math
+        uint32_t v[2][32];
+        if (!(dbg_mode & 2)) {
+          tc_ld32(taddr + (colhalf * 2 + 0) * 32, v[0]);
+          tc_ld32(taddr + (colhalf * 2 + 1) * 32, v[1]);
           tc_wait_ld();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->tempty[ab]);                   // this warp has drained its part of the accumulator
+#pragma unroll
+        for (int ch = 0; ch < ((dbg_mode & 2) ? 0 : 2); ch++) {       // 32 TMEM columns = 8 GEMM columns = 4 queries
+          const int chunk = colhalf * 2 + ch;
           if (dbg && blockIdx.x == 0 && tile_no < TC5_DBG_TILES) {
 #pragma unroll
-            for (int c = 0; c < 32; c++) dbg[((size_t)tile_no * TC5_M + quad * 32 + lane) * TC5_N + chunk * 32 + c] = v[c];
+            for (int c = 0; c < 32; c++) dbg[((size_t)tile_no * TC5_M + quad * 32 + lane) * TC5_N + chunk * 32 + c] = v[ch][c];
           }
           uint64_t part[8], send4[4], keep4[4], send2[2], keep2[2];
 #pragma unroll
-          for (int c = 0; c < 8; c++) part[c] = tc5_lane_partial(v + 4 * c, W.w, W.wp);   // < 2^53
+          for (int c = 0; c < 8; c++) part[c] = tc5_lane_partial(v[ch] + 4 * c, W.w, W.wp);   // < 2^53
           tc5_rs_select_a(l, part, send4, keep4);
 #pragma unroll
           for (int i = 0; i < 4; i++) keep4[i] += shfl_xor_u64(send4[i], 2);
@@ -355,9 +297,6 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
             *reinterpret_cast<uint2*>(dst) = r;
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S->tempty[ab]);                   // this warp has drained its part of the accumulator
       }
     }
   }
@@ -374,10 +313,11 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
 
 size_t tc5_db_bytes(const Tc5Geom& T, int slices) { return (size_t)slices * 2 * POLY * T.mt * T.ks * TC5_TILE; }
 size_t tc5_query_bytes(const Tc5Geom& T) { return (size_t)2 * POLY * T.ks * TC5_TILE; }
-static size_t tc5_smem_bytes(const Tc5Geom& T) {
-  return (size_t)2 * T.ks * TC5_TILE + (size_t)TC5_RING_BYTES + sizeof(Tc5Smem) + 16;
+static size_t tc5_smem_bytes(const Tc5Geom& T, int ksps, int bbufs) {
+  return (size_t)bbufs * T.ks * TC5_TILE + (size_t)tc5_ring_stages(T.ks, ksps, bbufs) * ksps * TC5_TILE + sizeof(Tc5Smem) + 16;
 }
-bool tc5_supported(const Tc5Geom& T) { return T.dim0 % 2 == 0 && tc5_smem_bytes(T) <= 227 * 1024; }
+// at least two ring stages beside a single-buffered query operand
+bool tc5_supported(const Tc5Geom& T) { return T.dim0 % 2 == 0 && tc5_ring_stages(T.ks, 4, 1) >= 2; }
 
 void launch_db_to_tc5(const Tc5Geom& T, const uint4* db0_slice, uint8_t* dbt, int slice, cudaStream_t s) {
   ++g_kernel_launches;
@@ -396,7 +336,6 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
                          size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s) {
   if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
   if (!tc5_supported(T)) throw Error(-2, "tcgen05 multiply: dim0 too large for one CTA's shared memory");
-  const size_t smem = tc5_smem_bytes(T);
   ++g_kernel_launches;
   const int grid = sm_count > 0 ? (sm_count < 2 * POLY ? sm_count : 2 * POLY) : 148;
   // bring-up aid (scripts/tc5_probe.py): B200PIR_TC5_DUMP=<file> receives the raw s32 accumulators D[M][N] of the first
@@ -409,14 +348,23 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
     B200_CUDA(cudaMemsetAsync(dbg, 0xFF, dbg_words * 4, s));
   }
   static const int dbg_mode = getenv("B200PIR_TC5_DBG") ? atoi(getenv("B200PIR_TC5_DBG")) : 0;     // analysis only: wrong results
-  static const int ksps = getenv("B200PIR_TC5_KSPS") ? atoi(getenv("B200PIR_TC5_KSPS")) : 4;
-#define TC5_LAUNCH(K)                                                                                                          \
+  static const int ksps_env = getenv("B200PIR_TC5_KSPS") ? atoi(getenv("B200PIR_TC5_KSPS")) : 8;
+  static const int bbufs_env = getenv("B200PIR_TC5_BBUFS") ? atoi(getenv("B200PIR_TC5_BBUFS")) : 2;
+  static const int abufs = getenv("B200PIR_TC5_ABUFS") ? atoi(getenv("B200PIR_TC5_ABUFS")) : 4;
+  int ksps = ksps_env == 4 ? 4 : 8, bbufs = bbufs_env == 2 ? 2 : 1;
+  if (tc5_ring_stages(T.ks, ksps, bbufs) < 2) ksps = 4;                  // large dim0: smaller stages,
+  if (tc5_ring_stages(T.ks, ksps, bbufs) < 2) bbufs = 1;                 // single-buffered operand
+  const size_t smem = tc5_smem_bytes(T, ksps, bbufs);
+#define TC5_LAUNCH(K, B, A)                                                                                                    \
   do {                                                                                                                         \
-    opt_in_smem(k_multiply_tc5<K>, 227 * 1024);                                                                                \
-    k_multiply_tc5<K><<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count, dbg,   \
-                                                      dbg_mode);                                                               \
+    opt_in_smem(k_multiply_tc5<K, B, A>, 227 * 1024);                                                                          \
+    k_multiply_tc5<K, B, A><<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count,   \
+                                                            dbg, dbg_mode);                                                    \
   } while (0)
-  if (ksps == 1) TC5_LAUNCH(1); else if (ksps == 2) TC5_LAUNCH(2); else if (ksps == 8) TC5_LAUNCH(8); else TC5_LAUNCH(4);
+#define TC5_PICK_A(K, B) do { if (abufs == 2) TC5_LAUNCH(K, B, 2); else TC5_LAUNCH(K, B, 4); } while (0)
+  if (ksps == 4) { if (bbufs == 2) TC5_PICK_A(4, 2); else TC5_PICK_A(4, 1); }
+  else { if (bbufs == 2) TC5_PICK_A(8, 2); else TC5_PICK_A(8, 1); }
+#undef TC5_PICK_A
 #undef TC5_LAUNCH
   if (dump) {
     std::vector<uint32_t> host(dbg_words);

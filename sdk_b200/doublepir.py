@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import LIB, check
+from ._lib import LIB, check, B200PirError  # noqa: F401
 
 
 class PackedMatrix:
@@ -92,3 +92,35 @@ def answer(db, queries, h_1, a_2_transpose, p, delta, x, ne):
     hm.close()
     am.close()
     return msg
+
+
+def matmul(a, b, device=0):
+    """`&Matrix * &Matrix` (matrix/ops.rs:169-191), wrapping u32, for a left operand with small signed entries (|a| < 2^15):
+    exact 8-bit limb products on the tensor cores."""
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError("a.cols %r b.rows %r" % (a.shape, b.shape))
+    out = np.zeros((a.shape[0], b.shape[1]), dtype=np.uint32)
+    check(LIB.b200pir_dpir_matmul(device, a.ctypes.data, a.shape[0], a.shape[1], b.ctypes.data, b.shape[1], out.ctypes.data))
+    return out
+
+
+def setup(db, a1, a2, p, delta, x, device=0):
+    """doublepir.rs:76-108 setup(): returns dict(db_squished, h1_squished, a2_t, h2) = (server_state pieces, hint).
+    db: l x m with entries centred in [-p/2, p/2) (wrapping u32); a1: m x n; a2: (l/x) x n."""
+    db = np.ascontiguousarray(db, dtype=np.uint32)
+    a1 = np.ascontiguousarray(a1, dtype=np.uint32)
+    a2 = np.ascontiguousarray(a2, dtype=np.uint32)
+    l, m = db.shape
+    n = a1.shape[1]
+    if a1.shape[0] != m or a2.shape != (l // x, n) or l % x:
+        raise ValueError("shapes: db (l, m), a1 (m, n), a2 (l/x, n)")
+    lx = l // x
+    rows1 = n * delta * x
+    out = dict(db_squished=np.zeros((l, (m + 2) // 3), dtype=np.uint32), h1_squished=np.zeros((rows1, (lx + 2) // 3), dtype=np.uint32),
+               a2_t=np.zeros((n, lx + (3 - lx % 3) % 3), dtype=np.uint32), h2=np.zeros((rows1, n), dtype=np.uint32))
+    check(LIB.b200pir_dpir_setup(device, db.ctypes.data, l, m, a1.ctypes.data, n, a2.ctypes.data, p, delta, x,
+                                 out["db_squished"].ctypes.data, out["h1_squished"].ctypes.data, out["a2_t"].ctypes.data,
+                                 out["h2"].ctypes.data))
+    return out

@@ -397,6 +397,28 @@ def dpir_matvec_packed(a, b, rows, cols):
     return out
 
 
+def dpir_mul(a, b, ar, ac, bc):
+    """matrix/ops.rs:169-191 (wrapping u32): (ar x ac) * (ac x bc)."""
+    out = np.zeros(ar * bc, dtype=np.uint32)
+    _ck(LIB.orc_dpir_mul(_p32(out), _p32(np.ascontiguousarray(a, dtype=np.uint32)), _p32(np.ascontiguousarray(b, dtype=np.uint32)),
+                         C.c_size_t(ar), C.c_size_t(ac), C.c_size_t(bc)))
+    return out.reshape(ar, bc)
+
+
+def dpir_setup(db, l, m, a1, n, a2, p, delta, x):
+    """doublepir.rs:76-108.  db: l x m centered entries; a1: m x n; a2: (l/x) x n.  Returns dict(db_sq, h1_sq, a2_t, h2)."""
+    rows1 = n * delta * x
+    lx = l // x
+    lx3 = lx + (3 - lx % 3) % 3
+    out = dict(db_sq=np.zeros((l, (m + 2) // 3), dtype=np.uint32), h1_sq=np.zeros((rows1, (lx + 2) // 3), dtype=np.uint32),
+               a2_t=np.zeros((n, lx3), dtype=np.uint32), h2=np.zeros((rows1, n), dtype=np.uint32))
+    _ck(LIB.orc_dpir_setup(_p32(np.ascontiguousarray(db, dtype=np.uint32)), C.c_size_t(l), C.c_size_t(m),
+                           _p32(np.ascontiguousarray(a1, dtype=np.uint32)), C.c_size_t(n),
+                           _p32(np.ascontiguousarray(a2, dtype=np.uint32)), C.c_uint32(p), C.c_size_t(delta), C.c_size_t(x),
+                           _p32(out["db_sq"]), _p32(out["h1_sq"]), _p32(out["a2_t"]), _p32(out["h2"])))
+    return out
+
+
 def dpir_matrix_mul_transposed_packed(a, b, a_rows, a_cols, b_rows, b_cols):
     out = np.zeros(a_rows * b_rows, dtype=np.uint32)
     _ck(LIB.orc_dpir_matrix_mul_transposed_packed(_p32(out), _p32(a), _p32(b), C.c_size_t(a_rows), C.c_size_t(a_cols),

@@ -138,6 +138,34 @@ def test_direct_upload_wire_format_round_trip():
     assert np.array_equal(cl.decode_response(P.process_query(pp, q2, db)), P.db_plain_item(0xB1755, idx))
 
 
+def test_dpir_setup_restatement_against_its_definition():
+    # doublepir.rs:76-108: the oracle's setup() against an independent numpy evaluation of the same definition
+    # (h_1 = db a_1; transpose; base-p digits centred; concat_cols(x); h_2 = h_1 a_2; squish with 3 x 10 bits)
+    rng = np.random.default_rng(1)
+    l, m, n, p, delta, x = 24, 20, 8, 929, 4, 2
+    db = (rng.integers(0, p, (l, m)).astype(np.int64) - p // 2).astype(np.uint32)
+    a1 = rng.integers(0, 2**32, (m, n), dtype=np.uint64).astype(np.uint32)
+    a2 = rng.integers(0, 2**32, (l // x, n), dtype=np.uint64).astype(np.uint32)
+    o = O.dpir_setup(db, l, m, a1, n, a2, p, delta, x)
+    h1 = ((db.astype(np.uint64) @ a1.astype(np.uint64)) & 0xFFFFFFFF).T.copy()
+    ex = np.zeros((n * delta, l), dtype=np.uint64)
+    v = h1.copy()
+    for f in range(delta):
+        ex[f::delta] = ((v % p) - p // 2) & 0xFFFFFFFF
+        v //= p
+    cc = np.zeros((n * delta * x, l // x), dtype=np.uint64)
+    for j in range(l):
+        cc[np.arange(n * delta) + n * delta * (j % x), j // x] = ex[:, j]
+    assert np.array_equal(((cc @ a2.astype(np.uint64)) & 0xFFFFFFFF).astype(np.uint32), o["h2"])
+    raw = (cc + p // 2) & 0xFFFFFFFF
+    sq = np.zeros((n * delta * x, (l // x + 2) // 3), dtype=np.uint64)
+    for k in range(l // x):
+        sq[:, k // 3] += raw[:, k] << (10 * (k % 3))
+    assert np.array_equal((sq & 0xFFFFFFFF).astype(np.uint32), o["h1_sq"])
+    assert np.array_equal(o["a2_t"][:, : l // x], a2.T) and not o["a2_t"][:, l // x:].any()
+    assert np.array_equal(O.dpir_mul(db, a1, l, m, n), ((db.astype(np.uint64) @ a1.astype(np.uint64)) & 0xFFFFFFFF).astype(np.uint32))
+
+
 def test_oracle_reproduces_golden_fixtures():
     # tests/golden/spiral_golden.json was frozen from this oracle after the KAT pinning; any drift shows up here
     import json

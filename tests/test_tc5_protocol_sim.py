@@ -1,5 +1,5 @@
 """Discrete-event simulation of the barrier protocol of k_multiply_tc5 (sdk_b200/csrc/tc5_kernels.cu): the three roles
-(bulk-copy producer, MMA issuer, four epilogue warps) are transcribed loop for loop as coroutines over a model of
+(bulk-copy producer, MMA issuer, eight epilogue warps) are transcribed loop for loop as coroutines over a model of
 mbarrier phases / transaction counts, with randomised completion delays for the asynchronous agents (bulk copies,
 tcgen05.commit arrivals).  Checked: the run terminates (no deadlock), no shared-memory stage / B buffer / TMEM buffer is
 overwritten before its readers are done, nothing is read before it has been written, and no barrier ever runs two
@@ -10,8 +10,7 @@ import random
 
 import pytest
 
-STAGES = 5
-KS_PER_STAGE = 4
+EPI_WARPS = 8
 
 
 class Bar:
@@ -42,12 +41,14 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def simulate(n_items, tiles_per_item, ks, seed):
+def simulate(n_items, tiles_per_item, ks, seed, STAGES=5, KS_PER_STAGE=4, BBUFS=2, ABUFS=2):
+    """STAGES ring stages of KS_PER_STAGE k-steps, BBUFS buffers of the query operand, ABUFS accumulator buffers: the template /
+    run-time parameters of k_multiply_tc5."""
     rng = random.Random(seed)
     full = [Bar(1) for _ in range(STAGES)]
     empty = [Bar(1) for _ in range(STAGES)]
-    bfull, bempty = [Bar(1), Bar(1)], [Bar(1), Bar(1)]
-    tfull, tempty = [Bar(1), Bar(1)], [Bar(4), Bar(4)]
+    bfull, bempty = [Bar(1) for _ in range(BBUFS)], [Bar(1) for _ in range(BBUFS)]
+    tfull, tempty = [Bar(1) for _ in range(ABUFS)], [Bar(EPI_WARPS) for _ in range(ABUFS)]
     stages_per_tile = (ks + KS_PER_STAGE - 1) // KS_PER_STAGE
     now = [0.0]
     events = []                      # (time, seq, fn)
@@ -60,8 +61,8 @@ def simulate(n_items, tiles_per_item, ks, seed):
     # ground truth for the hazard checks
     a_content = [None] * STAGES      # (item, tile, st) the stage currently holds, or ("loading", ...)
     a_readers = [0] * STAGES         # MMAs issued on the stage and not yet complete
-    b_content, b_readers = [None, None], [0, 0]
-    t_content, t_writers, t_readers = [None, None], [0, 0], [0, 0]
+    b_content, b_readers = [None] * BBUFS, [0] * BBUFS
+    t_content, t_writers, t_readers = [None] * ABUFS, [0] * ABUFS, [0] * ABUFS
     log = {"tiles_done": 0, "max_lead": 0}
 
     def wait(bar, parity):
@@ -71,8 +72,8 @@ def simulate(n_items, tiles_per_item, ks, seed):
     def producer():
         stage, sphase, it = 0, 0, 0
         for item in range(n_items):
-            bb = it & 1
-            yield from wait(bempty[bb], ((it >> 1) & 1) ^ 1)
+            bb = it % BBUFS
+            yield from wait(bempty[bb], ((it // BBUFS) & 1) ^ 1)
             assert b_readers[bb] == 0, "B buffer overwritten while MMAs still read it"
             bfull[bb].expect_tx(ks)
             b_content[bb] = ("loading", item)
@@ -103,13 +104,13 @@ def simulate(n_items, tiles_per_item, ks, seed):
     def mma():
         stage, sphase, it, tile_no = 0, 0, 0, 0
         for item in range(n_items):
-            bb = it & 1
-            yield from wait(bfull[bb], (it >> 1) & 1)
+            bb = it % BBUFS
+            yield from wait(bfull[bb], (it // BBUFS) & 1)
             assert b_content[bb] == item, "MMA reads a B buffer that does not hold this item"
             b_readers[bb] += 1
             for t in range(tiles_per_item):
-                ab = tile_no & 1
-                yield from wait(tempty[ab], ((tile_no >> 1) & 1) ^ 1)
+                ab = tile_no % ABUFS
+                yield from wait(tempty[ab], ((tile_no // ABUFS) & 1) ^ 1)
                 assert t_readers[ab] == 0, "accumulator overwritten while the epilogue still reads it"
                 t_content[ab] = ("accumulating", item, t)
                 t_writers[ab] += 1
@@ -141,8 +142,8 @@ def simulate(n_items, tiles_per_item, ks, seed):
         tile_no = 0
         for item in range(n_items):
             for t in range(tiles_per_item):
-                ab = tile_no & 1
-                yield from wait(tfull[ab], (tile_no >> 1) & 1)
+                ab = tile_no % ABUFS
+                yield from wait(tfull[ab], (tile_no // ABUFS) & 1)
                 assert t_content[ab] == (item, t) and t_writers[ab] == 0, "epilogue reads an accumulator that is not final"
                 t_readers[ab] += 1
                 for _ in range(rng.randint(1, 4)):
@@ -153,7 +154,7 @@ def simulate(n_items, tiles_per_item, ks, seed):
                     log["tiles_done"] += 1
                 tile_no += 1
 
-    roles = [producer(), mma()] + [epilogue(w) for w in range(4)]
+    roles = [producer(), mma()] + [epilogue(w) for w in range(EPI_WARPS)]
     alive = list(roles)
     idle_rounds = 0
     while alive:
@@ -183,5 +184,10 @@ def simulate(n_items, tiles_per_item, ks, seed):
 
 @pytest.mark.parametrize("n_items,tiles,ks", [(1, 1, 1), (3, 1, 2), (5, 8, 16), (4, 3, 5), (7, 2, 16), (2, 32, 16)])
 def test_tc5_barrier_protocol_terminates_without_hazards(n_items, tiles, ks):
-    for seed in range(12):
+    for seed in range(6):
         assert simulate(n_items, tiles, ks, seed) == n_items * tiles
+        # the shipped configuration: 32 KiB stages, single-buffered query operand, four accumulator buffers (S8: 5 stages)
+        assert simulate(n_items, tiles, ks, seed, STAGES=5, KS_PER_STAGE=8, BBUFS=1, ABUFS=4) == n_items * tiles
+        assert simulate(n_items, tiles, ks, seed, STAGES=3, KS_PER_STAGE=8, BBUFS=2, ABUFS=4) == n_items * tiles
+        assert simulate(n_items, tiles, ks, seed, STAGES=10, KS_PER_STAGE=4, BBUFS=1, ABUFS=2) == n_items * tiles
+        assert simulate(n_items, tiles, ks, seed, STAGES=2, KS_PER_STAGE=4, BBUFS=1, ABUFS=4) == n_items * tiles
