@@ -148,12 +148,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload, batch):
-    """dram bytes per launch of the multiply kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(workload, batch, db_format):
+    """dram bytes per launch of the multiply kernel from the committed ncu --set full capture of this configuration, if any
+    (profiles/roofline_traffic.json; key = workload, queries per step, database format)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             d = json.load(f)
-        return d.get("%s_batch%d" % (workload, batch))
+        return d.get("%s_batch%d_format%d" % (workload, batch, db_format))
     except Exception:
         return None
 
@@ -614,9 +615,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname + " = multiply_reg_by_database, server.rs:155-221",
                 "queries_per_launch": nq_per_launch,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(name, B), "peak_source": peak_src,
+                "traffic": ncu_traffic(name, B, args.db_format), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mul_ms,
-                "kernel_share_of_step": stage["multiply"] / max(stage["total"], 1e-9)}
+                "kernel_share_of_step": stage["multiply"] / max(stage["total"], 1e-9),
+                "note": "kernel_ms = CUDA-event time of the multiply kernel alone; the re-tiling of the query operand that precedes it "
+                        "is stage 'query_image'"}
 
     if rank == 0:
         cpu = None

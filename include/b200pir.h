@@ -204,8 +204,9 @@ int b200pir_finish_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t*
 
 /* Per-stage device time of the last profiled call, in milliseconds, measured with CUDA events on the
  * context's stream.  Enable with b200pir_ctx_set_option(ctx, "profile", 1).
- * out[0..7] = expand, first-dim multiply, from_ntt, fold, pack, encode, total, multiply launches */
-int b200pir_last_stage_ms(b200pir_ctx* ctx, double* out8);
+ * out[0..8] = expand, first-dim multiply kernel, from_ntt, fold, pack, encode, total, multiply launches, re-tiling of the query
+ * operand for the tensor-core first dimension (k_query_to_tc5 / k_query_to_frag) */
+int b200pir_last_stage_ms(b200pir_ctx* ctx, double* out9);
 /* Number of CUDA kernels this library has launched from the calling host thread since load. */
 unsigned long long b200pir_kernel_launches(void);
 

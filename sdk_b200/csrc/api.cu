@@ -70,7 +70,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
-enum Stage { ST_EXPAND = 0, ST_MUL, ST_FROMNTT, ST_FOLD, ST_PACK, ST_ENCODE, ST_COUNT };
+enum Stage { ST_EXPAND = 0, ST_MUL, ST_FROMNTT, ST_FOLD, ST_PACK, ST_ENCODE, ST_QIMG /* query operand re-tiling */, ST_COUNT };
 
 }  // namespace
 
@@ -146,7 +146,7 @@ struct b200pir_ctx {
   std::vector<cudaEvent_t> event_pool;
   size_t event_next = 0;
   int mul_launches = 0;
-  double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double last_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // expand, multiply, from_ntt, fold, pack, encode, total, multiply launches, query image
 
   size_t v_words() const { return ((size_t)1 << g) * 4 * POLY; }
   size_t fold_words() const { return (size_t)hp.nu_2 * 2 * 2 * hp.t_gsw * 2 * POLY; }
@@ -174,11 +174,11 @@ struct b200pir_ctx {
   void prof_collect() {
     if (!profile) return;
     B200_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < 8; i++) last_ms[i] = 0;
+    for (int i = 0; i < 9; i++) last_ms[i] = 0;
     for (auto& s : spans) {
       float ms = 0;
       cudaEventElapsedTime(&ms, s.a, s.b);
-      last_ms[s.stage] += ms;
+      last_ms[s.stage == ST_QIMG ? 8 : s.stage] += ms;
       last_ms[6] += ms;
     }
     last_ms[7] = mul_launches;
@@ -248,6 +248,7 @@ PpTable b200pir_ctx::pp_table(b200pir_pp* pp, size_t count) {
 
 struct b200pir_dpir {
   int device;
+  std::mutex mu;            // calls on one handle stage through its b / out buffers: serialised
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   uint64_t rows, cols;
@@ -410,8 +411,11 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
     c->w_qt.ensure(tc5_query_bytes(db->T));
     for (size_t qi = 0; qi < count; qi += 16) {
       const int nq = (int)std::min<size_t>(16, count - qi);
+      {
+        b200pir_ctx::Scope sq(c, ST_QIMG);
+        launch_query_to_tc5(db->T, qdev + qi * q_stride, q_stride, nq, c->w_qt.p, c->stream);
+      }
       b200pir_ctx::Scope sc(c, ST_MUL);
-      launch_query_to_tc5(db->T, qdev + qi * q_stride, q_stride, nq, c->w_qt.p, c->stream);
       launch_multiply_tc5(c->dp, db->T, db->t.p, c->w_qt.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
                           c->sm_count, c->stream);
       c->mul_launches++;
@@ -427,8 +431,11 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
     for (size_t qi = 0; qi < count; qi += per_pass) {
       const int nq = (int)std::min<size_t>(per_pass, count - qi);
       {
-        b200pir_ctx::Scope sc(c, ST_MUL);
+        b200pir_ctx::Scope sq(c, ST_QIMG);
         launch_query_to_frag(db->F, qdev + qi * q_stride, q_stride, nq, c->w_qf.p, c->stream);
+      }
+      {
+        b200pir_ctx::Scope sc(c, ST_MUL);
         launch_multiply_imma(c->dp, db->F, db->f.p, c->w_qf.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
                              c->imma_variant, c->stream);
         c->mul_launches++;
@@ -1632,12 +1639,12 @@ int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* ga
 
 unsigned long long b200pir_kernel_launches(void) { return g_kernel_launches; }
 
-int b200pir_last_stage_ms(b200pir_ctx* c, double* out8) {
+int b200pir_last_stage_ms(b200pir_ctx* c, double* out9) {
   API_BEGIN
-  if (!c || !out8) throw Error(B200PIR_E_BADARG, "null argument");
+  if (!c || !out9) throw Error(B200PIR_E_BADARG, "null argument");
   Guard gd(c);
   c->prof_collect();
-  for (int i = 0; i < 8; i++) out8[i] = c->last_ms[i];
+  for (int i = 0; i < 9; i++) out9[i] = c->last_ms[i];
   API_END
 }
 
@@ -1757,7 +1764,9 @@ void b200pir_dpir_destroy(b200pir_dpir* m) {
 int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream) {
   API_BEGIN
   if (!m) throw Error(B200PIR_E_BADARG, "null handle");
+  std::lock_guard<std::mutex> lk(m->mu);
   cudaSetDevice(m->device);
+  B200_CUDA(cudaStreamSynchronize(m->stream));                     // pending work on the old stream first
   if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   m->stream = (cudaStream_t)cuda_stream;
   m->own_stream = false;
@@ -1766,6 +1775,7 @@ int b200pir_dpir_set_stream(b200pir_dpir* m, void* cuda_stream) {
 int b200pir_dpir_matvec_packed_dev(b200pir_dpir* m, const uint32_t* b_dev, uint32_t* out_dev, int variant) {
   API_BEGIN
   if (!m || !b_dev || !out_dev) throw Error(B200PIR_E_BADARG, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
   cudaSetDevice(m->device);
   launch_dpir_matvec(out_dev, m->a.p, b_dev, m->rows, m->cols, variant, m->stream);
   B200_CUDA(cudaGetLastError());
@@ -1777,6 +1787,7 @@ int b200pir_dpir_matvec_packed_rows(b200pir_dpir* m, uint64_t row_begin, uint64_
   if (!m || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");
   if (row_begin + row_count > m->rows) throw Error(B200PIR_E_SHAPE, "row range out of bounds");
   if (row_count == 0) return 0;
+  std::lock_guard<std::mutex> lk(m->mu);
   cudaSetDevice(m->device);
   B200_CUDA(cudaMemcpyAsync(m->b.p, b, 3 * m->cols * 4, cudaMemcpyHostToDevice, m->stream));
   launch_dpir_matvec(m->out.p, m->a.p + row_begin * m->cols, m->b.p, row_count, m->cols, 0, m->stream);
@@ -1821,6 +1832,7 @@ int b200pir_dpir_transpose_expand_concat_cols_squish(int device, const uint32_t*
 int b200pir_dpir_matvec_packed(b200pir_dpir* m, const uint32_t* b, uint32_t* out) {
   API_BEGIN
   if (!m || !b || !out) throw Error(B200PIR_E_BADARG, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
   cudaSetDevice(m->device);
   B200_CUDA(cudaMemcpyAsync(m->b.p, b, 3 * m->cols * 4, cudaMemcpyHostToDevice, m->stream));
   launch_dpir_matvec(m->out.p, m->a.p, m->b.p, m->rows, m->cols, 0, m->stream);

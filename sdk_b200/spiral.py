@@ -24,6 +24,13 @@ def _ptr(a, dtype=np.uint64):
     return a.ctypes.data
 
 
+def _need(a, words, what):
+    """The C ABI takes no lengths for these buffers (as the Rust functions take slices whose lengths they assert): check here,
+    so a short array is a ValueError and not an out-of-bounds read inside cudaMemcpy."""
+    if a is not None and a.size != words:
+        raise ValueError("%s must hold %d words, got %d" % (what, words, a.size))
+
+
 class Params:
     """spiral_rs::params::Params (params.rs:49-82) + the GPU context built from it."""
 
@@ -50,6 +57,17 @@ class Params:
         sb, qb, rb = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(LIB.b200pir_ctx_sizes(self._h, C.byref(sb), C.byref(qb), C.byref(rb)))
         self.setup_bytes, self.query_bytes, self.response_bytes = sb.value, qb.value, rb.value
+        import math
+        W = POLY_LEN * CRT_COUNT
+        self.g = int(math.ceil(math.log2(self.t_gsw * self.nu_2 + self.dim0)))
+        self.stop_round = int(math.ceil(math.log2(self.t_gsw * self.nu_2))) if self.nu_2 else 0
+        self.num_packing = self.n if self.version == 0 else 2
+        self.has_right = self.expand_queries and (self.version == 0 or self.t_exp_right != self.t_exp_left)
+        # word counts of the matrices of PublicParameters (client.rs:146-152) and of the stage-level operands
+        self.words = dict(pack=self.num_packing * (self.n + 1) * self.t_conv * W, left=self.g * 2 * self.t_exp_left * W,
+                          right=(self.stop_round + 1) * 2 * self.t_exp_right * W, conv=2 * 2 * self.t_conv * W,
+                          v_folding=self.nu_2 * 2 * 2 * self.t_gsw * W, v_buf=self.dim0 * 2 * POLY_LEN,
+                          v_ct=self.nu_2 * 2 * 2 * self.t_gsw * POLY_LEN, ct=2 * POLY_LEN, v=(1 << self.g) * 2 * W)
 
     @classmethod
     def from_json(cls, obj, device=0):
@@ -81,9 +99,9 @@ class Params:
         check(LIB.b200pir_ctx_synchronize(self._h))
 
     def last_stage_ms(self):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 9)()
         check(LIB.b200pir_last_stage_ms(self._h, out))
-        keys = ("expand", "multiply", "from_ntt", "fold", "pack", "encode", "total", "multiply_launches")
+        keys = ("expand", "multiply", "from_ntt", "fold", "pack", "encode", "total", "multiply_launches", "query_image")
         return dict(zip(keys, list(out)))
 
 
@@ -166,6 +184,11 @@ class PublicParameters:
 
     def __init__(self, params, v_packing, v_expansion_left=None, v_expansion_right=None, v_conversion=None):
         self.params = params
+        _need(v_packing, params.words["pack"], "v_packing")
+        if params.expand_queries:
+            _need(v_expansion_left, params.words["left"], "v_expansion_left")
+            _need(v_expansion_right, params.words["right"], "v_expansion_right")
+            _need(v_conversion, params.words["conv"], "v_conversion")
         h = C.c_void_p()
         check(LIB.b200pir_pp_create(params._h, _ptr(v_packing), _ptr(v_expansion_left), _ptr(v_expansion_right),
                                     _ptr(v_conversion), C.byref(h)))
@@ -266,11 +289,16 @@ def fold_ciphertexts(params, v_cts, v_folding, v_folding_neg=None):
     v_folding_neg=None means get_v_folding_neg(v_folding) (what process_query passes) and selects the
     library's fast path."""
     num = v_cts.size // (2 * POLY_LEN)
+    if v_cts.size != num * 2 * POLY_LEN or num == 0 or num & (num - 1) or num > params.num_per:
+        raise ValueError("v_cts must hold a power of two (<= num_per) of 2 x poly_len ciphertexts")
+    _need(v_folding, params.words["v_folding"], "v_folding")
+    _need(v_folding_neg, params.words["v_folding"], "v_folding_neg")
     check(LIB.b200pir_fold_ciphertexts(params._h, _ptr(v_cts), num, _ptr(v_folding), _ptr(v_folding_neg)))
 
 
 def get_v_folding_neg(params, v_folding):
     """server.rs:505-523."""
+    _need(v_folding, params.words["v_folding"], "v_folding")
     out = np.zeros_like(v_folding)
     check(LIB.b200pir_get_v_folding_neg(params._h, _ptr(out), _ptr(v_folding)))
     return out
@@ -278,11 +306,13 @@ def get_v_folding_neg(params, v_folding):
 
 def coefficient_expansion(params, public_params, v):
     """server.rs:19-121, in place over v = 2^g x PolyMatrixNTT(2,1)."""
+    _need(v, params.words["v"], "v")
     check(LIB.b200pir_coefficient_expansion(params._h, public_params._h, _ptr(v)))
 
 
 def expand_query(params, public_params, query):
     """server.rs:525-591 -> (v_reg_reoriented, v_folding)."""
+    _need(query.ct, params.words["ct"], "query.ct")
     v_reg = np.zeros(params.dim0 * 2 * POLY_LEN, dtype=np.uint64)
     v_fold = np.zeros(max(1, params.nu_2 * 2 * 2 * params.t_gsw * CRT_COUNT * POLY_LEN), dtype=np.uint64)
     check(LIB.b200pir_expand_query(params._h, public_params._h, _ptr(query.ct), _ptr(v_reg), _ptr(v_fold)))
@@ -291,6 +321,7 @@ def expand_query(params, public_params, query):
 
 def pack(params, public_params, v_ct):
     """server.rs:429-468 / lib/server/src/compute/pack.rs (by params.version)."""
+    _need(v_ct, params.n * params.n * 2 * POLY_LEN, "v_ct")
     out = np.zeros((params.n + 1) * params.n * CRT_COUNT * POLY_LEN, dtype=np.uint64)
     check(LIB.b200pir_pack(params._h, public_params._h, _ptr(v_ct), _ptr(out)))
     return out
@@ -298,6 +329,7 @@ def pack(params, public_params, v_ct):
 
 def encode(params, v_packed_ct):
     """server.rs:470-503."""
+    _need(v_packed_ct, params.instances * (params.n + 1) * params.n * POLY_LEN, "v_packed_ct")
     out = np.zeros(params.response_bytes, dtype=np.uint8)
     n = C.c_size_t(0)
     check(LIB.b200pir_encode(params._h, _ptr(v_packed_ct), _ptr(out, np.uint8), C.byref(n)))
@@ -306,6 +338,11 @@ def encode(params, v_packed_ct):
 
 def process_query(params, public_params, query, db):
     """spiral_rs::server::process_query (server.rs:650-741) -> response bytes."""
+    if params.expand_queries:
+        _need(query.ct, params.words["ct"], "query.ct")
+    else:
+        _need(query.v_buf, params.words["v_buf"], "query.v_buf")
+        _need(query.v_ct, params.words["v_ct"], "query.v_ct")
     out = np.zeros(params.response_bytes, dtype=np.uint8)
     n = C.c_size_t(0)
     check(LIB.b200pir_process_query(params._h, db._h, public_params._h, _ptr(query.ct), _ptr(query.v_buf),
@@ -357,6 +394,7 @@ def coalesce_stats(params):
 def process_query_batch(params, public_params, query_cts, db):
     """`count` expanded-mode queries of one client; the database is streamed once per group."""
     count = query_cts.size // (2 * POLY_LEN)
+    _need(query_cts, count * 2 * POLY_LEN, "query_cts")
     out = np.zeros(count * params.response_bytes, dtype=np.uint8)
     n = C.c_size_t(0)
     check(LIB.b200pir_process_query_batch(params._h, db._h, public_params._h, _ptr(query_cts), count,

@@ -321,6 +321,13 @@ def test_error_behaviour():
         S.Params(device=99, **P.kw)
     with pytest.raises(S.B200PirError):
         S.Database.from_words(G, np.zeros(17, dtype=np.uint64))
+    # short buffers are refused by the host mirror (the C ABI, like the Rust slices it stands for, carries no lengths there)
+    with pytest.raises(ValueError):
+        S.PublicParameters(G, pp["pack"][:-1], pp["left"], pp["right"], pp["conv"])
+    with pytest.raises(ValueError):
+        S.process_query(G, gpp, S.Query(ct=np.zeros(2 * P.N - 1, dtype=np.uint64)), gdb)
+    with pytest.raises(ValueError):
+        S.pack(G, gpp, np.zeros(5, dtype=np.uint64))
     # gadget dimension 2 = 29-bit digits, above q_n: outside the transforms' input range, rejected (no reference parameter set uses it)
     with pytest.raises(S.B200PirError) as ei:
         S.Params(**dict(P.kw, t_gsw=2))

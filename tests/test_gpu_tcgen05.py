@@ -70,22 +70,21 @@ def test_tc5_synthetic_and_upsert_equal_bulk_upload():
 def test_tc5_long_k_many_tiles_worst_case():
     S, _, _, _, _, _, _, _ = setup_case("T")
     kw = dict(O.PARAM_SETS["T"])
-    kw.update(nu_1=10, nu_2=6, n=1, db_item_size=2048)          # dim0 = 1024 does not fit the kernel's shared memory
-    P = O.Params(**kw)
-    G = S.Params(**kw)
-    with pytest.raises(S.B200PirError):
-        S.Database(G, fmt=2)
-    G.close()
-    kw.update(nu_1=9, nu_2=7)                                    # dim0 = 512 (16 k-steps), 128 rows = 4 row tiles
-    P = O.Params(**kw)
-    G = S.Params(**kw)
-    w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
-    rng = np.random.default_rng(23)
-    dbw = np.full(P.dim0 * P.num_per * P.N, w, dtype=np.uint64)
-    dbw[::5] = rng.integers(0, Q0, dbw[::5].size, dtype=np.uint64) | (rng.integers(0, Q1, dbw[::5].size, dtype=np.uint64) << np.uint64(32))
-    v = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
-    v[::3] = rng.integers(0, Q0, v[::3].size, dtype=np.uint64) | (rng.integers(0, Q1, v[::3].size, dtype=np.uint64) << np.uint64(32))
-    tdb = S.Database.from_words(G, dbw, fmt=2)
-    assert np.array_equal(S.multiply_reg_by_database(G, tdb, 0, v), P.multiply_reg_by_database(dbw, v))
-    tdb.close()
-    G.close()
+    kw.update(n=1, db_item_size=2048)
+    # dim0 = 1024: 32 k-steps, the largest accumulators the limb arithmetic allows (1024 x 127 x 127 < 2^24), a 128 KiB query
+    # operand (single-buffered beside the ring); dim0 = 512: 16 k-steps, 128 rows = 4 row tiles, double-buffered operand
+    for nu_1, nu_2 in ((10, 6), (9, 7)):
+        kw.update(nu_1=nu_1, nu_2=nu_2)
+        P = O.Params(**kw)
+        G = S.Params(**kw)
+        w = np.uint64((Q0 - 1) | ((Q1 - 1) << 32))
+        rng = np.random.default_rng(23 + nu_1)
+        dbw = np.full(P.dim0 * P.num_per * P.N, w, dtype=np.uint64)
+        dbw[::5] = rng.integers(0, Q0, dbw[::5].size, dtype=np.uint64) | (rng.integers(0, Q1, dbw[::5].size, dtype=np.uint64) << np.uint64(32))
+        v = np.full(P.dim0 * 2 * P.N, w, dtype=np.uint64)
+        v[::3] = rng.integers(0, Q0, v[::3].size, dtype=np.uint64) | (rng.integers(0, Q1, v[::3].size, dtype=np.uint64) << np.uint64(32))
+        tdb = S.Database.from_words(G, dbw, fmt=2)
+        assert tdb.info()["format"] == 2
+        assert np.array_equal(S.multiply_reg_by_database(G, tdb, 0, v), P.multiply_reg_by_database(dbw, v)), nu_1
+        tdb.close()
+        G.close()
