@@ -303,6 +303,102 @@ def run_reference_arm(args, kw, workload_name, rank, world):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- kernel-level workloads
+def kernel_workload(args):
+    """BASELINE configs #4 (DoublePIR 2^24 x 1366 packed words, HBM GB/s vs roofline) and #5 (NTT / INTT throughput, poly_len
+    2048 and 4096, 2^16 polynomials x 2 CRT moduli) as bench lines: `--workload dpir`, `--workload ntt`.  Single GPU."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import sdk_b200.spiral as S
+    import sdk_b200.doublepir as D
+    from sdk_b200._lib import LIB, check
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    peak, peak_src = measured_peak()
+    stream = torch.cuda.current_stream()
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.time()
+    if args.workload == "dpir":
+        rows, cols = 1 << 24, 1366                                   # 2^24 x ceil(2^12 / 3) u32 = 91.7 GB, larger than L2 by far
+        m = D.PackedMatrix(rows=rows, cols=cols, synthetic_seed=7)
+        check(LIB.b200pir_dpir_set_stream(m._h, C.c_void_p(stream.cuda_stream)))
+        rng = np.random.default_rng(11)
+        hb = rng.integers(0, 1 << 32, 3 * cols, dtype=np.uint64).astype(np.uint32)
+        b = torch.from_numpy(hb.view(np.int32)).cuda()
+        out = torch.zeros(rows, dtype=torch.int32, device="cuda")
+        ms = timed(lambda: check(LIB.b200pir_dpir_matvec_packed_dev(m._h, b.data_ptr(), out.data_ptr(), 0)))
+        alg = 4 * rows * cols + 12 * cols + 4 * rows
+        ho = np.zeros(rows, dtype=np.uint32)
+        t1 = time.perf_counter()
+        for _ in range(3):
+            check(LIB.b200pir_dpir_matvec_packed(m._h, hb.ctypes.data, ho.ctypes.data))           # host b in, host out
+        e2e_ms = (time.perf_counter() - t1) / 3 * 1e3
+        # CPU port on a bounded row sample (2^18 rows = 1.4 GB), scaled
+        import oracle_lib as O
+        srows = 1 << 18
+        a_s = rng.integers(0, 1 << 30, srows * cols, dtype=np.uint32)
+        t1 = time.perf_counter()
+        O.dpir_matvec_packed(a_s, hb, srows, cols)
+        cpu_s = (time.perf_counter() - t1) * (rows / srows)
+        line = {"metric": "DoublePIR matrix_mul_vec_packed HBM GB/s (2^24 x 1366 packed words)", "value": alg / ms / 1e6, "unit": "GB/s",
+                "ms_per_step": ms, "dtype": "u32", "config": {"workload": "dpir: BASELINE configs[3], 2^24 rows x 1366 words (3 x 10 bit), 91.7 GB",
+                                                               "l2": "inputs larger than L2"},
+                "roofline": {"bound": "hbm", "kernel": "k_dpir_matvec_row", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s",
+                             "frac": alg / ms / 1e6 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+                "e2e": {"value": alg / e2e_ms / 1e6, "unit": "GB/s", "h2d_bytes_per_step": 12 * cols, "d2h_bytes_per_step": 4 * rows},
+                "cpu_baseline": {"value": alg / cpu_s / 1e9, "unit": "GB/s", "cores": int(O.LIB.orc_num_threads()), "kind": "port",
+                                 "sample": "oracle matrix_mul_vec_packed (OpenMP) on 2^18 of 2^24 rows, scaled x64"},
+                "gpu_launches": args.steps}
+        m.close()
+    else:
+        kw = WORKLOADS["T"]
+        G = S.Params(**kw)
+        G.set_stream(stream.cuda_stream)
+        count = 1 << 16
+        res = {}
+        for poly_len, fn in ((2048, LIB.b200pir_ntt32_dev), (4096, LIB.b200pir_ntt4096_dev)):
+            x = torch.randint(0, Q1, (count * 2 * poly_len,), dtype=torch.int32, device="cuda")
+            for name, inv in (("forward", 0), ("inverse", 1)):
+                if inv:
+                    check(fn(G._h, x.data_ptr(), count, 0))               # inverse timed on canonical transform outputs
+                ms = timed(lambda: check(fn(G._h, x.data_ptr(), count, inv)))
+                byt = 2 * count * 2 * poly_len * 4
+                res["%d_%s" % (poly_len, name)] = {"ms": ms, "polys_per_s": count / ms * 1e3, "GB/s_u32": byt / ms / 1e6,
+                                                   "frac_of_hbm_peak_u32": byt / ms / 1e6 / peak}
+            del x
+        f = res["2048_forward"]
+        line = {"metric": "NTT throughput, 2^16 polynomials x 2 CRT moduli (28-bit), poly_len 2048 forward", "value": f["polys_per_s"],
+                "unit": "polynomials/s", "ms_per_step": f["ms"], "dtype": "u32",
+                "config": {"workload": "ntt: BASELINE configs[4], poly_len 2048 and 4096, forward and inverse",
+                           "l2": "batch (1 GiB at 2048, 2 GiB at 4096) larger than L2"},
+                "sweep": res,
+                "roofline": {"bound": "hbm", "kernel": "k_ntt32 (relaxed-range butterflies)", "achieved": f["GB/s_u32"], "peak": peak, "unit": "GB/s",
+                             "frac": f["frac_of_hbm_peak_u32"], "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": 2 * count * 2 * 2048 * 4,
+                             "note": "the transform is bound by the integer-multiply pipe (scripts/ubench/bfly.cu: 915-1100 clocks per "
+                                     "transform per SM), not by HBM"},
+                "gpu_launches": 4 * args.steps}
+        G.close()
+    clocks = sampler.stop(t0, time.time())
+    line.update({"n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+                 "vs_baseline": None, "data": "synthetic", "clocks": clocks})
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -348,6 +444,13 @@ def main():
     if args.batch is None:
         args.batch = args.batch_per_gpu * N
 
+    if args.workload in ("dpir", "ntt"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "kernel-level workloads carry their CPU baseline inside the GPU line"}))
+            return
+        if rank == 0:
+            kernel_workload(args)
+        return
     name = args.workload or "S8"
     kw = dict(WORKLOADS[name])
     import math

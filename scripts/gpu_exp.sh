@@ -17,12 +17,10 @@ PY
 }
 {
 echo "== new tests"
-timeout 900 python -m pytest tests/test_gpu_bench_config.py tests/test_gpu_tcgen05.py -x -q 2>&1 | tail -15
-echo "== first dimension with converged issue warps"
-run "ksps8 B1 A4 (default)" X=1 --
-run "ksps8 B2 A4" B200PIR_TC5_BBUFS=2 --
-run "ksps4 B1 A4" B200PIR_TC5_KSPS=4 --
-run "ksps4 B2 A2" B200PIR_TC5_KSPS=4 B200PIR_TC5_BBUFS=2 B200PIR_TC5_ABUFS=2 --
-run "no epilogue" B200PIR_TC5_DBG=2 --
-run "copy only" B200PIR_TC5_DBG=3 --
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "error_behaviour or dpir or fold" 2>&1 | tail -6
+echo "== fold variants"
+run "fold lz 3/SM" X=1 -- --fold-variant 2
+run "fold lz 3/SM + L1 prefetch" X=1 -- --fold-variant 5
+run "fold lz 2/SM + L1 prefetch" X=1 -- --fold-variant 6
+run "fold lz 2/SM regtw + prefetch" X=1 -- --fold-variant 7
 } 2>&1 | tee gpurun_out/gpu_exp.log

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Multi-GPU session: bash scripts/gpu_multi.sh N [tag]   (under gpurun --gpus N)
+N=${1:-2}
+TAG=${2:-r02}
+mkdir -p gpurun_out
+run() {
+  local label=$1; shift
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+    bench.py --gpus $N --steps 10 --warmup 3 "$@" > gpurun_out/multi.json 2> gpurun_out/multi.err
+  python - "$label" <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open("gpurun_out/multi.json").read().strip().splitlines() if l.startswith("{")][-1])
+    print("%-28s %8.1f q/s  e2e %8.1f  ms/step %.3f  verified %s " % (sys.argv[1], d["value"], d["e2e"]["value"], d["ms_per_step"], d.get("verified")),
+          {k: round(v, 3) for k, v in d["stage_ms_per_step"].items()})
+except Exception as e:
+    print(sys.argv[1], "failed:", e, open("gpurun_out/multi.err").read()[-1500:])
+PY
+}
+{
+echo "== $N GPUs"
+run "default" X=1 --
+cp gpurun_out/multi.json gpurun_out/bench_${TAG}_n${N}.json
+run "NCCL_MAX_CTAS=8" NCCL_MAX_CTAS=8 --
+run "waves 1" X=1 -- --waves 1
+} 2>&1 | tee gpurun_out/gpu_multi_${TAG}_n${N}.log

@@ -92,8 +92,7 @@ struct b200pir_ctx {
   DevBuf<uint32_t> d_neg1;   // [11][2][2048] ntt32 (params.rs:98-107)
   // options
   int mul_variant = 0, max_group = 16, profile = 0;  // max_group: queries per database pass (IMAD path: <= 4)
-  int fold_variant = 2;          // 2: relaxed-range transforms, 3 CTAs/SM (default); 3: same at 2 CTAs/SM; 4: twiddles in registers;
-                                 // 1 / 0: the per-butterfly-corrected kernel of round 1 at 3 / 2 CTAs per SM
+  int fold_variant = 2;          // k_fold_res_lz at 3 CTAs per SM (default); 3: 2 CTAs per SM (A/B switch)
   int intt_variant = 0;
   int expand_variant = 0;        // wide rounds: 0 paired + residue pipeline (3 CTAs/SM), 2 paired single kernel; 1: never paired
   long pair_min_ctas = 592;      // 4 x 148 SMs

@@ -485,64 +485,6 @@ __device__ __forceinline__ void ntt_inverse_group2(int tid, uint32_t (&x0)[8], u
   inv_pass_a(tid, x0, smem0, lo, q, two_q);
   inv_pass_a(tid, x1, smem1, lo, q, two_q);
 }
-// Twiddles of passes C and D held in registers (13 (W, W') pairs per thread): a thread uses the SAME table entries in every
-// transform, so a kernel that runs many transforms loads them once instead of re-reading 104 bytes of shared memory per
-// thread and transform (35 % of the transform's shared-memory traffic).
-struct TwRegsC {
-  Twiddle c0, c1[2], c2[4];
-  template <typename Tab>
-  __device__ __forceinline__ void load(int tid, Tab tab) {
-    const int H = tid >> 2;
-    c0 = tab(64 + H);
-    tab.load2(128 + 2 * H, c1);
-    tab.load4(256 + 4 * H, c2);
-  }
-  __device__ __forceinline__ Twiddle operator()(int) const { return c0; }
-  __device__ __forceinline__ void load2(int, Twiddle (&t)[2]) const { t[0] = c1[0]; t[1] = c1[1]; }
-  __device__ __forceinline__ void load4(int, Twiddle (&t)[4]) const { t[0] = c2[0]; t[1] = c2[1]; t[2] = c2[2]; t[3] = c2[3]; }
-};
-struct TwRegsD {
-  Twiddle d9[2], d10[4];
-  template <typename Tab>
-  __device__ __forceinline__ void load(int tid, Tab tab) {
-    tab.load2(512 + 2 * tid, d9);
-    tab.load4(1024 + 4 * tid, d10);
-  }
-  __device__ __forceinline__ void load2(int, Twiddle (&t)[2]) const { t[0] = d9[0]; t[1] = d9[1]; }
-  __device__ __forceinline__ void load4(int, Twiddle (&t)[4]) const { t[0] = d10[0]; t[1] = d10[1]; t[2] = d10[2]; t[3] = d10[3]; }
-};
-// forward transforms with separate accessors for pass C and pass D
-template <int OUT, bool IN4Q = false, typename Sync, typename TabLo, typename TabC, typename TabD>
-__device__ __forceinline__ void ntt_forward_group2_lz(int tid, uint32_t (&x0)[8], uint32_t (&x1)[8], uint32_t* smem0,
-                                                      uint32_t* smem1, TabLo lo, TabC hc, TabD hd, uint32_t q, Sync gsync) {
-  const uint32_t two_q = 2 * q;
-  gsync();
-  fwd_pass_a_lz<IN4Q>(tid, x0, smem0, lo, q, two_q);
-  fwd_pass_a_lz<IN4Q>(tid, x1, smem1, lo, q, two_q);
-  gsync();
-  fwd_pass_b_lz(tid, x0, smem0, lo, q, two_q);
-  fwd_pass_b_lz(tid, x1, smem1, lo, q, two_q);
-  gsync();
-  fwd_pass_c_lz(tid, x0, smem0, hc, q, two_q);
-  fwd_pass_c_lz(tid, x1, smem1, hc, q, two_q);
-  gsync();
-  fwd_pass_d_lz<OUT>(tid, x0, smem0, hd, q, two_q);
-  fwd_pass_d_lz<OUT>(tid, x1, smem1, hd, q, two_q);
-}
-template <int OUT, bool IN4Q = false, typename Sync, typename TabLo, typename TabC, typename TabD>
-__device__ __forceinline__ void ntt_forward_group_lz(int tid, uint32_t (&x)[8], uint32_t* smem, TabLo lo, TabC hc, TabD hd,
-                                                     uint32_t q, Sync gsync) {
-  const uint32_t two_q = 2 * q;
-  gsync();
-  fwd_pass_a_lz<IN4Q>(tid, x, smem, lo, q, two_q);
-  gsync();
-  fwd_pass_b_lz(tid, x, smem, lo, q, two_q);
-  gsync();
-  fwd_pass_c_lz(tid, x, smem, hc, q, two_q);
-  gsync();
-  fwd_pass_d_lz<OUT>(tid, x, smem, hd, q, two_q);
-}
-
 // relaxed-range versions (see above).  Forward: inputs < 2q (IN4Q: < 4q), outputs per OUT; inverse: inputs < 2q,
 // canonical outputs, `lo`/`hi` must serve the un-halved inverse tables of build_tables_lz.
 template <int OUT, bool IN4Q = false, typename Sync, typename TabLo, typename TabHi>

@@ -407,14 +407,31 @@ k_fold_round(DevParams P, uint64_t* cts, size_t batch_stride, int half, const ui
 // transforms, no CRT lift on the way out, and no v_folding_neg at all.
 // grid = (batch*half, 2 moduli), 256 threads.  in/out are distinct buffers (ping-pong): the CTA of
 // modulus n reads BOTH residues of its inputs (for the gadget digits) while the other CTA writes.
-template <int MINB>
+// Digit k of vh minus digit k of vi, offset by q: in (q - 2^bits, q + 2^bits), a subset of [0, 2q) for bits <= 27 (the
+// context rejects gadget dimensions below 3, so bits <= 19) — the relaxed-range forward transform needs no more.
+// BYTE: bits == 8, where digit k is simply byte k; the values are < 2^56, so byte 7 serves as the zero filler.
+template <bool BYTE>
+__device__ __forceinline__ uint32_t digit_diff(uint64_t vh, uint64_t vi, int k, int bits, uint64_t mask, uint32_t q) {
+  if (BYTE) {
+    const uint32_t sel = 0x7770u | (uint32_t)k;
+    return __byte_perm((uint32_t)vh, (uint32_t)(vh >> 32), sel) - __byte_perm((uint32_t)vi, (uint32_t)(vi >> 32), sel) + q;
+  }
+  return gadget_digit(vh, k, bits, mask) - gadget_digit(vi, k, bits, mask) + q;
+}
+
+// Same step as k_fold_res on the relaxed-range transforms (ntt_core.cuh "lz"): no per-butterfly range correction in the
+// forward transforms (outputs < 16q feed the 64-bit multiply-accumulate directly: 16 products of < 2^32 x < 2^28 fit),
+// no halving in the inverse transform, byte-permute digit extraction when bits_per = 8, 32-bit Barrett in the CRT lift.
+// Tried on top of this and measured without gain (S8, 16 queries; fold stage 3.53 ms): pass C / D twiddles held in registers at
+// 2 CTAs per SM (3.60 ms: 35 % less shared-memory traffic, so that is not the limit), key columns prefetched into L1 before the
+// pair's transforms (3.60 ms: the L2 latency ncu attributes to the multiply-accumulate is covered by the other CTAs).  The
+// kernel runs at ~80 % of its integer-multiply-pipe bound.
+template <int MINB, bool BYTE>
 __global__ void __launch_bounds__(256, MINB)
-k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
-           const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
-           const uint32_t* __restrict__ zero_flags /* null, or [batch][2*half]: 1 = ciphertext is all zero */) {
-  if (zero_flags) {
-    // lib/server/src/compute/fold.rs:37-43 (the sparse server's fold): an all-zero first operand is replaced by the
-    // second one, an all-zero second operand leaves the first one as it is; no external product in either case
+k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
+              const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
+              const uint32_t* __restrict__ zero_flags /* null, or [batch][2*half]: 1 = ciphertext is all zero */) {
+  if (zero_flags) {            // lib/server/src/compute/fold.rs:37-43, see k_fold_res
     const int bz = blockIdx.x / half, iz = blockIdx.x % half;
     const uint32_t fa = zero_flags[(size_t)bz * 2 * half + iz], fb = zero_flags[(size_t)bz * 2 * half + half + iz];
     if (fa | fb) {
@@ -451,137 +468,6 @@ k_fold_res(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ 
   for (int r = 0; r < 2; r++)
 #pragma unroll
     for (int e = 0; e < 8; e++) acc[r][e] = 0;
-#pragma unroll 1
-  for (int rho = 0; rho < 2; rho++) {
-    uint64_t vi[8], vh[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int z = a * 256 + g.tid;
-      vi[a] = crt_compose(__ldg(ci + (rho * 2 + 0) * POLY + z), __ldg(ci + (rho * 2 + 1) * POLY + z), P);
-      vh[a] = crt_compose(__ldg(ch + (rho * 2 + 0) * POLY + z), __ldg(ch + (rho * 2 + 1) * POLY + z), P);
-    }
-    // key-matrix column of digit k: rho + 2k
-    const uint32_t* c0 = C + ((size_t)rho * 2 + g.n) * POLY + g.tid * 8;
-    int k = 0;
-#pragma unroll 1
-    for (; k + 1 < t_gsw; k += 2) {
-      uint32_t x0[8], x1[8];
-#pragma unroll
-      for (int a = 0; a < 8; a++) {
-        uint32_t d0 = gadget_digit(vh[a], k, bits, mask) - gadget_digit(vi[a], k, bits, mask);
-        uint32_t d1 = gadget_digit(vh[a], k + 1, bits, mask) - gadget_digit(vi[a], k + 1, bits, mask);
-        x0[a] = ntt_min(d0, d0 + q);           // negative differences wrap: add q
-        x1[a] = ntt_min(d1, d1 + q);
-      }
-      ntt_forward_group2<false>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        uint32_t cv[8];
-        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
-#pragma unroll
-        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
-        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)(k + 1) * 4 * POLY);
-#pragma unroll
-        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x1[e] * cv[e];
-      }
-    }
-    if (k < t_gsw) {                            // odd t_gsw: last digit alone
-      uint32_t x0[8];
-#pragma unroll
-      for (int a = 0; a < 8; a++) {
-        uint32_t d0 = gadget_digit(vh[a], k, bits, mask) - gadget_digit(vi[a], k, bits, mask);
-        x0[a] = ntt_min(d0, d0 + q);
-      }
-      ntt_forward_group<false>(g.tid, x0, sm0, lo, hi, q, CtaSync());
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        uint32_t cv[8];
-        ld8_ro(cv, c0 + (size_t)r * row_step + (size_t)k * 4 * POLY);
-#pragma unroll
-        for (int e = 0; e < 8; e++) acc[r][e] += (uint64_t)x0[e] * cv[e];
-      }
-    }
-    // lazy NTT outputs (< 2^30): products < 2^58; t_gsw of them per rho -> reduce between the two rows when needed
-    if (rho == 0 && 2 * t_gsw > 60) acc_reduce<2>(acc, g);
-  }
-  uint32_t y0[8], y1[8];
-#pragma unroll
-  for (int e = 0; e < 8; e++) {
-    y0[e] = barrett64(acc[0][e], g.cr1, q);
-    y1[e] = barrett64(acc[1][e], g.cr1, q);
-  }
-  ntt_inverse_group2(g.tid, y0, y1, sm0, sm1, TwConst{g.n, 1}, TwGlobal{g.inv}, q, CtaSync());
-  uint32_t* co = out + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
-#pragma unroll
-  for (int a = 0; a < 8; a++) {
-    const int z = a * 256 + g.tid;
-    co[(0 * 2 + g.n) * POLY + z] = addmod(y0[a], __ldg(ci + (0 * 2 + g.n) * POLY + z), q);
-    co[(1 * 2 + g.n) * POLY + z] = addmod(y1[a], __ldg(ci + (1 * 2 + g.n) * POLY + z), q);
-  }
-}
-
-// Digit k of vh minus digit k of vi, offset by q: in (q - 2^bits, q + 2^bits), a subset of [0, 2q) for bits <= 27 (the
-// context rejects gadget dimensions below 3, so bits <= 19) — the relaxed-range forward transform needs no more.
-// BYTE: bits == 8, where digit k is simply byte k; the values are < 2^56, so byte 7 serves as the zero filler.
-template <bool BYTE>
-__device__ __forceinline__ uint32_t digit_diff(uint64_t vh, uint64_t vi, int k, int bits, uint64_t mask, uint32_t q) {
-  if (BYTE) {
-    const uint32_t sel = 0x7770u | (uint32_t)k;
-    return __byte_perm((uint32_t)vh, (uint32_t)(vh >> 32), sel) - __byte_perm((uint32_t)vi, (uint32_t)(vi >> 32), sel) + q;
-  }
-  return gadget_digit(vh, k, bits, mask) - gadget_digit(vi, k, bits, mask) + q;
-}
-
-// Same step as k_fold_res on the relaxed-range transforms (ntt_core.cuh "lz"): no per-butterfly range correction in the
-// forward transforms (outputs < 16q feed the 64-bit multiply-accumulate directly: 16 products of < 2^32 x < 2^28 fit),
-// no halving in the inverse transform, byte-permute digit extraction when bits_per = 8, 32-bit Barrett in the CRT lift.
-// REGTW: the forward transforms' pass C / D twiddles live in registers (TwRegsC / TwRegsD) instead of a shared-memory copy of
-// the table: 26 more registers, so it runs at 2 CTAs per SM (128 registers), with 18 KiB instead of 34 KiB of shared memory.
-template <int MINB, bool BYTE, bool REGTW>
-__global__ void __launch_bounds__(256, MINB)
-k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t batch_stride, int half,
-              const uint32_t* __restrict__ c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
-              const uint32_t* __restrict__ zero_flags /* null, or [batch][2*half]: 1 = ciphertext is all zero */) {
-  if (zero_flags) {            // lib/server/src/compute/fold.rs:37-43, see k_fold_res
-    const int bz = blockIdx.x / half, iz = blockIdx.x % half;
-    const uint32_t fa = zero_flags[(size_t)bz * 2 * half + iz], fb = zero_flags[(size_t)bz * 2 * half + half + iz];
-    if (fa | fb) {
-      const uint32_t* src = in + (size_t)bz * batch_stride + (size_t)((fa ? half : 0) + iz) * 4 * POLY;
-      uint32_t* dst = out + (size_t)bz * batch_stride + (size_t)iz * 4 * POLY;
-#pragma unroll
-      for (int rho = 0; rho < 2; rho++) {
-        uint32_t x[8];
-        ld8_ro(x, src + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8);
-        st8(dst + ((size_t)rho * 2 + blockIdx.y) * POLY + threadIdx.x * 8, x);
-      }
-      return;
-    }
-  }
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
-  uint32_t* sm0 = reinterpret_cast<uint32_t*>(dyn_smem);
-  uint32_t* sm1 = sm0 + NTT_SMEM_WORDS;
-  Twiddle* tw = reinterpret_cast<Twiddle*>(sm1 + NTT_SMEM_WORDS);
-  Grp g = make_grp_single(P, sm0, blockIdx.y);
-  const TwConst lo{g.n, 0};
-  TwRegsC rc;
-  TwRegsD rd;
-  if (REGTW) { rc.load(g.tid, TwGlobal{g.fwd}); rd.load(g.tid, TwGlobal{g.fwd}); }
-  else stage_fwd_twiddles(g, tw);
-  const TwShared hi{tw};
-  const int b = blockIdx.x / half, i = blockIdx.x % half;
-  const uint32_t* ci = in + (size_t)b * batch_stride + (size_t)i * 4 * POLY;
-  const uint32_t* ch = in + (size_t)b * batch_stride + (size_t)(half + i) * 4 * POLY;
-  const uint32_t* C = c_pos + (size_t)(b / slices_per_query) * c_batch_stride;
-  const int cols = 2 * t_gsw;
-  const size_t row_step = (size_t)cols * 2 * POLY;
-  const uint64_t mask = (1ull << bits) - 1;
-  const uint32_t q = g.q;
-
-  uint64_t acc[2][8];
-#pragma unroll
-  for (int r = 0; r < 2; r++)
-#pragma unroll
-    for (int e = 0; e < 8; e++) acc[r][e] = 0;
   int cnt = 0;                                   // products (< 2^60 each) held by every accumulator: at most 16
 #pragma unroll 1
   for (int rho = 0; rho < 2; rho++) {
@@ -602,8 +488,7 @@ k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict
         x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
         x1[a] = digit_diff<BYTE>(vh[a], vi[a], k + 1, bits, mask, q);
       }
-      if (REGTW) ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, rc, rd, q, CtaSync());
-      else ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
+      ntt_forward_group2_lz<NTT_OUT_LAZY16>(g.tid, x0, x1, sm0, sm1, lo, hi, q, CtaSync());
       if (cnt + 2 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
       cnt += 2;
 #pragma unroll
@@ -621,8 +506,7 @@ k_fold_res_lz(DevParams P, const uint32_t* __restrict__ in, uint32_t* __restrict
       uint32_t x0[8];
 #pragma unroll
       for (int a = 0; a < 8; a++) x0[a] = digit_diff<BYTE>(vh[a], vi[a], k, bits, mask, q);
-      if (REGTW) ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, rc, rd, q, CtaSync());
-      else ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, hi, q, CtaSync());
+      ntt_forward_group_lz<NTT_OUT_LAZY16>(g.tid, x0, sm0, lo, hi, q, CtaSync());
       if (cnt + 1 > 16) { acc_reduce<2>(acc, g); cnt = 1; }
       cnt += 1;
 #pragma unroll
@@ -1321,38 +1205,22 @@ void launch_fold_res(const DevParams& P, const uint32_t* in, uint32_t* out, size
                      const uint32_t* c_pos, size_t c_batch_stride, int slices_per_query, int t_gsw, int bits,
                      int variant, uint32_t* zero_flags, cudaStream_t s) {
   if (batch == 0 || half == 0) return;
-  opt_in_smem(k_fold_res<2>, (int)kDynSmemFold);
-  opt_in_smem(k_fold_res<3>, (int)kDynSmemFold);
   if (zero_flags) {            // scratch of batch * 2 * half words: recomputed every round, as the reference re-tests every step
     ++g_kernel_launches;
     k_ct_zero_flags<<<(unsigned)(batch * 2 * half), 256, 0, s>>>(in, batch_stride, 2 * half, zero_flags);
   }
   ++g_kernel_launches;
-  // variant 2 (default): relaxed-range transforms, 3 CTAs per SM; 3: the same at 2 CTAs per SM
-  if (variant >= 2 && variant <= 4) {
-    const dim3 grid((unsigned)(batch * half), 2);
-#define FOLD_LZ(MINB, BYTE, REGTW)                                                                                      \
-    do {                                                                                                                \
-      const size_t smem = REGTW ? (size_t)(2 * NTT_SMEM_WORDS) * 4 : kDynSmemFold;                                      \
-      opt_in_smem(k_fold_res_lz<MINB, BYTE, REGTW>, (int)smem);                                                         \
-      k_fold_res_lz<MINB, BYTE, REGTW><<<grid, 256, smem, s>>>(P, in, out, batch_stride, half, c_pos, c_batch_stride,   \
-                                                              slices_per_query, t_gsw, bits, zero_flags);              \
-    } while (0)
-    if (variant == 2) { if (bits == 8) FOLD_LZ(3, true, false); else FOLD_LZ(3, false, false); }
-    else if (variant == 3) { if (bits == 8) FOLD_LZ(2, true, false); else FOLD_LZ(2, false, false); }
-    else { if (bits == 8) FOLD_LZ(2, true, true); else FOLD_LZ(2, false, true); }       // 4: twiddles in registers, 2 CTAs per SM
+  // variant 3: 2 CTAs per SM (128 registers); anything else: 3 CTAs per SM (80 registers) — same speed on S8, kept for A/B runs
+  const dim3 grid((unsigned)(batch * half), 2);
+#define FOLD_LZ(MINB, BYTE)                                                                                             \
+  do {                                                                                                                  \
+    opt_in_smem(k_fold_res_lz<MINB, BYTE>, (int)kDynSmemFold);                                                          \
+    k_fold_res_lz<MINB, BYTE><<<grid, 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos, c_batch_stride,    \
+                                                             slices_per_query, t_gsw, bits, zero_flags);               \
+  } while (0)
+  if (variant == 3) { if (bits == 8) FOLD_LZ(2, true); else FOLD_LZ(2, false); }
+  else { if (bits == 8) FOLD_LZ(3, true); else FOLD_LZ(3, false); }
 #undef FOLD_LZ
-    return;
-  }
-  // variant 1: 3 CTAs per SM (80 registers, a few spills) instead of 2 (128 registers)
-  if (variant == 1)
-    k_fold_res<3><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
-                                                                              c_batch_stride, slices_per_query, t_gsw, bits,
-                                                                              zero_flags);
-  else
-    k_fold_res<2><<<dim3((unsigned)(batch * half), 2), 256, kDynSmemFold, s>>>(P, in, out, batch_stride, half, c_pos,
-                                                                              c_batch_stride, slices_per_query, t_gsw, bits,
-                                                                              zero_flags);
 }
 void launch_from_ntt(const DevParams& P, uint64_t* out_raw, const uint32_t* in, size_t count, cudaStream_t s) {
   if (count) ++g_kernel_launches, k_from_ntt<<<(unsigned)count, CTA, 0, s>>>(P, out_raw, in);

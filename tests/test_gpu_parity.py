@@ -315,7 +315,7 @@ def test_error_behaviour():
     S, P, cl, pp, db, G, gdb, gpp = setup_case("T")
     with pytest.raises(S.B200PirError):
         S.multiply_reg_by_database(G, gdb, 99, np.zeros(P.dim0 * 2 * P.N, dtype=np.uint64))      # slice out of range
-    with pytest.raises(S.B200PirError):
+    with pytest.raises((S.B200PirError, ValueError)):
         S.fold_ciphertexts(G, np.zeros(3 * 2 * P.N, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64))
     with pytest.raises(S.B200PirError):
         S.Params(device=99, **P.kw)
