@@ -411,7 +411,14 @@ def main():
                     help="queries per step (whole job); must be a multiple of --gpus.  Default: --batch-per-gpu x GPUs")
     ap.add_argument("--batch-per-gpu", type=int, default=int(os.environ.get("B200PIR_BENCH_BATCH", "16")),
                     help="concurrent queries per GPU (BASELINE.json config #3: 128 concurrent queries on 8 GPUs)")
-    ap.add_argument("--waves", type=int, default=2,
+    ap.add_argument("--exchange", default=os.environ.get("B200PIR_BENCH_EXCHANGE", "ce"), choices=["ce", "nccl"],
+                    help="N > 1: how the expanded queries reach the other ranks.  ce = pushed into the peers' gather buffers by the "
+                         "copy engines over CUDA-IPC mappings (no SM-resident collective kernels competing with the compute kernels; "
+                         "a 4-byte NCCL all-reduce per wave orders the ranks); nccl = ncclAllGather")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="N > 1, copy-engine exchange: do not enqueue the expansion + pushes of step k + 1 before the first dimension "
+                         "of step k")
+    ap.add_argument("--waves", type=int, default=None,
                     help="N > 1: each rank's queries are processed in this many waves so that the all-gather of one wave's "
                          "expanded queries overlaps the expansion / first dimension of the other")
     ap.add_argument("--mul-variant", type=int, default=0)
@@ -525,6 +532,8 @@ def main():
     Bl = B // N                                      # queries this rank receives / answers per step
     W = 1
     if N > 1:
+        if args.waves is None:
+            args.waves = 1 if (args.exchange == "ce" and args.pipeline) else 2     # the pipeline already hides the transfer
         W = args.waves if (args.waves >= 1 and Bl % args.waves == 0) else 1
         Blw, Bw = Bl // W, (Bl // W) * N             # per wave: local queries, global queries
         fold_words = kw["nu_2"] * 2 * 2 * kw["t_gsw"] * 2 * POLY
@@ -537,16 +546,99 @@ def main():
         d_partial = [zi(Bw * d["slices"] * ct_words) for _ in range(W)]
         d_gather = [zi(N * Bw * d["slices"] * ct_words) for _ in range(W)]
         coll_bytes = W * (N - 1) * (d_qexp_l[0].numel() + d_vf_l[0].numel() + d_partial[0].numel()) * 4
+        # ---- copy-engine exchange: gather buffers allocated through the library (cudaMalloc + IPC handle), double-buffered across
+        # steps, every peer's buffers mapped into this process
+        exchange = args.exchange
+        if exchange == "ce":
+            try:
+                qexp_b, vf_b = Blw * d["dim0"] * POLY * 16, Blw * fold_words * 4          # bytes one rank contributes per wave
+                mine, handles = {}, {}
+                NBUF = 3
+                for par in range(NBUF):
+                    for w in range(W):
+                        for kind, nbytes in (("q", N * qexp_b), ("v", N * vf_b)):
+                            ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                            check(LIB.b200pir_peer_alloc(local_rank, nbytes, C.byref(ptr), h))
+                            mine[(par, w, kind)] = ptr.value
+                            handles[(par, w, kind)] = h.raw
+                all_handles = [None] * N
+                dist.all_gather_object(all_handles, handles)
+                peer = {}
+                for r in range(N):
+                    if r == rank:
+                        continue
+                    for key, h in all_handles[r].items():
+                        ptr = C.c_void_p()
+                        check(LIB.b200pir_peer_open(local_rank, h, C.byref(ptr)))
+                        peer[(r,) + key] = ptr.value
+                copy_stream = torch.cuda.Stream()
+                tiny = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(W)]
+                prev_barrier = [None] * W
+                barriers = {}
+                step_no = [0]
+            except Exception as e:
+                log("peer-memory exchange unavailable (%r): falling back to ncclAllGather" % (e,))
+                exchange = "nccl (peer setup failed: %s)" % (str(e)[:120],)
+
+    # ---- N > 1, copy-engine exchange.  NBUF gather-buffer sets rotate over the steps.  Safety of a push into set (k % NBUF) at
+    # the peers: they last read that set in step k - NBUF; barrier(k - 1) (a 4-byte all-reduce each rank issues after its
+    # pushes of step k - 1) has completed before the push starts, hence every rank has issued its pushes of step k - 1, and
+    # those are stream-ordered after that rank's first dimension of step k - 1 - (pipelined ? 1 : 0) >= k - NBUF.
+    def ce_expand_push(k):
+        bset = k % NBUF
+        cur = torch.cuda.current_stream()
+        for w in range(W):
+            # expand straight into this rank's slot of its own gather buffers, then push the slot to every peer
+            q_own = mine[(bset, w, "q")] + rank * qexp_b
+            v_own = mine[(bset, w, "v")] + rank * vf_b
+            check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                if prev_barrier[w] is not None:
+                    prev_barrier[w].wait()
+                for r in range(N):
+                    if r != rank:
+                        check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "q")] + rank * qexp_b, q_own, qexp_b, copy_stream.cuda_stream))
+                        check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "v")] + rank * vf_b, v_own, vf_b, copy_stream.cuda_stream))
+                # 4-byte all-reduce ordered after the pushes: complete when every rank's pushes have landed
+                prev_barrier[w] = dist.all_reduce(tiny[w], async_op=True)
+            barriers[(k, w)] = prev_barrier[w]
+
+    def ce_compute(k):
+        bset = k % NBUF
+        sv = []
+        for w in range(W):
+            barriers.pop((k, w)).wait()
+            check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, mine[(bset, w, "q")], mine[(bset, w, "v")], Bw, d_partial[w].data_ptr()))
+            sv.append(dist.all_gather_into_tensor(d_gather[w], d_partial[w], async_op=True))
+        for w in range(W):
+            sv[w].wait()
+            check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, d_gather[w].data_ptr(), N, Bw, rank * Blw, Blw,
+                                                 mine[(bset, w, "v")] + rank * vf_b, d_out.data_ptr() + w * Blw * rb))
 
     def step_dev():
         if N == 1:
             check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), B, d_out.data_ptr()))
+        elif exchange == "ce":
+            # each rank expands the Bl queries it received and pushes them to every peer; every rank runs the first dimension +
+            # local fold rounds of ALL B queries on its rows; survivors are all-gathered (NCCL, 32 KiB per query and slice); each
+            # rank finishes its own Bl queries.  Pipelined: the expansion and the pushes of step k + 1 are enqueued BEFORE the
+            # first dimension of step k, so the NVLink transfer (24 MiB per query to every peer) runs under step k's compute.
+            k = step_no[0]
+            step_no[0] += 1
+            if args.pipeline:
+                if k == 0:
+                    ce_expand_push(0)
+                ce_expand_push(k + 1)
+                ce_compute(k)
+            else:
+                ce_expand_push(k)
+                ce_compute(k)
         else:
-            # each rank expands the Bl queries it received; expanded queries are all-gathered; every rank runs the
-            # first dimension + local fold rounds of ALL B queries on its rows; survivors are all-gathered; each rank
-            # finishes (last log2 N rounds + pack + encode) its own Bl queries.  The queries go through in W waves: the
-            # collectives are asynchronous (NCCL's stream), so wave w's all-gather runs under wave w+1's expansion and
-            # wave w-1's first dimension; .wait() orders the compute stream after the collective, never the host.
+            # NCCL all-gather of the expanded queries in W waves: the collectives are asynchronous (NCCL's stream), so wave w's
+            # all-gather runs under wave w+1's expansion and wave w-1's first dimension
             ag = []
             for w in range(W):
                 check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw,
@@ -748,12 +840,15 @@ def main():
             "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W, "queries_per_pass": per_pass,
+                       "exchange": (exchange if N > 1 else None), "pipelined": bool(N > 1 and exchange == "ce" and args.pipeline),
                        "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
                        "first_dimension_kernel": kname,
-                       "parallelism": ("rows ii mod %d, %d concurrent queries per GPU; queries expanded by the receiving rank; "
-                                       "asynchronous NCCL all-gather of expanded queries and of surviving ciphertexts in %d "
-                                       "waves (%d bytes received per rank per step)" % (N, B // N, W, coll_bytes))
+                       "parallelism": ("rows ii mod %d, %d concurrent queries per GPU; queries expanded by the receiving rank; expanded "
+                                       "queries exchanged by %s, surviving ciphertexts by asynchronous NCCL all-gather, in %d "
+                                       "waves (%d bytes received per rank per step)"
+                                       % (N, B // N, "copy-engine pushes into peer memory (CUDA IPC over NVLink)" if exchange == "ce"
+                                          else "asynchronous NCCL all-gather", W, coll_bytes))
                        if N > 1 else "single GPU",
                        "l2": "inputs larger than L2 (database %.1f GiB per GPU streamed every step)" % (db_bytes / 2**30)},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": (B * qb) if N == 1 else B * 2 * POLY * 8,

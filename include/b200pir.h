@@ -95,6 +95,12 @@ int b200pir_db_fill_synthetic(b200pir_ctx* ctx, b200pir_db* db, uint64_t seed);
 /* What `db` is: its layout (the "db_format" it was created with, resolved when that was -1), the second-dimension rows
  * this GPU holds, and its size in HBM.  Any out pointer may be NULL. */
 int b200pir_db_info(b200pir_db* db, int* format, uint64_t* local_rows, uint64_t* hbm_bytes);
+/* lib/server's SparseDb (db/sparse_db.rs:5-47): an item exists once it has been written (upsert / update_item_raw; bulk uploads,
+ * file loads and the synthetic fill write every item).  `items` = present items on this GPU, `capacity` = slices x local rows x
+ * dim0.  Absent items are zero polynomials in HBM, so results equal the sparse server's sums; on the tcgen05 layout every
+ * 32-row x 32-j tile without a present item is neither fetched nor multiplied (multiply_reg_by_sparse_database skips absent
+ * items, compute/dot_product.rs:35). */
+int b200pir_db_present_items(b200pir_db* db, uint64_t* items, uint64_t* capacity);
 
 /* ---- public parameters: replaces &PublicParameters (client.rs:146-152), all matrices in NTT form ---- */
 /* v_packing: num_packing x (n+1) x t_conv ; v_expansion_left: g x 2 x t_exp_left ;
@@ -207,6 +213,17 @@ int b200pir_finish_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t*
  * out[0..8] = expand, first-dim multiply kernel, from_ntt, fold, pack, encode, total, multiply launches, re-tiling of the query
  * operand for the tensor-core first dimension (k_query_to_tc5 / k_query_to_frag) */
 int b200pir_last_stage_ms(b200pir_ctx* ctx, double* out9);
+/* ---- peer memory for the multi-GPU exchange (one process per GPU, NVLink) ------------------------------------------------
+ * The expanded queries every rank needs (24 MiB per query) are PUSHED into the peers' gather buffers by the copy engines
+ * (cudaMemcpyAsync over CUDA-IPC mappings), not all-gathered by SM-resident collective kernels that compete with the
+ * compute kernels for SMs.  b200pir_peer_alloc: device buffer + the 64-byte IPC handle to hand to the other ranks (any
+ * transport); b200pir_peer_open: map a peer's buffer (handle from ANOTHER process) for access from `device`;
+ * b200pir_peer_copy_async: stream-ordered copy between any two device pointers (local or mapped). */
+int b200pir_peer_alloc(int device, size_t bytes, void** out_ptr, uint8_t out_handle[64]);
+int b200pir_peer_open(int device, const uint8_t handle[64], void** out_ptr);
+int b200pir_peer_close(int device, void* mapped_ptr);
+int b200pir_peer_free(int device, void* ptr);
+int b200pir_peer_copy_async(void* dst, const void* src, size_t bytes, void* cuda_stream);
 /* Number of CUDA kernels this library has launched from the calling host thread since load. */
 unsigned long long b200pir_kernel_launches(void);
 

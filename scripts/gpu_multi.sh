@@ -21,8 +21,11 @@ PY
 }
 {
 echo "== $N GPUs"
-run "default" X=1 --
+run "copy engines, pipelined (default)" X=1 --
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_n${N}.json
-run "NCCL_MAX_CTAS=8" NCCL_MAX_CTAS=8 --
-run "waves 1" X=1 -- --waves 1
+tail -3 gpurun_out/multi.err | cut -c1-300
+if [ "$N" = "2" ]; then
+run "copy engines, 2 waves, no pipeline" X=1 -- --no-pipeline
+run "nccl all-gather, 2 waves" X=1 -- --exchange nccl
+fi
 } 2>&1 | tee gpurun_out/gpu_multi_${TAG}_n${N}.log

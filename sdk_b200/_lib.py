@@ -44,6 +44,7 @@ def _load():
         "b200pir_db_update_item_raw": (C.c_int, [vp, vp, C.c_uint64, u8p, C.c_size_t]),
         "b200pir_db_fill_synthetic": (C.c_int, [vp, vp, C.c_uint64]),
         "b200pir_db_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "b200pir_db_present_items": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "b200pir_pp_create": (C.c_int, [vp, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
         "b200pir_pp_create_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(vp)]),
         "b200pir_query_from_bytes": (C.c_int, [vp, u8p, C.c_size_t, u64p]),
@@ -75,6 +76,11 @@ def _load():
         "b200pir_finish_queries_dev": (C.c_int, [vp, vp, u32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, u32p, u8p]),
         "b200pir_last_stage_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "b200pir_kernel_launches": (C.c_ulonglong, []),
+        "b200pir_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
+        "b200pir_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
+        "b200pir_peer_close": (C.c_int, [C.c_int, vp]),
+        "b200pir_peer_free": (C.c_int, [C.c_int, vp]),
+        "b200pir_peer_copy_async": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "b200pir_dpir_create": (C.c_int, [C.c_int, u32p, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_create_synthetic": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_dpir_destroy": (None, [vp]),

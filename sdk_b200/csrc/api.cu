@@ -217,6 +217,42 @@ struct b200pir_db {
   Tc5Geom T;
   ImmaGeom F;
   size_t slice_cells() const { return (size_t)rows * (ctx->dim0 / 2) * POLY; }
+  // Presence (lib/server's SparseDb, db/sparse_db.rs:5-47: an item exists once it has been written).  Storage stays dense in HBM
+  // (absent = zero polynomial, so every sum is unchanged); what the map buys is COST: on the tcgen05 path whole 32-row x 32-j
+  // tiles without a present item are neither fetched nor multiplied (tile_mask, one bit per tile, kept on the device).
+  std::vector<uint64_t> present;          // bit ((slice * rows + il) * dim0 + j)
+  uint64_t present_count = 0;
+  std::vector<uint32_t> h_tile_mask;      // [slice][mt], bit ks
+  DevBuf<uint32_t> tile_mask;
+  uint64_t capacity() const { return (uint64_t)ctx->slices * rows * ctx->dim0; }
+  void presence_init() {
+    present.assign((capacity() + 63) / 64, 0);
+    present_count = 0;
+    h_tile_mask.assign((size_t)ctx->slices * T.mt, 0u);
+    tile_mask.alloc(h_tile_mask.size());
+    B200_CUDA(cudaMemset(tile_mask.p, 0, h_tile_mask.size() * 4));
+  }
+  // one item written (stream-ordered update of the device mask word)
+  void mark(int slice, int il, int j, cudaStream_t s) {
+    const uint64_t bit = ((uint64_t)slice * rows + il) * ctx->dim0 + j;
+    if (!((present[bit >> 6] >> (bit & 63)) & 1)) { present[bit >> 6] |= 1ull << (bit & 63); present_count++; }
+    const size_t w = (size_t)slice * T.mt + (il >> 5);
+    const uint32_t nv = h_tile_mask[w] | (1u << (j >> 5));
+    if (nv != h_tile_mask[w]) {
+      h_tile_mask[w] = nv;
+      B200_CUDA(cudaMemcpyAsync(tile_mask.p + w, &h_tile_mask[w], 4, cudaMemcpyHostToDevice, s));
+    }
+  }
+  // a whole slice written at once (bulk upload, file load, synthetic fill): every item of it exists from now on
+  void mark_slice(int slice, cudaStream_t s) {
+    const uint64_t lo = (uint64_t)slice * rows * ctx->dim0, hi = lo + (uint64_t)rows * ctx->dim0;
+    for (uint64_t b = lo; b < hi; b++)
+      if (!((present[b >> 6] >> (b & 63)) & 1)) { present[b >> 6] |= 1ull << (b & 63); present_count++; }
+    const uint32_t full = T.ks >= 32 ? 0xffffffffu : ((1u << T.ks) - 1u);
+    for (int m = 0; m < T.mt; m++) h_tile_mask[(size_t)slice * T.mt + m] = full;
+    B200_CUDA(cudaMemcpyAsync(tile_mask.p + (size_t)slice * T.mt, &h_tile_mask[(size_t)slice * T.mt], (size_t)T.mt * 4,
+                              cudaMemcpyHostToDevice, s));
+  }
 };
 
 struct b200pir_pp {
@@ -415,7 +451,7 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
         launch_query_to_tc5(db->T, qdev + qi * q_stride, q_stride, nq, c->w_qt.p, c->stream);
       }
       b200pir_ctx::Scope sc(c, ST_MUL);
-      launch_multiply_tc5(c->dp, db->T, db->t.p, c->w_qt.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
+      launch_multiply_tc5(c->dp, db->T, db->t.p, db->tile_mask.p, c->w_qt.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
                           c->sm_count, c->stream);
       c->mul_launches++;
     }
@@ -672,6 +708,7 @@ int b200pir_db_create(b200pir_ctx* c, uint64_t shard_index, uint64_t shard_count
   db->F = make_imma_geom(c->dim0, db->rows);
   db->T = make_tc5_geom(c->dim0, db->rows);
   db->format = c->db_format >= 0 ? c->db_format : (tc5_supported(db->T) ? 2 : 1);
+  db->presence_init();
   if (db->format == 0) {
     size_t cells = (size_t)c->slices * db->slice_cells();
     db->d.alloc(cells);
@@ -724,6 +761,8 @@ void upload_slice_impl(b200pir_ctx* c, b200pir_db* db, uint64_t slice, Fetch fet
     launch_db_to_tc5(db->T, tmp.p, db->t.p, (int)slice, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
   }
+  db->mark_slice((int)slice, c->stream);
+  B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
 }
 }  // namespace
@@ -788,6 +827,7 @@ int b200pir_db_upsert_item(b200pir_ctx* c, b200pir_db* db, uint64_t slice, uint6
   if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
   else if (db->format == 2) launch_db_upsert_tc5(db->T, db->t.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
   else launch_db_upsert_frag(db->F, db->f.p, (int)slice, ii / db->shard.count, j, tmp.p, c->stream);
+  db->mark((int)slice, ii / db->shard.count, j, c->stream);
   // the host RwLock gives upserts exclusive access (bin/server.rs:35,49): finish before returning
   B200_CUDA(cudaStreamSynchronize(c->stream));
   API_END
@@ -815,6 +855,7 @@ int b200pir_db_update_item_raw(b200pir_ctx* c, b200pir_db* db, uint64_t db_idx, 
     if (db->format == 0) launch_db_upsert(c->geom(db->rows), db->d.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
     else if (db->format == 2) launch_db_upsert_tc5(db->T, db->t.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
     else launch_db_upsert_frag(db->F, db->f.p, (int)s, ii / db->shard.count, j, polys.p + s * POLY, c->stream);
+    db->mark((int)s, ii / db->shard.count, j, c->stream);
   }
   B200_CUDA(cudaStreamSynchronize(c->stream));                                // writers hold the host write lock
   B200_CUDA(cudaGetLastError());
@@ -871,10 +912,19 @@ int b200pir_db_load_raw_file(b200pir_ctx* c, b200pir_db* db, const char* path) {
     }
     B200_CUDA(cudaStreamSynchronize(c->stream));                              // `host` is refilled next
   }
+  for (int s = 0; s < c->slices; s++) db->mark_slice(s, c->stream);            // load_db_from_seek builds a dense database
+  B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
   API_END
 }
 
+int b200pir_db_present_items(b200pir_db* db, uint64_t* items, uint64_t* capacity) {
+  API_BEGIN
+  if (!db) throw Error(B200PIR_E_BADARG, "null db");
+  if (items) *items = db->present_count;
+  if (capacity) *capacity = db->capacity();
+  API_END
+}
 int b200pir_db_info(b200pir_db* db, int* format, uint64_t* local_rows, uint64_t* hbm_bytes) {
   API_BEGIN
   if (!db) throw Error(B200PIR_E_BADARG, "null db");
@@ -904,6 +954,7 @@ int b200pir_db_fill_synthetic(b200pir_ctx* c, b200pir_db* db, uint64_t seed) {
       else launch_db_to_frag(db->F, tmp.p, db->f.p, s0, c->stream);
     }
   }
+  for (int s0 = 0; s0 < c->slices; s0++) db->mark_slice(s0, c->stream);
   B200_CUDA(cudaStreamSynchronize(c->stream));
   B200_CUDA(cudaGetLastError());
   API_END
@@ -1150,7 +1201,7 @@ int b200pir_multiply_reg_by_database(b200pir_ctx* c, b200pir_db* db, uint64_t sl
     DevBuf<uint8_t> qt(tc5_query_bytes(db->T));
     DevBuf<uint32_t> zm((size_t)c->slices * rows * 4 * POLY);
     launch_query_to_tc5(db->T, qd.p, 0, 1, qt.p, c->stream);
-    launch_multiply_tc5(c->dp, db->T, db->t.p, qt.p, zm.p, 0, 1, (int)slice, 1, c->sm_count, c->stream);
+    launch_multiply_tc5(c->dp, db->T, db->t.p, db->tile_mask.p, qt.p, zm.p, 0, 1, (int)slice, 1, c->sm_count, c->stream);
     launch_zmajor_to_ntt32(db->F, zm.p, o.p + (size_t)slice * rows * 4 * POLY, (int)slice, c->stream);
     B200_CUDA(cudaStreamSynchronize(c->stream));
   } else {
@@ -1637,6 +1688,49 @@ int b200pir_query_stage_b_dev(b200pir_ctx* c, b200pir_pp* pp, const uint32_t* ga
 }
 
 unsigned long long b200pir_kernel_launches(void) { return g_kernel_launches; }
+
+// ---- peer memory (CUDA IPC) for the copy-engine exchange of the multi-GPU flow
+int b200pir_peer_alloc(int device, size_t bytes, void** out_ptr, uint8_t out_handle[64]) {
+  API_BEGIN
+  if (!out_ptr || !out_handle || !bytes) throw Error(B200PIR_E_BADARG, "null or empty argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  B200_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  B200_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); throw Error(B200PIR_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(out_handle, &h, 64);
+  *out_ptr = p;
+  API_END
+}
+int b200pir_peer_open(int device, const uint8_t handle[64], void** out_ptr) {
+  API_BEGIN
+  if (!handle || !out_ptr) throw Error(B200PIR_E_BADARG, "null argument");
+  B200_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  B200_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  API_END
+}
+int b200pir_peer_close(int device, void* mapped_ptr) {
+  API_BEGIN
+  B200_CUDA(cudaSetDevice(device));
+  if (mapped_ptr) B200_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
+  API_END
+}
+int b200pir_peer_free(int device, void* ptr) {
+  API_BEGIN
+  B200_CUDA(cudaSetDevice(device));
+  if (ptr) B200_CUDA(cudaFree(ptr));
+  API_END
+}
+int b200pir_peer_copy_async(void* dst, const void* src, size_t bytes, void* cuda_stream) {
+  API_BEGIN
+  if (!dst || !src) throw Error(B200PIR_E_BADARG, "null argument");
+  if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+  API_END
+}
 
 int b200pir_last_stage_ms(b200pir_ctx* c, double* out9) {
   API_BEGIN

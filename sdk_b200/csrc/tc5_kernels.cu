@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
 k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const uint8_t* __restrict__ qt,
                uint32_t* __restrict__ out_zm, size_t out_stride, int nq, int slice_begin, int slice_count,
                uint32_t* __restrict__ dbg /* bring-up aid: raw accumulators of CTA 0's first TC5_DBG_TILES tiles, or null */,
-               int dbg_mode) {
+               int dbg_mode, const uint32_t* __restrict__ tile_mask /* [slice][mt]: bit ks = the 32-row x 32-j tile holds a present item */) {
   const bool hinted = (dbg_mode & 4) != 0;
 #define mbar_wait(bar, par) do { if (hinted) mbar_wait_hinted(bar, par); else (mbar_wait)(bar, par); } while (0)
   constexpr int TC5_KS_PER_STAGE = KSPS;
@@ -187,13 +187,23 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
       for (int sl = 0; sl < slice_count; sl++)
         for (int mt = 0; mt < T.mt; mt++) {
           const uint8_t* src = dbt + tc5_db_tile(T, slice_begin + sl, n, z, mt, 0) * TC5_TILE;
+          // lib/server's sparse database (db/sparse_db.rs, compute/dot_product.rs:35): tiles without a present item are neither
+          // fetched nor multiplied (they are zero: the sums are unchanged); a stage without any such tile takes no ring slot
+          const uint32_t mask = __ldg(tile_mask + (size_t)(slice_begin + sl) * T.mt + mt);
           for (int st = 0; st < stages_per_tile; st++) {
             const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
+            const uint32_t full_m = ks_here == 32 ? 0xffffffffu : ((1u << ks_here) - 1u);
+            const uint32_t km = (mask >> (st * TC5_KS_PER_STAGE)) & full_m;
+            if (km == 0) continue;
             mbar_wait(&S->empty[stage], sphase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&S->full[stage], (uint32_t)ks_here * TC5_TILE);
-              bulk_g2s(smem_a + (size_t)stage * TC5_STAGE_BYTES, src + (size_t)st * TC5_STAGE_BYTES, (uint32_t)ks_here * TC5_TILE,
-                       &S->full[stage]);
+              uint8_t* dst = smem_a + (size_t)stage * TC5_STAGE_BYTES;
+              const uint8_t* from = src + (size_t)st * TC5_STAGE_BYTES;
+              mbar_expect_tx(&S->full[stage], (uint32_t)__popc(km) * TC5_TILE);
+              if (km == full_m) bulk_g2s(dst, from, (uint32_t)ks_here * TC5_TILE, &S->full[stage]);
+              else
+                for (int kk = 0; kk < ks_here; kk++)
+                  if ((km >> kk) & 1u) bulk_g2s(dst + (size_t)kk * TC5_TILE, from + (size_t)kk * TC5_TILE, TC5_TILE, &S->full[stage]);
             }
             __syncwarp();
             if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
@@ -208,13 +218,18 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
       const int bb = it % BBUFS;
       mbar_wait(&S->bfull[bb], (it / BBUFS) & 1);
       const uint32_t b_addr = smem_u32(smem_b + (size_t)bb * b_bytes);
-      for (int t = 0; t < tiles_per_item; t++, tile_no++) {
+      for (int t = 0, sl = 0, mt = 0; t < tiles_per_item; t++, tile_no++, mt++) {
+        if (mt == T.mt) { mt = 0; sl++; }
+        const uint32_t mask = __ldg(tile_mask + (size_t)(slice_begin + sl) * T.mt + mt);
+        uint32_t issued = 0;                                          // the first MMA of a tile overwrites the accumulator
         const int ab = tile_no % ABUFS;
         mbar_wait(&S->tempty[ab], ((tile_no / ABUFS) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)ab * TC5_N;
         for (int st = 0; st < stages_per_tile; st++) {
           const int ks_here = min(TC5_KS_PER_STAGE, T.ks - st * TC5_KS_PER_STAGE);
+          const uint32_t km = (mask >> (st * TC5_KS_PER_STAGE)) & (ks_here == 32 ? 0xffffffffu : ((1u << ks_here) - 1u));
+          if (km == 0) continue;                                      // nothing fetched for this stage (see the producer)
           mbar_wait(&S->full[stage], sphase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * TC5_STAGE_BYTES);
@@ -223,14 +238,16 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
             else {
 #pragma unroll
               for (int kk = 0; kk < TC5_KS_PER_STAGE; kk++) {
-                if (kk < ks_here) {
+                if ((km >> kk) & 1u) {
                   const int ks = st * TC5_KS_PER_STAGE + kk;
-                  tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), ks > 0 ? 1u : 0u);
+                  tc_mma_i8(d_addr, tc5_smem_desc(a_addr + kk * TC5_TILE), tc5_smem_desc(b_addr + ks * TC5_TILE), issued);
+                  issued = 1u;
                 }
               }
               tc_commit(&S->empty[stage]);                            // frees the A stage when these MMAs have completed
             }
           }
+          issued = 1u;                                                // warp-uniform copy of the elected lane's flag (km != 0)
           __syncwarp();
           if (++stage == TC5_STAGES) { stage = 0; sphase ^= 1; }
         }
@@ -262,13 +279,18 @@ k_multiply_tc5(DevParams P, Tc5Geom T, const uint8_t* __restrict__ dbt, const ui
         tc_fence_after();
         const int ii = mt * 32 + tc5_lane_row(quad, lane);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ab * TC5_N;
+        const bool empty_tile = __ldg(tile_mask + (size_t)slice * T.mt + mt) == 0;   // no MMA touched the accumulator: the product is zero
         // both 32-column chunks of this warp go to registers first, so the accumulator buffer is released after the TMEM
         // load latency, not after the arithmetic: the MMA of a later tile never waits for epilogue math
         uint32_t v[2][32];
-        if (!(dbg_mode & 2)) {
+        if (!(dbg_mode & 2) && !empty_tile) {
           tc_ld32(taddr + (colhalf * 2 + 0) * 32, v[0]);
           tc_ld32(taddr + (colhalf * 2 + 1) * 32, v[1]);
           tc_wait_ld();
+        }
+        if (empty_tile) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) { v[0][c] = 0; v[1][c] = 0; }
         }
         tc_fence_before();
         __syncwarp();
@@ -332,8 +354,8 @@ void launch_query_to_tc5(const Tc5Geom& T, const uint4* q_dev, size_t q_stride, 
   ++g_kernel_launches;
   k_query_to_tc5<<<dim3(POLY / 2, T.ks), 256, 0, s>>>(T, q_dev, q_stride, nq, qt);
 }
-void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint8_t* qt, uint32_t* out_zm,
-                         size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s) {
+void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint32_t* tile_mask, const uint8_t* qt,
+                         uint32_t* out_zm, size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s) {
   if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
   if (!tc5_supported(T)) throw Error(-2, "tcgen05 multiply: dim0 too large for one CTA's shared memory");
   ++g_kernel_launches;
@@ -359,7 +381,7 @@ void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* db
   do {                                                                                                                         \
     opt_in_smem(k_multiply_tc5<K, B, A>, 227 * 1024);                                                                          \
     k_multiply_tc5<K, B, A><<<grid, TC5_THREADS, smem, s>>>(P, T, dbt, qt, out_zm, out_stride, nq, slice_begin, slice_count,   \
-                                                            dbg, dbg_mode);                                                    \
+                                                            dbg, dbg_mode, tile_mask);                                         \
   } while (0)
 #define TC5_PICK_A(K, B) do { if (abufs == 2) TC5_LAUNCH(K, B, 2); else TC5_LAUNCH(K, B, 4); } while (0)
   if (ksps == 4) { if (bbufs == 2) TC5_PICK_A(4, 2); else TC5_PICK_A(4, 1); }

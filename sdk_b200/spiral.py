@@ -165,7 +165,9 @@ class Database:
         """{"format": resolved layout (0, 1 or 2), "local_rows": second-dimension rows on this GPU, "hbm_bytes": size}"""
         f, r, b = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
         check(LIB.b200pir_db_info(self._h, C.byref(f), C.byref(r), C.byref(b)))
-        return {"format": f.value, "local_rows": r.value, "hbm_bytes": b.value}
+        it, cap = C.c_uint64(0), C.c_uint64(0)
+        check(LIB.b200pir_db_present_items(self._h, C.byref(it), C.byref(cap)))
+        return {"format": f.value, "local_rows": r.value, "hbm_bytes": b.value, "present_items": it.value, "capacity": cap.value}
 
     def close(self):
         if getattr(self, "_h", None):
