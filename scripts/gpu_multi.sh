@@ -24,6 +24,12 @@ echo "== $N GPUs"
 run "copy engines, pipelined (default)" X=1 --
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_n${N}.json
 tail -3 gpurun_out/multi.err | cut -c1-300
+if [ "$N" = "8" ]; then
+echo "== BASELINE configs[2]: S256 (32 GiB plaintext = 256 GiB packed) over 8 GPUs, 128 concurrent queries"
+run "S256, 128 queries" X=1 -- --workload S256 --steps 5
+cp gpurun_out/multi.json gpurun_out/bench_${TAG}_s256_n${N}.json
+tail -3 gpurun_out/multi.err | cut -c1-300
+fi
 if [ "$N" = "2" ]; then
 run "copy engines, 2 waves, no pipeline" X=1 -- --no-pipeline
 run "nccl all-gather, 2 waves" X=1 -- --exchange nccl
