@@ -572,6 +572,9 @@ def main():
                         check(LIB.b200pir_peer_open(local_rank, h, C.byref(ptr)))
                         peer[(r,) + key] = ptr.value
                 copy_stream = torch.cuda.Stream()
+                # one stream per peer: pushes to different peers run on different copy engines at the same time (a single stream
+                # serialises them on one engine: 2.7 GB per step at N = 8 took ~14 ms, profiles/bench_r02_n8_single_copy_stream.json)
+                peer_streams = {r: torch.cuda.Stream() for r in range(N) if r != rank}
                 tiny = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(W)]
                 prev_barrier = [None] * W
                 barriers = {}
@@ -598,10 +601,15 @@ def main():
                 copy_stream.wait_event(ev)
                 if prev_barrier[w] is not None:
                     prev_barrier[w].wait()
-                for r in range(N):
-                    if r != rank:
-                        check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "q")] + rank * qexp_b, q_own, qexp_b, copy_stream.cuda_stream))
-                        check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "v")] + rank * vf_b, v_own, vf_b, copy_stream.cuda_stream))
+                go = torch.cuda.Event()
+                go.record(copy_stream)
+                for r, ps in peer_streams.items():
+                    ps.wait_event(go)
+                    check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "q")] + rank * qexp_b, q_own, qexp_b, ps.cuda_stream))
+                    check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "v")] + rank * vf_b, v_own, vf_b, ps.cuda_stream))
+                    done = torch.cuda.Event()
+                    done.record(ps)
+                    copy_stream.wait_event(done)
                 # 4-byte all-reduce ordered after the pushes: complete when every rank's pushes have landed
                 prev_barrier[w] = dist.all_reduce(tiny[w], async_op=True)
             barriers[(k, w)] = prev_barrier[w]
@@ -777,7 +785,11 @@ def main():
     # responses to ITS queries from the last step (d_out); it recomputes them on an UNSHARDED copy of the same synthetic
     # database with the single-GPU path (itself checked against the oracle by tests/) and the bytes must be identical.
     verified = None
-    if N > 1 and not args.no_verify:
+    full_db_bytes = d["slices"] * d["dim0"] * d["num_per"] * POLY * 8
+    verify_note = None
+    if N > 1 and not args.no_verify and full_db_bytes > 96 * 2**30:
+        verify_note = "skipped: the unsharded database (%.0f GiB) does not fit one GPU beside the shard" % (full_db_bytes / 2**30)
+    elif N > 1 and not args.no_verify:
         step_dev()
         torch.cuda.synchronize()
         full = S.Database(G, shard_index=0, shard_count=1, fmt=args.db_format)
@@ -859,7 +871,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
             "single_query_latency_ms": single_ms, "single_query_roofline": single_roofline,
             "concurrent_queries_sweep": sweep,
-            "verified": verified,
+            "verified": verified, "verify_note": verify_note,
             "timed_region": "un-instrumented; stage_ms_per_step and roofline.kernel_ms come from a separate pass of the same steps "
                             "with per-stage CUDA events",
         }
