@@ -551,7 +551,11 @@ def main():
         exchange = args.exchange
         if exchange == "ce":
             try:
-                qexp_b, vf_b = Blw * d["dim0"] * POLY * 16, Blw * fold_words * 4          # bytes one rank contributes per wave
+                # tcgen05 databases: the expanded queries travel as UMMA tile images (one image per rank and wave, re-tiled once by
+                # the rank that expanded them); other layouts: uint4 [query][dim0][2048]
+                use_images = args.db_format == 2 and Blw <= 16
+                qexp_b = int(LIB.b200pir_query_image_bytes(G._h)) if use_images else Blw * d["dim0"] * POLY * 16
+                vf_b = Blw * fold_words * 4                                               # bytes one rank contributes per wave
                 mine, handles = {}, {}
                 NBUF = 3
                 for par in range(NBUF):
@@ -594,7 +598,10 @@ def main():
             # expand straight into this rank's slot of its own gather buffers, then push the slot to every peer
             q_own = mine[(bset, w, "q")] + rank * qexp_b
             v_own = mine[(bset, w, "v")] + rank * vf_b
-            check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
+            if use_images:
+                check(LIB.b200pir_expand_queries_images_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
+            else:
+                check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
             ev = torch.cuda.Event()
             ev.record(cur)
             with torch.cuda.stream(copy_stream):
@@ -619,7 +626,11 @@ def main():
         sv = []
         for w in range(W):
             barriers.pop((k, w)).wait()
-            check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, mine[(bset, w, "q")], mine[(bset, w, "v")], Bw, d_partial[w].data_ptr()))
+            if use_images:
+                check(LIB.b200pir_first_dim_fold_images_dev(G._h, gdb._h, mine[(bset, w, "q")], N, Blw, mine[(bset, w, "v")],
+                                                            d_partial[w].data_ptr()))
+            else:
+                check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, mine[(bset, w, "q")], mine[(bset, w, "v")], Bw, d_partial[w].data_ptr()))
             sv.append(dist.all_gather_into_tensor(d_gather[w], d_partial[w], async_op=True))
         for w in range(W):
             sv[w].wait()
@@ -853,6 +864,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name, "params": kw, "batch": B, "batch_per_gpu": B // N, "waves": W, "queries_per_pass": per_pass,
                        "exchange": (exchange if N > 1 else None), "pipelined": bool(N > 1 and exchange == "ce" and args.pipeline),
+                       "exchange_format": ("UMMA tile images" if (N > 1 and exchange == "ce" and use_images) else "uint4 [query][dim0][2048]") if N > 1 else None,
                        "db_bytes_per_gpu": db_bytes,
                        "plaintext_bytes": d["slices"] * d["dim0"] * d["num_per"] * POLY,
                        "first_dimension_kernel": kname,

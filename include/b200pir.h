@@ -204,6 +204,15 @@ int b200pir_expand_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t*
                                void* q_expanded_dev, uint32_t* v_folding_dev);
 int b200pir_first_dim_fold_dev(b200pir_ctx* ctx, b200pir_db* db, const void* q_expanded_dev, const uint32_t* v_folding_dev,
                                size_t count, uint32_t* partial_dev);
+/* The first two phases with the first-dimension operand exchanged as UMMA tile images (tcgen05-layout databases): the rank that
+ * expands a group of <= 16 queries also re-tiles it, once (fused with reorient_reg_ciphertexts, util.rs:323-355); the receivers
+ * multiply straight from the images.  image_dev: b200pir_query_image_bytes(ctx) bytes per group; partial_dev as above with
+ * query index = group * per_group + i. */
+size_t b200pir_query_image_bytes(b200pir_ctx* ctx);
+int b200pir_expand_queries_images_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count, void* image_dev,
+                                      uint32_t* v_folding_dev);
+int b200pir_first_dim_fold_images_dev(b200pir_ctx* ctx, b200pir_db* db, const void* images_dev, size_t groups, size_t per_group,
+                                      const uint32_t* v_folding_dev, uint32_t* partial_dev);
 int b200pir_finish_queries_dev(b200pir_ctx* ctx, b200pir_pp* pp, const uint32_t* gathered_dev, size_t world,
                                size_t total_count, size_t first, size_t count, const uint32_t* v_folding_dev,
                                uint8_t* out_dev);

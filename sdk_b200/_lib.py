@@ -73,6 +73,9 @@ def _load():
         "b200pir_query_stage_b_dev": (C.c_int, [vp, vp, u64p, C.c_size_t, C.c_size_t, u8p]),
         "b200pir_expand_queries_dev": (C.c_int, [vp, vp, u64p, C.c_size_t, vp, u32p]),
         "b200pir_first_dim_fold_dev": (C.c_int, [vp, vp, vp, u32p, C.c_size_t, u32p]),
+        "b200pir_query_image_bytes": (C.c_size_t, [vp]),
+        "b200pir_expand_queries_images_dev": (C.c_int, [vp, vp, u64p, C.c_size_t, vp, u32p]),
+        "b200pir_first_dim_fold_images_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, u32p, u32p]),
         "b200pir_finish_queries_dev": (C.c_int, [vp, vp, u32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, u32p, u8p]),
         "b200pir_last_stage_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "b200pir_kernel_launches": (C.c_ulonglong, []),

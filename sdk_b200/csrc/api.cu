@@ -359,16 +359,25 @@ void run_coefficient_expansion(b200pir_ctx* c, b200pir_pp* pp, uint32_t* v, size
   }
 }
 
-// server.rs:525-591 for `nq` queries.  v: [nq][2^g][4][2048]; writes q_dev and v_fold of every query.
+// server.rs:525-591 for `nq` queries.  v: [nq][2^g][4][2048]; writes v_fold of every query and the first-dimension operand:
+// q_dev (uint4 [query][dim0][2048], reorient_reg_ciphertexts util.rs:323-355) or, when `images` is given (tcgen05 databases),
+// the UMMA tile images of groups of 16 queries directly (image g = queries 16g .., tc5_query_bytes apart): no intermediate.
 void run_expand_query(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_raw, uint32_t* v, uint4* q_dev,
-                      uint32_t* v_fold, int nq) {
+                      uint32_t* v_fold, int nq, uint8_t* images = nullptr) {
   const auto& hp = c->hp;
   cudaStream_t s = c->stream;
   // no clear of v: every slot the query path reads (even slots < 2 dim0, odd slots < 2 t_gsw nu_2) is written by the rounds
   launch_to_ntt_strided(c->dp, v, c->v_words(), query_raw, (size_t)2 * POLY, 2, nq, s);   // v[0] = query.ct.ntt()
   run_coefficient_expansion(c, pp, v, c->v_words(), nq, false);
   const int factor = hp.nu_2 > 0 ? 2 : 1;
-  launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
+  if (images) {
+    const Tc5Geom T = make_tc5_geom(c->dim0, 32);
+    for (int q0 = 0; q0 < nq; q0 += 16)
+      launch_reorient_to_tc5(T, v + (size_t)q0 * c->v_words(), c->v_words(), factor, std::min(16, nq - q0),
+                             images + (size_t)(q0 / 16) * tc5_query_bytes(T), s);
+  } else {
+    launch_reorient(c->geom(c->num_per), q_dev, (size_t)c->dim0 * POLY, v, c->v_words(), nq, factor, s);
+  }
   if (hp.nu_2 > 0)
     launch_regev_to_gsw(c->dp, v_fold, c->fold_words(), v, c->v_words(), nq, (int)hp.nu_2, 2, 1, c->pp_table(pp, (size_t)nq).conv,
                         (int)hp.t_gsw, (int)hp.t_conv, c->bits_conv, s);
@@ -407,15 +416,18 @@ const uint32_t* run_fold_res(b200pir_ctx* c, uint32_t* a, uint32_t* b, size_t ba
 }
 
 // expansion (or direct upload) for `count` queries already in w_query / w_qdev,w_vfold
-void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count) {
+void run_prepare(b200pir_ctx* c, b200pir_pp* pp, size_t count, bool images = false) {
   b200pir_ctx::Scope sc(c, ST_EXPAND);
-  if (c->hp.expand_queries) run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p, (int)count);
+  if (images) c->w_qt.ensure((count + 15) / 16 * tc5_query_bytes(make_tc5_geom(c->dim0, 32)));
+  if (c->hp.expand_queries)
+    run_expand_query(c, pp, c->w_query.p, c->w_v.p, c->w_qdev.p, c->w_vfold.p, (int)count, images ? c->w_qt.p : nullptr);
   // v_folding_neg (server.rs:680) is not materialised: the fold fast path uses G - C_k implicitly.
 }
 
 // first dimension + from_ntt + local fold.  Leaves survivors at w_cts[(qi*slices + slice)*rows*2*POLY].
+// `images`: the first-dimension operand already sits as tile images (groups of `per_group` <= 16 queries, one image each)
 void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const uint4* qdev = nullptr,
-                            const uint32_t* vfold = nullptr) {
+                            const uint32_t* vfold = nullptr, const uint8_t* images = nullptr, size_t per_group = 16) {
   if (!qdev) qdev = c->w_qdev.p;
   if (!vfold) vfold = c->w_vfold.p;
   const int rows = db->rows;
@@ -443,15 +455,17 @@ void run_first_dim_and_fold(b200pir_ctx* c, b200pir_db* db, size_t count, const 
     }
   } else if (db->format == 2) {
     // tcgen05 path: same z-major product as the mma.sync path, 16 queries per database pass
-    c->w_qt.ensure(tc5_query_bytes(db->T));
-    for (size_t qi = 0; qi < count; qi += 16) {
-      const int nq = (int)std::min<size_t>(16, count - qi);
-      {
+    if (!images) c->w_qt.ensure(tc5_query_bytes(db->T));
+    const size_t step = images ? per_group : 16;
+    for (size_t qi = 0, g = 0; qi < count; qi += step, g++) {
+      const int nq = (int)std::min<size_t>(step, count - qi);
+      const uint8_t* qt = images ? images + g * tc5_query_bytes(db->T) : c->w_qt.p;
+      if (!images) {
         b200pir_ctx::Scope sq(c, ST_QIMG);
         launch_query_to_tc5(db->T, qdev + qi * q_stride, q_stride, nq, c->w_qt.p, c->stream);
       }
       b200pir_ctx::Scope sc(c, ST_MUL);
-      launch_multiply_tc5(c->dp, db->T, db->t.p, db->tile_mask.p, c->w_qt.p, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
+      launch_multiply_tc5(c->dp, db->T, db->t.p, db->tile_mask.p, qt, c->w_cts.p + qi * out_stride, out_stride, nq, 0, c->slices,
                           c->sm_count, c->stream);
       c->mul_launches++;
     }
@@ -1373,9 +1387,10 @@ int b200pir_encode(b200pir_ctx* c, const uint64_t* v_packed_raw, uint8_t* out, s
 
 // ---------------------------------------------------------------- process_query
 static void run_query_batch_resident(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, size_t count, uint8_t* out_dev) {
-  // queries are already in c->w_query
-  run_prepare(c, pp, count);
-  run_first_dim_and_fold(c, db, count);
+  // queries are already in c->w_query; tcgen05 databases get their operand as tile images straight from the expansion
+  const bool images = db->format == 2 && c->hp.expand_queries;
+  run_prepare(c, pp, count, images);
+  run_first_dim_and_fold(c, db, count, nullptr, nullptr, images ? c->w_qt.p : nullptr, 16);
   run_pack_encode(c, pp, c->folded, c->folded_stride, count, out_dev);
 }
 
@@ -1605,6 +1620,44 @@ int b200pir_first_dim_fold_dev(b200pir_ctx* c, b200pir_db* db, const void* q_exp
   if (count == 0) return 0;
   c->ensure_workspace_lite(count, db->rows);
   run_first_dim_and_fold(c, db, count, (const uint4*)q_expanded_dev, v_folding_dev);
+  B200_CUDA(cudaMemcpy2DAsync(partial_dev, 4 * POLY * 4, c->folded, c->folded_stride * 4, 4 * POLY * 4, count * c->slices,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+// The same two phases with the first-dimension operand exchanged as UMMA tile images (tcgen05 databases): the rank that expands a
+// group of <= 16 queries also re-tiles it, once; the receivers multiply straight from the image.
+size_t b200pir_query_image_bytes(b200pir_ctx* c) { return c ? tc5_query_bytes(make_tc5_geom(c->dim0, 32)) : 0; }
+int b200pir_expand_queries_images_dev(b200pir_ctx* c, b200pir_pp* pp, const uint64_t* query_cts_dev, size_t count, void* image_dev,
+                                      uint32_t* v_folding_dev) {
+  API_BEGIN
+  if (!c || !query_cts_dev || !image_dev || (!v_folding_dev && c->hp.nu_2)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_pp(c, pp);
+  if (!c->hp.expand_queries) throw Error(B200PIR_E_BADARG, "needs expand_queries");
+  if (count == 0 || count > 16) throw Error(B200PIR_E_SHAPE, "one image holds 1..16 queries");
+  if (!tc5_supported(make_tc5_geom(c->dim0, 32))) throw Error(B200PIR_E_UNSUPPORTED, "dim0 too large for the tcgen05 kernel");
+  c->w_v.ensure(count * c->v_words());
+  c->prof_reset();
+  {
+    b200pir_ctx::Scope sc(c, ST_EXPAND);
+    run_expand_query(c, pp, query_cts_dev, c->w_v.p, nullptr, v_folding_dev, (int)count, (uint8_t*)image_dev);
+  }
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
+int b200pir_first_dim_fold_images_dev(b200pir_ctx* c, b200pir_db* db, const void* images_dev, size_t groups, size_t per_group,
+                                      const uint32_t* v_folding_dev, uint32_t* partial_dev) {
+  API_BEGIN
+  if (!c || !images_dev || !partial_dev || (!v_folding_dev && c->hp.nu_2)) throw Error(B200PIR_E_BADARG, "null argument");
+  Guard gd(c);
+  check_db(c, db);
+  if (db->format != 2) throw Error(B200PIR_E_BADARG, "tile images need a tcgen05-layout database (db_format 2)");
+  if (per_group == 0 || per_group > 16) throw Error(B200PIR_E_SHAPE, "one image holds 1..16 queries");
+  const size_t count = groups * per_group;
+  if (count == 0) return 0;
+  c->ensure_workspace_lite(count, db->rows);
+  run_first_dim_and_fold(c, db, count, nullptr, v_folding_dev, (const uint8_t*)images_dev, per_group);
   B200_CUDA(cudaMemcpy2DAsync(partial_dev, 4 * POLY * 4, c->folded, c->folded_stride * 4, 4 * POLY * 4, count * c->slices,
                               cudaMemcpyDeviceToDevice, c->stream));
   B200_CUDA(cudaGetLastError());

@@ -110,6 +110,9 @@ void launch_db_to_tc5(const Tc5Geom& T, const uint4* db0_slice, uint8_t* dbt, in
 void launch_db_upsert_tc5(const Tc5Geom& T, uint8_t* dbt, int slice, int il, int j, const uint64_t* poly, cudaStream_t s);
 void launch_query_to_tc5(const Tc5Geom& T, const uint4* q_dev, size_t q_stride, int nq, uint8_t* qt, cudaStream_t s);
 // out_zm as launch_multiply_imma; up to 16 queries per pass; one persistent CTA per SM
+// reorient_reg_ciphertexts (util.rs:323-355) fused with the re-tiling: expansion workspace v (ntt32 [query][slot][row][n][z]) ->
+// tile images of up to 16 queries (the B operand of launch_multiply_tc5)
+void launch_reorient_to_tc5(const Tc5Geom& T, const uint32_t* v, size_t v_stride, int idx_factor, int nq, uint8_t* qt, cudaStream_t s);
 // tile_mask: u32 [slice][mt], bit ks set = the tile (32 rows x 32 values of j) holds at least one present item; clear bits are
 // neither fetched nor multiplied (lib/server's sparse database: absent items cost nothing, db/sparse_db.rs, dot_product.rs:35)
 void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint32_t* tile_mask, const uint8_t* qt,

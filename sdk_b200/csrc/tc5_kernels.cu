@@ -109,6 +109,36 @@ k_query_to_tc5(Tc5Geom T, const uint4* __restrict__ q_dev, size_t q_stride, int 
     }
 }
 
+// The same images straight from the expansion workspace (reorient_reg_ciphertexts, util.rs:323-355, fused with the re-tiling):
+// v = ntt32 [query][slot][ct row][n][z] (v_stride words per query), first-dimension ciphertext j = slot idx_factor * j.
+// CTA = (8 consecutive z, ks): 2048 polynomial segments of 8 words (one 32-byte sector each), 8 per thread; the sixteen 4 KiB
+// tiles (8 z x 2 n) are assembled in shared memory and written out contiguously.
+__global__ void __launch_bounds__(256)
+k_reorient_to_tc5(Tc5Geom T, const uint32_t* __restrict__ v, size_t v_stride, int idx_factor, int nq, uint8_t* __restrict__ qt) {
+  extern __shared__ __align__(16) uint8_t rimg[];                    // [8 z][2 n][TC5_TILE]
+  const int z0 = blockIdx.x * 8, ks = blockIdx.y;
+  for (int i = threadIdx.x; i < 16 * TC5_TILE / 16; i += 256) reinterpret_cast<uint4*>(rimg)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int seg = threadIdx.x; seg < 16 * 32 * 4; seg += 256) {
+    const int n = seg & 1, r = (seg >> 1) & 1, k = (seg >> 2) & 31, q = seg >> 7;
+    const int j = ks * 32 + k;
+    if (q >= nq || j >= T.dim0) continue;
+    const uint32_t* src = v + (size_t)q * v_stride + ((size_t)idx_factor * j * 4 + r * 2 + n) * 2048 + z0;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int zz = 0; zz < 8; zz++) tc5_query_store(rimg + ((size_t)zz * 2 + n) * TC5_TILE, q, r, k, w[zz]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int zz = 0; zz < 8; zz++)
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      uint4* dst = reinterpret_cast<uint4*>(qt + tc5_q_tile(T, n, z0 + zz, ks) * TC5_TILE);
+      dst[threadIdx.x] = reinterpret_cast<const uint4*>(rimg + ((size_t)zz * 2 + n) * TC5_TILE)[threadIdx.x];
+    }
+}
+
 // ---- the multiply -----------------------------------------------------------------------------------------------------
 constexpr int TC5_MAX_STAGES = 24;
 struct Tc5Smem {
@@ -353,6 +383,12 @@ void launch_query_to_tc5(const Tc5Geom& T, const uint4* q_dev, size_t q_stride, 
   if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
   ++g_kernel_launches;
   k_query_to_tc5<<<dim3(POLY / 2, T.ks), 256, 0, s>>>(T, q_dev, q_stride, nq, qt);
+}
+void launch_reorient_to_tc5(const Tc5Geom& T, const uint32_t* v, size_t v_stride, int idx_factor, int nq, uint8_t* qt, cudaStream_t s) {
+  if (nq < 1 || nq > 16) throw Error(-2, "tcgen05 multiply: 1..16 queries per pass");
+  ++g_kernel_launches;
+  opt_in_smem(k_reorient_to_tc5, 16 * TC5_TILE);
+  k_reorient_to_tc5<<<dim3(POLY / 8, T.ks), 256, 16 * TC5_TILE, s>>>(T, v, v_stride, idx_factor, nq, qt);
 }
 void launch_multiply_tc5(const DevParams& P, const Tc5Geom& T, const uint8_t* dbt, const uint32_t* tile_mask, const uint8_t* qt,
                          uint32_t* out_zm, size_t out_stride, int nq, int slice_begin, int slice_count, int sm_count, cudaStream_t s) {

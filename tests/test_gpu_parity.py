@@ -559,6 +559,51 @@ def test_imma_multiply_many_tiles_long_k():
     G.close()
 
 
+@pytest.mark.parametrize("name,world", [("T0", 2), ("T1", 4), ("T", 2)])
+def test_three_phase_flow_with_tile_images_equals_oracle(name, world):
+    """bench.py's N>1 flow on tcgen05 databases: every "rank" expands its queries straight into a UMMA tile image (one image per
+    rank), the images are concatenated (the copy-engine pushes), every rank multiplies from the images of ALL ranks on its row
+    shard and folds, survivors are concatenated, each rank finishes its own queries.  Responses == oracle bytes."""
+    import torch
+    from sdk_b200._lib import LIB, check
+    S, P, cl, pp, db, G, gdb, gpp = setup_case(name)
+    per_rank = 3
+    total = per_rank * world
+    idxs = [(11 * k + 5) % (P.dim0 * P.num_per) for k in range(total)]
+    qs = np.concatenate([cl.generate_query(i)["ct"] for i in idxs])
+    d_q = torch.from_numpy(qs.view(np.int64)).cuda()
+    img_bytes = int(LIB.b200pir_query_image_bytes(G._h))
+    fold_words = P.nu_2 * 2 * 2 * P.t_gsw * 2 * P.N
+    ct_words = 4 * P.N
+    images = torch.zeros(world * img_bytes, dtype=torch.uint8, device="cuda")
+    vf = torch.zeros(total * fold_words, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        check(LIB.b200pir_expand_queries_images_dev(G._h, gpp._h, d_q.data_ptr() + r * per_rank * 2 * P.N * 8, per_rank,
+                                                    images.data_ptr() + r * img_bytes, vf.data_ptr() + r * per_rank * fold_words * 4))
+    gathered = torch.zeros(world * total * P.slices * ct_words, dtype=torch.int32, device="cuda")
+    slice_words = P.dim0 * P.num_per * P.N
+    shards = []
+    for r in range(world):
+        sh = S.Database(G, shard_index=r, shard_count=world, fmt=2)
+        for sl in range(P.slices):
+            sh.upload_slice(sl, db[sl * slice_words:(sl + 1) * slice_words])
+        shards.append(sh)
+        check(LIB.b200pir_first_dim_fold_images_dev(G._h, sh._h, images.data_ptr(), world, per_rank, vf.data_ptr(),
+                                                    gathered.data_ptr() + r * total * P.slices * ct_words * 4))
+    out = torch.zeros(total * G.response_bytes, dtype=torch.uint8, device="cuda")
+    for r in range(world):
+        check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, gathered.data_ptr(), world, total, r * per_rank, per_rank,
+                                             vf.data_ptr() + r * per_rank * fold_words * 4,
+                                             out.data_ptr() + r * per_rank * G.response_bytes))
+    G.synchronize()
+    got = out.cpu().numpy().reshape(total, G.response_bytes)
+    for k, i in enumerate(idxs):
+        ref = P.process_query(pp, dict(ct=qs[k * 2 * P.N:(k + 1) * 2 * P.N]), db)
+        assert np.array_equal(got[k], ref), (name, world, k)
+    for sh in shards:
+        sh.close()
+
+
 @pytest.mark.parametrize("name,world,fmt", [("T0", 2, 1), ("T0", 4, 0), ("T1", 2, 1), ("T0", 2, 2), ("T1", 2, 2)])
 def test_three_phase_multi_gpu_flow_equals_oracle(name, world, fmt):
     """bench.py's N>1 flow on one GPU: every "rank" expands its own queries, expanded queries are concatenated
