@@ -5,7 +5,8 @@ TAG=${1:-check}
 mkdir -p gpurun_out
 {
 echo "== pytest -m gpu"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_${TAG}.log 2>&1
+grep -E "^(FAILED|ERROR)|AssertionError|passed|failed" gpurun_out/pytest_${TAG}.log | cut -c1-400 | tail -15
 echo "== bench (default)"
 timeout 600 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 python - "$TAG" <<'PY'
