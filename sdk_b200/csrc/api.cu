@@ -294,6 +294,7 @@ struct b200pir_dpir {
 namespace {
 
 int fail(const std::exception& e) {
+  cudaGetLastError();        // a failed runtime call leaves its code as the "last error": clear it, or the next entry point's check reports it
   g_last_error = e.what();
   const Error* pe = dynamic_cast<const Error*>(&e);
   return pe ? pe->code : B200PIR_E_CUDA;
