@@ -56,7 +56,8 @@ int b200pir_ctx_synchronize(b200pir_ctx* ctx);
  * tcgen05 kernel supports the geometry, else 1; 0 = IMAD, 1 = mma.sync INT8 fragments, 2 = tcgen05 tile images, tc5_kernels.cu), "profile" (0 off, 1 per call,
  * 2 accumulate over calls until set again); A/B switches for kernel variants: "fold_variant", "intt_variant", "imma_variant",
  * "expand_variant" (0 = default everywhere); "coalesce" (1 = default: concurrent single-query callers
- * share database passes, see b200pir_coalesce_stats), "sparse_fold" (1 = fold like lib/server's sparse server,
+ * share database passes, see b200pir_coalesce_stats), "coalesce_window_us" (default 200: how long a batch that directly
+ * follows a multi-query batch is held open for the callers of that batch to return; 0 = never), "sparse_fold" (1 = fold like lib/server's sparse server,
  * compute/fold.rs:15-65: an all-zero ciphertext short-cuts the external product; 0 = spiral-rs's dense fold, default); "expand_pair_min_ctas" (expansion rounds with at least this many active
  * ciphertexts use the paired kernel, default 592);
  * unknown keys -> B200PIR_E_BADARG */

@@ -32,7 +32,8 @@ for n in (1, 8, 16, 32):
     print("n=%2d  one-client batch %.2f ms   process_queries same client %.2f ms   two clients %.2f ms" % (n, one, same, multi), flush=True)
 ser = t(lambda: S.process_query(G, ppa, S.Query(ct=qs[0]), gdb), 10)
 print("single process_query %.2f ms" % ser)
-for nthreads in (2, 8, 32):
+for window, nthreads in [(w, n) for w in (0, 200, 1000) for n in (2, 8, 32)]:
+    G.set_option("coalesce_window_us", window)
     b0, q0 = S.coalesce_stats(G)
     start = threading.Barrier(nthreads)
     def worker(k):
@@ -45,4 +46,4 @@ for nthreads in (2, 8, 32):
     for x in th: x.join()
     dt = time.perf_counter() - t0
     b1, q1 = S.coalesce_stats(G)
-    print("%2d threads x 4: %.1f ms total, %.2f ms per query, %d batches for %d queries" % (nthreads, dt * 1e3, dt * 1e3 / (4 * nthreads), b1 - b0, q1 - q0), flush=True)
+    print("window %4d us  %2d threads x 4: %.1f ms total, %.2f ms per query, %d batches for %d queries" % (window, nthreads, dt * 1e3, dt * 1e3 / (4 * nthreads), b1 - b0, q1 - q0), flush=True)

@@ -11,6 +11,7 @@
 #include <memory>
 #include <cstring>
 #include <condition_variable>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <set>
@@ -120,13 +121,21 @@ struct b200pir_ctx {
   // Coalescing of concurrent callers ("coalesce", default on): lib/server takes a READ lock around process_query
   // (bin/server.rs:102), so actix workers call it concurrently.  Requests arriving while a batch runs queue up here; the
   // thread that finds no batch in flight becomes the leader and serves everything queued (up to kCoalesceMax) in ONE
-  // database pass.  A lone caller is served immediately (no waiting window).
+  // database pass.  A lone caller is served immediately.  Two refinements for sustained load: a batch larger than one
+  // database pass (16 queries) is trimmed to whole passes, the remainder joining the next batch (it would have finished no
+  // earlier inside this one); and a leader that follows a multi-query batch by less than 1 ms gives the callers of that batch
+  // up to "coalesce_window_us" (default 200) to come back before it starts, so closed-loop clients do not alternate between
+  // full and near-empty passes.
   struct Pending {
     b200pir_db* db; b200pir_pp* pp; const uint64_t* query_ct; const uint8_t* query_bytes; uint8_t* out;
     int rc = 0; std::string err; bool done = false;
   };
   static constexpr size_t kCoalesceMax = 32;
+  static constexpr size_t kPassQueries = 16;
   int coalesce = 1;
+  int coalesce_window_us = 200;
+  size_t last_batch = 0;
+  std::chrono::steady_clock::time_point last_batch_end{};
   std::mutex qmu;
   std::condition_variable qcv;
   std::deque<Pending*> pending;
@@ -688,6 +697,7 @@ int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   else if (k == "imma_variant") c->imma_variant = (int)value;
   else if (k == "sparse_fold") c->sparse_fold = value != 0;
   else if (k == "coalesce") c->coalesce = value != 0;
+  else if (k == "coalesce_window_us") { if (value < 0 || value > 100000) throw Error(B200PIR_E_BADARG, "coalesce_window_us must be 0..100000"); c->coalesce_window_us = (int)value; }
   else if (k == "expand_variant") c->expand_variant = (int)value;
   else if (k == "expand_pair_min_ctas") c->pair_min_ctas = (long)value;
   else if (k == "db_format") { if (value < -1 || value > 2) throw Error(B200PIR_E_BADARG, "db_format must be -1 (automatic), 0, 1 or 2"); c->db_format = (int)value; }
@@ -1471,13 +1481,25 @@ int coalesced_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64
   me.db = db; me.pp = pp; me.query_ct = query_ct; me.query_bytes = query_bytes; me.out = out;
   std::unique_lock<std::mutex> lk(c->qmu);
   c->pending.push_back(&me);
+  c->qcv.notify_all();                       // a leader may be holding its batch open for us
   while (!me.done) {
     if (c->leader_active) { c->qcv.wait(lk); continue; }
-    // become the leader: take every queued request for the database at the head of the queue
+    // become the leader: take the queued requests for the database at the head of the queue
     c->leader_active = true;
+    if (c->coalesce_window_us > 0 && c->last_batch > 1 && c->pending.size() < std::min(c->last_batch, b200pir_ctx::kPassQueries)) {
+      const auto now = std::chrono::steady_clock::now();
+      if (now - c->last_batch_end < std::chrono::milliseconds(1)) {
+        const size_t want = std::min(c->last_batch, b200pir_ctx::kPassQueries);
+        c->qcv.wait_until(lk, now + std::chrono::microseconds(c->coalesce_window_us), [&] { return c->pending.size() >= want; });
+      }
+    }
     std::vector<b200pir_ctx::Pending*> batch;
     b200pir_db* bdb = c->pending.front()->db;
-    for (auto it = c->pending.begin(); it != c->pending.end() && batch.size() < b200pir_ctx::kCoalesceMax;) {
+    size_t avail = 0;
+    for (auto* p : c->pending) avail += p->db == bdb;
+    size_t take = std::min(avail, b200pir_ctx::kCoalesceMax);
+    if (take > b200pir_ctx::kPassQueries) take -= take % b200pir_ctx::kPassQueries;
+    for (auto it = c->pending.begin(); it != c->pending.end() && batch.size() < take;) {
       if ((*it)->db == bdb) { batch.push_back(*it); it = c->pending.erase(it); } else ++it;
     }
     lk.unlock();
@@ -1490,6 +1512,8 @@ int coalesced_query(b200pir_ctx* c, b200pir_db* db, b200pir_pp* pp, const uint64
     } catch (const std::exception& e) { rc = fail(e); err = e.what(); }
     lk.lock();
     c->coalesced_batches++; c->coalesced_queries += batch.size();
+    c->last_batch = batch.size();
+    c->last_batch_end = std::chrono::steady_clock::now();
     for (auto* p : batch) { p->rc = rc; p->err = err; p->done = true; }
     c->leader_active = false;
     c->qcv.notify_all();
