@@ -418,6 +418,7 @@ def main():
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="N > 1, copy-engine exchange: do not enqueue the expansion + pushes of step k + 1 before the first dimension "
                          "of step k")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: print a CUDA-event timeline of four steps to stderr")
     ap.add_argument("--waves", type=int, default=None,
                     help="N > 1: each rank's queries are processed in this many waves so that the all-gather of one wave's "
                          "expanded queries overlaps the expansion / first dimension of the other")
@@ -448,6 +449,10 @@ def main():
     if world != args.gpus and world > 1:
         log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
     N = max(world, 1)
+    if N > 1:
+        # main + copy + one stream per peer + NCCL's: more streams than the default 8 hardware queues, and streams that share
+        # a queue serialise behind each other's waits
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if args.batch is None:
         args.batch = args.batch_per_gpu * N
 
@@ -591,10 +596,20 @@ def main():
     # the peers: they last read that set in step k - NBUF; barrier(k - 1) (a 4-byte all-reduce each rank issues after its
     # pushes of step k - 1) has completed before the push starts, hence every rank has issued its pushes of step k - 1, and
     # those are stream-ordered after that rank's first dimension of step k - 1 - (pipelined ? 1 : 0) >= k - NBUF.
+    TL = []                                         # --timeline: (label, step, CUDA event) in stream order
+    tl_on = [False]
+
+    def mark(label, k, stream=None):
+        if tl_on[0]:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream if stream is not None else torch.cuda.current_stream())
+            TL.append((label, k, e))
+
     def ce_expand_push(k):
         bset = k % NBUF
         cur = torch.cuda.current_stream()
         for w in range(W):
+            mark("expand.begin", k)
             # expand straight into this rank's slot of its own gather buffers, then push the slot to every peer
             q_own = mine[(bset, w, "q")] + rank * qexp_b
             v_own = mine[(bset, w, "v")] + rank * vf_b
@@ -602,6 +617,7 @@ def main():
                 check(LIB.b200pir_expand_queries_images_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
             else:
                 check(LIB.b200pir_expand_queries_dev(G._h, gpp._h, d_q.data_ptr() + w * Blw * 2 * POLY * 8, Blw, q_own, v_own))
+            mark("expand.end", k)
             ev = torch.cuda.Event()
             ev.record(cur)
             with torch.cuda.stream(copy_stream):
@@ -610,6 +626,7 @@ def main():
                     prev_barrier[w].wait()
                 go = torch.cuda.Event()
                 go.record(copy_stream)
+                mark("push.begin", k, copy_stream)
                 for r, ps in peer_streams.items():
                     ps.wait_event(go)
                     check(LIB.b200pir_peer_copy_async(peer[(r, bset, w, "q")] + rank * qexp_b, q_own, qexp_b, ps.cuda_stream))
@@ -617,6 +634,7 @@ def main():
                     done = torch.cuda.Event()
                     done.record(ps)
                     copy_stream.wait_event(done)
+                mark("push.end", k, copy_stream)
                 # 4-byte all-reduce ordered after the pushes: complete when every rank's pushes have landed
                 prev_barrier[w] = dist.all_reduce(tiny[w], async_op=True)
             barriers[(k, w)] = prev_barrier[w]
@@ -626,16 +644,20 @@ def main():
         sv = []
         for w in range(W):
             barriers.pop((k, w)).wait()
+            mark("first_dim.begin (all pushes landed)", k)
             if use_images:
                 check(LIB.b200pir_first_dim_fold_images_dev(G._h, gdb._h, mine[(bset, w, "q")], N, Blw, mine[(bset, w, "v")],
                                                             d_partial[w].data_ptr()))
             else:
                 check(LIB.b200pir_first_dim_fold_dev(G._h, gdb._h, mine[(bset, w, "q")], mine[(bset, w, "v")], Bw, d_partial[w].data_ptr()))
+            mark("first_dim+local_fold.end", k)
             sv.append(dist.all_gather_into_tensor(d_gather[w], d_partial[w], async_op=True))
         for w in range(W):
             sv[w].wait()
+            mark("survivors gathered", k)
             check(LIB.b200pir_finish_queries_dev(G._h, gpp._h, d_gather[w].data_ptr(), N, Bw, rank * Blw, Blw,
                                                  mine[(bset, w, "v")] + rank * vf_b, d_out.data_ptr() + w * Blw * rb))
+            mark("finish.end", k)
 
     def step_dev():
         if N == 1:
@@ -712,6 +734,18 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = LIB.b200pir_kernel_launches() - launches0
     ms_total = ev0.elapsed_time(ev1)
+    if args.timeline and N > 1 and exchange == "ce":
+        # where a step's time goes on this rank's streams (a separate, short pass; printed by every rank to stderr)
+        tl_on[0] = True
+        for _ in range(4):
+            step_dev()
+        barrier()
+        tl_on[0] = False
+        t_first = TL[0][2]
+        lines = ["rank %d timeline (ms since the first mark; main stream unless push.*)" % rank]
+        for label, k, e in TL:
+            lines.append("  %9.3f  step %2d  %s" % (t_first.elapsed_time(e), k, label))
+        log("\n".join(lines)) if rank in (0, N - 1) else None
     # per-stage / per-kernel times come from a SEPARATE pass of the same steps with per-stage CUDA events on
     # (the timed region above is un-instrumented)
     G.set_option("profile", 2)

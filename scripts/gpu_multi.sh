@@ -24,7 +24,14 @@ echo "== $N GPUs"
 run "copy engines, pipelined (default)" X=1 --
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_n${N}.json
 tail -3 gpurun_out/multi.err | cut -c1-300
-if [ "$N" = "8" ]; then
+if [ -n "$TIMELINE" ]; then
+run "default + timeline" X=1 -- --timeline --no-verify --steps-only
+grep -A200 "rank 0 timeline" gpurun_out/multi.err | head -120
+run "8 hardware queues" CUDA_DEVICE_MAX_CONNECTIONS=8 -- --no-verify --steps-only
+run "no pipeline, 2 waves" X=1 -- --no-pipeline --no-verify --steps-only
+run "pipeline, 2 waves" X=1 -- --waves 2 --no-verify --steps-only
+fi
+if [ "$N" = "8" ] && [ -z "$TIMELINE" ]; then
 echo "== BASELINE configs[2]: S256 (32 GiB plaintext = 256 GiB packed) over 8 GPUs, 128 concurrent queries"
 run "S256, 128 queries" X=1 -- --workload S256 --steps 5
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_s256_n${N}.json
