@@ -585,6 +585,10 @@ def main():
                 # serialises them on one engine: 2.7 GB per step at N = 8 took ~14 ms, profiles/bench_r02_n8_single_copy_stream.json)
                 peer_streams = {r: torch.cuda.Stream() for r in range(N) if r != rank}
                 tiny = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(W)]
+                # the "pushes landed" all-reduces get their own communicator: on the default one the survivors' all-gather of
+                # step k would queue behind barrier(k + 1), i.e. behind the whole transfer of step k + 1 (measured: 4.3 ms of a
+                # 12.8 ms step at N = 8, profiles/timeline_r02_n8.md)
+                bar_group = dist.new_group(backend="nccl")
                 prev_barrier = [None] * W
                 barriers = {}
                 step_no = [0]
@@ -636,7 +640,7 @@ def main():
                     copy_stream.wait_event(done)
                 mark("push.end", k, copy_stream)
                 # 4-byte all-reduce ordered after the pushes: complete when every rank's pushes have landed
-                prev_barrier[w] = dist.all_reduce(tiny[w], async_op=True)
+                prev_barrier[w] = dist.all_reduce(tiny[w], group=bar_group, async_op=True)
             barriers[(k, w)] = prev_barrier[w]
 
     def ce_compute(k):
