@@ -21,7 +21,8 @@ PY
 }
 {
 echo "== $N GPUs"
-run "copy engines, pipelined (default)" X=1 --
+run "copy engines, pipelined (default)" X=1 -- --timeline
+grep -A34 "rank 0 timeline" gpurun_out/multi.err | head -36
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_n${N}.json
 tail -3 gpurun_out/multi.err | cut -c1-300
 if [ -n "$TIMELINE" ]; then
@@ -31,7 +32,7 @@ run "8 hardware queues" CUDA_DEVICE_MAX_CONNECTIONS=8 -- --no-verify --steps-onl
 run "no pipeline, 2 waves" X=1 -- --no-pipeline --no-verify --steps-only
 run "pipeline, 2 waves" X=1 -- --waves 2 --no-verify --steps-only
 fi
-if [ "$N" = "8" ] && [ -z "$TIMELINE" ]; then
+if [ "$N" = "8" ] && [ -z "$TIMELINE" ] && [ -z "$SKIP_S256" ]; then
 echo "== BASELINE configs[2]: S256 (32 GiB plaintext = 256 GiB packed) over 8 GPUs, 128 concurrent queries"
 run "S256, 128 queries" X=1 -- --workload S256 --steps 5
 cp gpurun_out/multi.json gpurun_out/bench_${TAG}_s256_n${N}.json
