@@ -65,55 +65,6 @@ def test_s8_every_layout_gives_the_same_bytes(s8):
         other.close()
 
 
-# ------------------------------------------------------------------ concurrent callers (SURVEY 8b "Threading")
-def test_concurrent_callers_are_coalesced(s8):
-    """lib/server calls process_query from concurrent actix workers under a read lock (bin/server.rs:102).  32 host threads,
-    each serving 4 requests back to back through b200pir_process_query on ONE context (two clients with different keys,
-    alternating): identical bytes to serial calls, far fewer database passes than queries, and at least 3x the serial
-    queries/s (one 8 GiB pass serves up to 16 callers; a lone caller is never made to wait)."""
-    import threading
-    import time
-    S, P, cl_a, G, gdb, gpp_a = s8
-    cl_b = O.Client(P, 4242)
-    pp_b = cl_b.generate_keys()
-    gpp_b = S.PublicParameters(G, pp_b["pack"], pp_b["left"], pp_b["right"], pp_b["conv"])
-    n, per_worker = 32, 4
-    who = [(cl_a, gpp_a) if k % 2 == 0 else (cl_b, gpp_b) for k in range(n)]
-    idxs = [(7919 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
-    qs = [S.Query(ct=cl.generate_query(i)["ct"]) for (cl, _), i in zip(who, idxs)]
-    serial = [S.process_query(G, g, q, gdb).copy() for (_, g), q in zip(who, qs)]         # also warms the workspace up
-    for k, ((cl, _), i) in enumerate(zip(who, idxs)):
-        assert np.array_equal(cl.decode_response(serial[k]), P.db_plain_item(SEED, i)), k
-    t0 = time.perf_counter()
-    for _ in range(per_worker):
-        for (_, g), q in zip(who, qs):
-            S.process_query(G, g, q, gdb)
-    t_serial = time.perf_counter() - t0
-    b0, q0 = S.coalesce_stats(G)
-    bad = []
-    start = threading.Barrier(n)
-
-    def worker(k):
-        start.wait()
-        for _ in range(per_worker):
-            if not np.array_equal(S.process_query(G, who[k][1], qs[k], gdb), serial[k]):
-                bad.append(k)
-
-    threads = [threading.Thread(target=worker, args=(k,)) for k in range(n)]
-    t0 = time.perf_counter()
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    t_conc = time.perf_counter() - t0
-    b1, q1 = S.coalesce_stats(G)
-    assert not bad, bad
-    assert q1 - q0 == n * per_worker, (q1 - q0)
-    assert b1 - b0 <= n * per_worker // 4, ("database passes", b1 - b0, "queries", q1 - q0)
-    assert t_serial / t_conc >= 3.0, ("serial s", t_serial, "concurrent s", t_conc, "passes", b1 - b0)
-    gpp_b.close()
-
-
 # ------------------------------------------------------------------ BASELINE config #4: DoublePIR 2^24 x 1366 packed words
 def test_dpir_config4_full_size_against_oracle_row_sample():
     import sdk_b200.doublepir as D
