@@ -335,6 +335,32 @@ k_dpir_matvec_row(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, co
   }
 }
 
+// Rows too wide for `b` to fit in shared memory (3 * cols words > 200 KiB; the reference's short-and-wide databases, e.g.
+// l = 29, m = 65536 for 2^24 one-bit entries, doublepir.rs:471-483): one CTA per row, `b` read through L2.
+__global__ void __launch_bounds__(256)
+k_dpir_matvec_wide(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t rows,
+                   size_t cols) {
+  __shared__ uint32_t part[8];
+  const size_t row = blockIdx.x;
+  if (row >= rows) return;
+  const uint32_t* ar = a + row * cols;
+  uint32_t acc = 0;
+  for (size_t k = threadIdx.x; k < cols; k += blockDim.x) {
+    const uint32_t d = __ldg(ar + k);
+    const uint32_t* bp = b + 3 * k;
+    acc += (d & 1023u) * __ldg(bp) + ((d >> 10) & 1023u) * __ldg(bp + 1) + ((d >> 20) & 1023u) * __ldg(bp + 2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += part[w];
+    out[row] = t;
+  }
+}
+
 // kernels.rs:180-278: out[i][j] = sum_k sum_m ((a[i][k] >> 10m) & 1023) * b[j][3k+m]   (one warp per output)
 __global__ void k_dpir_mul_transposed(uint32_t* __restrict__ out, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
                                       size_t a_rows, size_t a_cols, size_t b_rows, size_t b_cols) {
@@ -449,7 +475,13 @@ void launch_dpir_matvec(uint32_t* out, const uint32_t* a, const uint32_t* b, siz
                         cudaStream_t s) {
   size_t cols_pad = (cols + 3) & ~(size_t)3;
   size_t smem = 3 * cols_pad * 4;
-  if (smem > 200 * 1024) throw Error(-2, "dpir: b too large for shared memory");
+  if (rows == 0) return;
+  if (smem > 200 * 1024) {
+    if (rows > 0x7FFFFFFFull) throw Error(-2, "dpir: too many rows for the wide-row kernel");
+    ++g_kernel_launches;
+    k_dpir_matvec_wide<<<(unsigned)rows, 256, 0, s>>>(out, a, b, rows, cols);
+    return;
+  }
   if ((cols & 1) == 0 && variant != 1 && variant != 4) {
     // default: one row per warp, 8 loads in flight per lane (variant 2: 4 loads)
     unsigned g = (unsigned)std::min<size_t>((rows + 7) / 8, (size_t)148 * 8);
