@@ -767,19 +767,23 @@ def main():
 
     # ---- single-query latency (device-resident, batch of 1), N == 1 only
     single_ms = None
+    single_p99 = None
     single_roofline = None
     if N == 1 and not args.steps_only:
         for _ in range(3):
             check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), 1, d_out.data_ptr()))
         torch.cuda.synchronize()
         G.set_option("profile", 2)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
+        # median of >= 100 single queries after warm-up, query already on the device
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+        for e0, e1 in evs:
+            e0.record()
             check(LIB.b200pir_process_query_batch_dev(G._h, gdb._h, gpp._h, d_q.data_ptr(), 1, d_out.data_ptr()))
-        e1.record()
+            e1.record()
         torch.cuda.synchronize()
-        single_ms = e0.elapsed_time(e1) / 10
+        lat = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+        single_ms = lat[len(lat) // 2]
+        single_p99 = lat[98]
         st1 = G.last_stage_ms()
         G.set_option("profile", 0)
         k_ms = st1["multiply"] / max(st1["multiply_launches"], 1)
@@ -919,7 +923,9 @@ def main():
                             else "three-phase device entry points around NCCL all-gathers, query ciphertexts copied from pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items() if k not in ("multiply_launches",)},
-            "single_query_latency_ms": single_ms, "single_query_roofline": single_roofline,
+            "single_query_latency_ms": single_ms, "single_query_latency_p99_ms": single_p99,
+            "single_query_latency_note": "median / 99th percentile of 100 device-resident single queries after warm-up",
+            "single_query_roofline": single_roofline,
             "concurrent_queries_sweep": sweep,
             "verified": verified, "verify_note": verify_note,
             "timed_region": "un-instrumented; stage_ms_per_step and roofline.kernel_ms come from a separate pass of the same steps "
