@@ -62,6 +62,11 @@ int b200pir_ctx_synchronize(b200pir_ctx* ctx);
  * ciphertexts use the paired kernel, default 592);
  * unknown keys -> B200PIR_E_BADARG */
 int b200pir_ctx_set_option(b200pir_ctx* ctx, const char* key, int64_t value);
+/* Size the context's workspace once, up front, for `queries` concurrent queries against a database with `rows_local`
+ * second-dimension rows (num_per for an unsharded database): afterwards no entry point allocates device memory for batches up
+ * to that size (the workspace otherwise grows on first use; coalesced single-query calls size it for 32 queries).
+ * B200PIR_E_CUDA when the device cannot hold it. */
+int b200pir_ctx_reserve(b200pir_ctx* ctx, size_t queries, size_t rows_local);
 /* params.setup_bytes / query_bytes / response length (params.rs:146-182, server.rs:476-481) */
 int b200pir_ctx_sizes(b200pir_ctx* ctx, uint64_t* setup_bytes, uint64_t* query_bytes, uint64_t* response_bytes);
 

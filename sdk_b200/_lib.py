@@ -33,6 +33,7 @@ def _load():
         "b200pir_ctx_set_stream": (C.c_int, [vp, vp]),
         "b200pir_ctx_synchronize": (C.c_int, [vp]),
         "b200pir_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+        "b200pir_ctx_reserve": (C.c_int, [vp, C.c_size_t, C.c_size_t]),
         "b200pir_ctx_sizes": (C.c_int, [vp, C.POINTER(C.c_uint64)] + [C.POINTER(C.c_uint64)] * 2),
         "b200pir_db_create": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
         "b200pir_db_destroy": (None, [vp]),

@@ -685,6 +685,17 @@ int b200pir_ctx_synchronize(b200pir_ctx* c) {
   B200_CUDA(cudaGetLastError());
   API_END
 }
+int b200pir_ctx_reserve(b200pir_ctx* c, size_t queries, size_t rows_local) {
+  API_BEGIN
+  if (!c) throw Error(B200PIR_E_BADARG, "null ctx");
+  if (queries == 0 || queries > 4096 || rows_local == 0 || rows_local > ((size_t)1 << c->hp.nu_2))
+    throw Error(B200PIR_E_BADARG, "reserve: 1..4096 queries, 1..num_per rows");
+  Guard gd(c);
+  B200_CUDA(cudaStreamSynchronize(c->stream));          // buffers may be replaced: nothing in flight may still use them
+  c->ensure_workspace(queries, rows_local);
+  B200_CUDA(cudaGetLastError());
+  API_END
+}
 int b200pir_ctx_set_option(b200pir_ctx* c, const char* key, int64_t value) {
   API_BEGIN
   if (!c || !key) throw Error(B200PIR_E_BADARG, "null argument");

@@ -92,6 +92,10 @@ class Params:
     def set_option(self, key, value):
         check(LIB.b200pir_ctx_set_option(self._h, key.encode(), int(value)))
 
+    def reserve(self, queries, rows_local=None):
+        """Allocate the workspace for `queries` concurrent queries now instead of on first use."""
+        check(LIB.b200pir_ctx_reserve(self._h, int(queries), int(rows_local if rows_local is not None else self.num_per)))
+
     def set_stream(self, cuda_stream):
         check(LIB.b200pir_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 

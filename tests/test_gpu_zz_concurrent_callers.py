@@ -127,3 +127,32 @@ def test_coalescing_can_be_switched_off(s8two):
         assert len(out) == 4 and all(np.array_equal(o, ref) for o in out)
     finally:
         G.set_option("coalesce", 1)
+
+
+def test_workspace_reserved_up_front(s8two):
+    """b200pir_ctx_reserve: the workspace for 32 concurrent queries allocated before the first query; same bytes afterwards,
+    bad sizes rejected."""
+    S, P, G, gdb, clients = s8two
+    from sdk_b200._lib import B200PirError
+    cl, g = clients[1]
+    q = S.Query(ct=cl.generate_query(4321)["ct"])
+    ref = S.process_query(G, g, q, gdb).copy()
+    G2 = S.Params(**P.kw)                                     # a fresh context: nothing allocated yet
+    try:
+        G2.reserve(32)
+        db2 = S.Database(G2)
+        db2.fill_synthetic(SEED)
+        cl2 = O.Client(P, 777)
+        pp = cl2.generate_keys()
+        g2 = S.PublicParameters(G2, pp["pack"], pp["left"], pp["right"], pp["conv"])
+        q2 = S.Query(ct=cl2.generate_query(4321)["ct"])
+        assert np.array_equal(cl2.decode_response(S.process_query(G2, g2, q2, db2)), P.db_plain_item(SEED, 4321))
+        with pytest.raises(B200PirError):
+            G2.reserve(0)
+        with pytest.raises(B200PirError):
+            G2.reserve(1, rows_local=P.num_per + 1)
+        g2.close()
+        db2.close()
+    finally:
+        G2.close()
+    assert np.array_equal(S.process_query(G, g, q, gdb), ref)
