@@ -355,6 +355,9 @@ int orc_client_decrypt_reg(void* c, const uint64_t* ct_ntt, uint64_t* out_raw) {
 }
 // ---- wire formats
 void orc_chacha20_block(const uint32_t* init16, uint32_t* out16) { chacha20_block(init16, out16); }
+// the generator the wire formats draw from: n consecutive next_u32() / next_u64() values of ChaCha20Rng::from_seed(seed)
+void orc_chacha20rng_u32(const uint8_t* seed32, size_t n, uint32_t* out) { ChaCha20Rng r(seed32); for (size_t i = 0; i < n; i++) out[i] = r.next_u32(); }
+void orc_chacha20rng_u64(const uint8_t* seed32, size_t n, uint64_t* out) { ChaCha20Rng r(seed32); for (size_t i = 0; i < n; i++) out[i] = r.next(); }
 int orc_client_pp_bytes(void* c, uint8_t* out, size_t* out_len) {
   ORC_TRY
   Client& cl = *(Client*)c;

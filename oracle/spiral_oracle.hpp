@@ -17,7 +17,9 @@
 // ciphertexts in the reference (its tests decrypt and compare, with fresh entropy), so the
 // pipeline is pinned by (i) the primitive KATs, (ii) line-by-line structural correspondence
 // (each function cites the reference lines it follows), (iii) the same decrypt-and-compare
-// tests.  Wire-level seed expansion (ChaCha20, rand_chacha 0.3.1) is "parity unpinned".
+// tests.  Wire-level seed expansion (ChaCha20, rand_chacha 0.3.1: a third-party crate absent from the
+// reference tree) is pinned by RFC 8439 / RFC 7539 vectors and the crate's published ChaCha20Rng
+// known-answer test instead of reference output (spiral_client.hpp).
 //
 // The Rust reference cannot be compiled here (no cargo/rustc in the image).
 #pragma once
