@@ -247,3 +247,81 @@ def test_load_db_from_seek_restatement():
     assert chunks[-1].size == bpc                                                     # reaches into item idx + 1
     polys = P2.update_item_raw(np.concatenate(chunks)).reshape(P2.slices, P2.N)
     assert np.array_equal(db2[:, :, idx % P2.num_per, idx // P2.num_per], polys)
+
+
+# ------------------------------------------------------------------ the reference's remaining stage tests, restated on the oracle
+def _dec_reg(P, cl, ct_ntt, scale_k):
+    # server.rs:753-770 dec_reg: coefficient 0, centred, rounded by scale_k; 0 -> 0, anything else -> 1
+    val = int(cl.decrypt_reg(ct_ntt)[0])
+    if val >= P.modulus // 2:
+        val -= P.modulus
+    return 0 if round(val / scale_k) == 0 else 1
+
+
+def test_coefficient_expansion_is_correct():
+    # server.rs:787-830: Enc(scale_k * X^7) expands into 2^g ciphertexts of which exactly number 7 is non-zero
+    P = O.Params.named("T")
+    cl = O.Client(P, 21)
+    pp = cl.generate_keys()
+    g = (P.t_gsw * P.nu_2 + P.dim0 - 1).bit_length()
+    assert (1 << g) == 1 << (P.nu_1 + 1)                      # the vector length the reference's test allocates
+    scale_k = P.modulus // P.p
+    target = 7
+    sigma = np.zeros(P.N, dtype=np.uint64)
+    sigma[target] = scale_k
+    v = np.zeros(((1 << g), 2 * P.W), dtype=np.uint64)
+    v[0] = cl.encrypt_reg(sigma)
+    test_ct = cl.encrypt_reg(sigma)
+    out = P.coefficient_expansion(v.reshape(-1), pp).reshape(1 << g, 2 * P.W)
+    assert _dec_reg(P, cl, test_ct, scale_k) == 0             # coefficient 0 of the unexpanded ciphertext is empty
+    for i in range(1 << g):
+        assert _dec_reg(P, cl, out[i], scale_k) == (1 if i == target else 0), i
+
+
+def test_regev_to_gsw_is_correct():
+    # server.rs:832-868 (db_dim_2 = 1): Regev encryptions of 2^(bits_per * i) -> a GSW ciphertext of 1; of zeros -> of 0
+    P = O.Params.named("T", nu_2=1)
+    cl = O.Client(P, 22)
+    pp = cl.generate_keys()
+    bits_per = P.bits_per(P.t_gsw)
+
+    def enc_constant(val):
+        sigma = np.zeros(P.N, dtype=np.uint64)
+        sigma[0] = val
+        return cl.encrypt_reg(sigma)
+
+    def dec_gsw(gsw):
+        # server.rs:772-785: the last column (index 2 t_gsw - 1), coefficient 0: "this offset should encode a large value"
+        m = gsw.reshape(2, 2 * P.t_gsw, P.W)
+        val = int(cl.decrypt_reg(np.concatenate([m[0, 2 * P.t_gsw - 1], m[1, 2 * P.t_gsw - 1]]))[0])
+        if val >= P.modulus // 2:
+            val -= P.modulus
+        return 0 if abs(val) < (1 << 10) else 1
+
+    conv = pp["conv"].reshape(-1)[: 2 * 2 * P.t_conv * P.W]                                  # v_conversion[0]
+    ones = np.concatenate([enc_constant(1 << (bits_per * i)) for i in range(P.t_gsw)])
+    zeros = np.concatenate([enc_constant(0) for _ in range(P.t_gsw)])
+    assert dec_gsw(P.regev_to_gsw(ones, conv)) == 1
+    assert dec_gsw(P.regev_to_gsw(zeros, conv)) == 0
+
+
+@pytest.mark.parametrize("target_row,hot_row,expect", [(2, 2, 1), (3, 3, 1), (0, 0, 1), (2, 1, 0)])
+def test_fold_ciphertexts_is_correct(target_row, hot_row, expect):
+    # server.rs:927-993: num_per Regev ciphertexts, a scale_k only in row `hot_row`; GSW encryptions of the bits of
+    # `target_row` select it.  The reference builds the GSW ciphertexts inline from the secret key; here they come from the
+    # oracle client's direct-upload query (client.rs:660-721 builds them the same way: column pairs (sk * sigma, sigma) with
+    # sigma = bit * 2^(bits_per * j)).
+    P = O.Params.named("T", expand_queries=False)
+    cl = O.Client(P, 23)
+    cl.generate_keys()
+    scale_k = P.modulus // P.p
+    q = cl.generate_query(5 * P.num_per + target_row)          # second-dimension part of the index = target_row
+    v_folding = P.to_ntt(q["v_ct"])                             # nu_2 x (2 x 2 t_gsw)
+    v_folding_neg = P.get_v_folding_neg(v_folding)
+    rows = []
+    for i in range(P.num_per):
+        sigma = np.zeros(P.N, dtype=np.uint64)
+        sigma[0] = scale_k if i == hot_row else 0
+        rows.append(P.from_ntt(cl.encrypt_reg(sigma)))
+    folded = P.fold_ciphertexts(np.concatenate(rows), v_folding, v_folding_neg)
+    assert _dec_reg(P, cl, P.to_ntt(folded[: 2 * P.N]), scale_k) == expect
