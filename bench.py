@@ -877,6 +877,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(name, B, args.db_format), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mul_ms,
+                "frac_of_nominal_8_tb_s": achieved / 8000.0,      # north_star quotes "~8 TB/s"; `frac` uses the measured copy peak
                 "kernel_share_of_step": stage["multiply"] / max(stage["total"], 1e-9),
                 "note": "kernel_ms = CUDA-event time of the multiply kernel alone; the re-tiling of the query operand that precedes it "
                         "is stage 'query_image'"}
