@@ -36,14 +36,14 @@ def s8two():
 
 
 def test_concurrent_callers_share_database_passes(s8two):
-    """32 host threads, each serving 4 requests back to back through b200pir_process_query on ONE context, the two clients
+    """32 host threads, each serving 8 requests back to back through b200pir_process_query on ONE context, the two clients
     alternating: every response identical to the serial call's and decoding to the planted item, far fewer database passes
     than queries, and at least 3x the serial queries/s (one 8 GiB pass serves 16 callers; a lone caller is never made to
     wait).  The timed loops call the C entry point directly (ctypes releases the GIL for the call), the way the reference's
     Rust workers would; the comparison of the bytes happens afterwards."""
     from sdk_b200._lib import LIB
     S, P, G, gdb, clients = s8two
-    n, per_worker = 32, 4
+    n, per_worker = 32, 8
     who = [clients[k % 2] for k in range(n)]
     idxs = [(7919 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
     cts = [np.ascontiguousarray(cl.generate_query(i)["ct"], dtype=np.uint64) for (cl, _), i in zip(who, idxs)]
