@@ -434,14 +434,18 @@ def dpir_transpose_expand_concat_cols_squish(a, rows, cols, modulus, delta, conc
     return out, out_rows, out_cols
 
 
-def dpir_answer(db, db_rows, db_cols, queries, h_1, h1_rows, h1_cols, a2t, a2t_rows, a2t_cols, p, delta, x, ne):
-    """doublepir.rs:246-350 (raw_data = None, chunk_idx = None).  queries: list of [q_1, q_2...] uint32 arrays."""
+def dpir_answer(db, db_rows, db_cols, queries, h_1, h1_rows, h1_cols, a2t, a2t_rows, a2t_cols, p, delta, x, ne, chunk_idx=None):
+    """doublepir.rs:246-350.  queries: list of [q_1, q_2...] uint32 arrays.  chunk_idx = k: the server that holds only the
+    k-th batch of rows (raw_data = that slice, :268-275): the other batches contribute zero rows (:270-273)."""
     nq = len(queries)
     batch = db_rows // nq
     parts, last = [], 0
     for b, q in enumerate(queries):
         bs = db_rows - last if b == nq - 1 else batch
-        parts.append(dpir_matvec_packed(np.ascontiguousarray(db[last * db_cols:(last + bs) * db_cols]), q[0], bs, db_cols))
+        if chunk_idx is not None and b != chunk_idx:
+            parts.append(np.zeros(bs, dtype=np.uint32))
+        else:
+            parts.append(dpir_matvec_packed(np.ascontiguousarray(db[last * db_cols:(last + bs) * db_cols]), q[0], bs, db_cols))
         last += bs
     a_1 = np.concatenate(parts)
     a_1, r1, c1 = dpir_transpose_expand_concat_cols_squish(a_1, db_rows, 1, p, delta, x)

@@ -121,7 +121,7 @@ def query(i, a_1, a_2, prm, info, rng):                                       # 
     return state, msg
 
 
-def recover(i, offline_h2, qmsg, answer, a_2, client, prm, info):              # doublepir.rs:352-458, batch_index 0
+def recover(i, offline_h2, qmsg, answer, a_2, client, prm, info, batch_index=0):   # doublepir.rs:352-458
     n, p, x, ne = prm["n"], prm["p"], info["x"], info["ne"]
     delta = math.ceil(prm["logq"] / math.log2(p))
     ext_delta = Q // p
@@ -134,9 +134,10 @@ def recover(i, offline_h2, qmsg, answer, a_2, client, prm, info):              #
     h1 = (h1.astype(np.uint64) + val3[None, :]).astype(U32)
     secret1 = client[0]
     vals = []
+    offset = (ne // x * 2) * batch_index                                       # "for batching"
     for k in range(ne // x):
-        a2 = answer[1 + 2 * k]
-        h2 = (answer[2 + 2 * k].astype(np.uint64) + val2).astype(U32)
+        a2 = answer[1 + 2 * k + offset]
+        h2 = (answer[2 + 2 * k + offset].astype(np.uint64) + val2).astype(U32)
         secret2 = client[1 + k]
         for j in range(x):
             state = np.concatenate([(a2[j * n * delta:(j + 1) * n * delta].astype(np.uint64) + val2).astype(U32),
@@ -162,25 +163,87 @@ def recover(i, offline_h2, qmsg, answer, a_2, client, prm, info):              #
     return val
 
 
+_prepared = {}
+
+
+def prepare(num_entries, bits, seed):
+    """pick_params, Db::with_data, init, setup (cached: the 2^24-entry setup is shared by two tests)"""
+    key = (num_entries, bits, seed)
+    if key not in _prepared:
+        rng = np.random.default_rng(seed)
+        prm = pick_params(num_entries, bits, SEC_PARAM, LOGQ)
+        data = rng.integers(0, min(1 << bits, 256), num_entries, dtype=np.uint8)   # the reference's iterator yields u8 items
+        info, db = db_with_data(num_entries, bits, prm, data)
+        n, l, m, p, x = prm["n"], prm["l"], prm["m"], prm["p"], info["x"]
+        delta = math.ceil(LOGQ / math.log2(p))
+        a_1 = rng.integers(0, Q, (m, n), dtype=np.uint64).astype(U32)              # init(), doublepir.rs:46-51
+        a_2 = rng.integers(0, Q, (l // x, n), dtype=np.uint64).astype(U32)
+        st = O.dpir_setup(db, l, m, a_1, n, a_2, p, delta, x)                      # server_state = [h1_sq, a2_t], hint = [h2]
+        _prepared[key] = (rng, prm, data, info, delta, a_1, a_2, st)
+    return _prepared[key]
+
+
+def run_answer(st, prm, info, delta, queries, chunk_idx=None):
+    n, l, m, p, x, ne = prm["n"], prm["l"], prm["m"], prm["p"], info["x"], info["ne"]
+    lx = l // x
+    return O.dpir_answer(st["db_sq"].reshape(-1), l, (m + 2) // 3, queries, st["h1_sq"].reshape(-1), n * delta * x, (lx + 2) // 3,
+                         st["a2_t"].reshape(-1), n, st["a2_t"].shape[1], p, delta, x, ne, chunk_idx=chunk_idx)
+
+
 @pytest.mark.parametrize("num_entries,bits,seed", [(1 << 24, 1, 1), (1 << 20, 10, 2)])
 def test_simple_end_to_end(num_entries, bits, seed):
-    rng = np.random.default_rng(seed)
-    prm = pick_params(num_entries, bits, SEC_PARAM, LOGQ)
+    rng, prm, data, info, delta, a_1, a_2, st = prepare(num_entries, bits, seed)
     if bits == 1:
         assert (prm["l"], prm["m"], prm["p"]) == (29, 65536, 512)              # the shape SURVEY 8(d) quotes for this test
-    data = rng.integers(0, min(1 << bits, 256), num_entries, dtype=np.uint8)   # the reference's iterator yields u8 items
-    info, db = db_with_data(num_entries, bits, prm, data)
-    n, l, m, p, x, ne = prm["n"], prm["l"], prm["m"], prm["p"], info["x"], info["ne"]
-    delta = math.ceil(LOGQ / math.log2(p))
-    a_1 = rng.integers(0, Q, (m, n), dtype=np.uint64).astype(U32)              # init(), doublepir.rs:46-51
-    a_2 = rng.integers(0, Q, (l // x, n), dtype=np.uint64).astype(U32)
-    st = O.dpir_setup(db, l, m, a_1, n, a_2, p, delta, x)                      # server_state = [h1_sq, a2_t], hint = [h2]
-    cols = (m + 2) // 3
-    lx = l // x
     for i in [0, num_entries - 1] + [int(v) for v in rng.integers(0, num_entries, 3)]:
         client, qmsg = query(i, a_1, a_2, prm, info, rng)
-        ans = O.dpir_answer(st["db_sq"].reshape(-1), l, cols, [qmsg], st["h1_sq"].reshape(-1), n * delta * x, (lx + 2) // 3,
-                            st["a2_t"].reshape(-1), n, st["a2_t"].shape[1], p, delta, x, ne)
-        assert len(ans) == 1 + 2 * (ne // x)
+        ans = run_answer(st, prm, info, delta, [qmsg])
+        assert len(ans) == 1 + 2 * (info["ne"] // info["x"])
         got = recover(i, st["h2"], qmsg, ans, a_2, client, prm, info)
         assert got == int(data[i]), (i, got, int(data[i]))
+
+
+def test_batched_end_to_end():
+    # doublepir.rs:526-606 batched_end_to_end_test: two queries in one answer(), each selecting a column from ITS batch of
+    # rows (rows 0..13 and 14..28 of the 29); one shared h1, per-query (a_2, h_2) pairs at offset 2 * batch_index
+    num_entries, bits = 1 << 24, 1
+    rng, prm, data, info, delta, a_1, a_2, st = prepare(num_entries, bits, 1)
+    batch_sz = 14 * 65536 * 9
+    for _ in range(2):
+        i1 = int(rng.integers(0, batch_sz))
+        i2 = (i1 + batch_sz) % num_entries
+        idxs = sorted([i1, i2])
+        qs = [query(i, a_1, a_2, prm, info, rng) for i in idxs]
+        ans = run_answer(st, prm, info, delta, [q for _, q in qs])
+        assert len(ans) == 1 + 2 * 2
+        for b, (i, (client, qmsg)) in enumerate(zip(idxs, qs)):
+            assert recover(i, st["h2"], qmsg, ans, a_2, client, prm, info, batch_index=b) == int(data[i]), (b, i)
+
+
+def test_chunked_end_to_end():
+    # doublepir.rs:607-716 chunked_end_to_end_test: the database rows split over two servers, each answers from its slice
+    # alone; the first message and every h_2 add up across servers, the a_2 messages are identical on both.  This is the
+    # model for sharding DoublePIR over GPUs with no collective (DESIGN section 6).
+    num_entries, bits = 1 << 24, 1
+    rng, prm, data, info, delta, a_1, a_2, st = prepare(num_entries, bits, 1)
+    batch_sz = 14 * 65536 * 9
+    i1 = int(rng.integers(0, batch_sz))
+    idxs = sorted([i1, (i1 + batch_sz) % num_entries])
+    qs = [query(i, a_1, a_2, prm, info, rng) for i in idxs]
+    full = None
+    for chunk in range(2):
+        resp = run_answer(st, prm, info, delta, [q for _, q in qs], chunk_idx=chunk)
+        assert len(resp) == 1 + 2 * 2
+        if full is None:
+            full = [r.copy() for r in resp]
+        else:
+            for k in range(len(resp)):
+                if k % 2 == 1:
+                    assert np.array_equal(full[k], resp[k])        # a_2 = h_1 * q_2 does not depend on the rows held
+                    continue
+                full[k] = full[k] + resp[k]                        # wrapping u32
+    whole = run_answer(st, prm, info, delta, [q for _, q in qs])
+    for a, b in zip(full, whole):
+        assert np.array_equal(a, b)                                # the per-server answers add up to the one-server answer
+    for b, (i, (client, qmsg)) in enumerate(zip(idxs, qs)):
+        assert recover(i, st["h2"], qmsg, full, a_2, client, prm, info, batch_index=b) == int(data[i]), (b, i)
