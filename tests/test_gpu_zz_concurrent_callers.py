@@ -156,3 +156,43 @@ def test_workspace_reserved_up_front(s8two):
     finally:
         G2.close()
     assert np.array_equal(S.process_query(G, g, q, gdb), ref)
+
+
+def test_native_threads_share_database_passes(tmp_path):
+    """The same measurement from native threads (tests/cpp/concurrent_callers.cpp): 32 std::threads, 8 requests each, every
+    request a serialized query through b200pir_process_query_bytes — what lib/server's workers would call.  No interpreter
+    lock between the callers and the library."""
+    import os
+    import subprocess
+    _gpu()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "concurrent_callers")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O2", "-pthread", "-o", exe,
+                           os.path.join(root, "tests", "cpp", "concurrent_callers.cpp"), "-L" + os.path.join(root, "sdk_b200"),
+                           "-lb200pir", "-Wl,-rpath," + os.path.join(root, "sdk_b200")])
+    P = O.Params.named("S8")
+    n, per_worker = 32, 8
+    kw = P.kw
+    order = ["n", "nu_1", "nu_2", "p", "q2_bits", "t_gsw", "t_conv", "t_exp_left", "t_exp_right", "instances", "db_item_size", "version"]
+    (tmp_path / "params.txt").write_text(" ".join(str(int(kw[k])) for k in order) + "\n")
+    clients = [O.Client(P, 5), O.Client(P, 4242)]
+    for c, cl in enumerate(clients):
+        cl.generate_keys()
+        (tmp_path / ("pp%d.bin" % c)).write_bytes(cl.pp_bytes().tobytes())
+    idxs = [(7919 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
+    blobs = []
+    for k, i in enumerate(idxs):
+        clients[k % 2].generate_query(i)
+        blobs.append(clients[k % 2].query_bytes().tobytes())
+    (tmp_path / "queries.bin").write_bytes(b"".join(blobs))
+    out = subprocess.check_output([exe, str(tmp_path), str(n), str(per_worker)], text=True, timeout=600)
+    serial_s, conc_s, passes, queries, bad = out.split()
+    serial_s, conc_s, passes, queries, bad = float(serial_s), float(conc_s), int(passes), int(queries), int(bad)
+    rb = P.response_bytes()
+    resp = np.frombuffer((tmp_path / "responses.bin").read_bytes(), dtype=np.uint8).reshape(n, rb)
+    for k, i in enumerate(idxs):
+        assert np.array_equal(clients[k % 2].decode_response(resp[k].copy()), P.db_plain_item(SEED, i)), k
+    assert bad == 0, bad
+    assert queries == n * per_worker, queries
+    assert passes <= n * per_worker // 4, ("database passes", passes, "queries", queries)
+    assert serial_s / conc_s >= 3.0, ("serial s", serial_s, "concurrent s", conc_s, "passes", passes)
