@@ -106,7 +106,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -115,6 +115,13 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=15.0):
+        """nvidia-smi needs up to seconds to start (longer on an 8-GPU box): do not enter the timed region before its first line,
+        or a short region ends unsampled."""
+        t = time.time()
+        while self.proc is not None and not self.lines and self.proc.poll() is None and time.time() - t < timeout:
+            time.sleep(0.02)
 
     def stop(self, t0, t1):
         if self.proc:
@@ -331,6 +338,7 @@ def kernel_workload(args):
 
     sampler = ClockSampler(0)
     sampler.start()
+    sampler.wait_first()
     t0 = time.time()
     if args.workload == "dpir":
         rows, cols = 1 << 24, 1366                                   # 2^24 x ceil(2^12 / 3) u32 = 91.7 GB, larger than L2 by far
@@ -724,8 +732,10 @@ def main():
     barrier()
     launches0 = LIB.b200pir_kernel_launches()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
+    if rank == 0:                    # rank 0 prints the line; N concurrent nvidia-smi processes only slow each other down
+        sampler.start()
+        sampler.wait_first()
+    time.sleep(0.1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
