@@ -22,6 +22,26 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTED), sorted(declared ^ set(L.EXPORTED))
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/b200pir.h must compile as C99 (no C++-isms, no torch or CUDA types) and a C program must
+    link against the library (the native callers in tests/cpp compile the same way on the GPU box)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "b200pir.h"\n#include <stdio.h>\n'
+                   'int main(void) { b200pir_params p; (void)p; printf("%d %s\\n", b200pir_device_count() >= 0, '
+                   'b200pir_last_error() ? "ok" : "null"); return 0; }\n')
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o",
+                           str(tmp_path / "abi"), str(src), "-L" + os.path.join(ROOT, "sdk_b200"), "-lb200pir",
+                           "-Wl,-rpath," + os.path.join(ROOT, "sdk_b200")])
+    out = subprocess.check_output([str(tmp_path / "abi")], text=True).split()
+    assert out == ["1", "ok"]
+    for cpp in ("concurrent_callers.cpp", "host_mirror_smoke.cpp"):          # the native test programs at least compile here
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-std=c++17", "-O1", "-pthread", "-Wall", "-o", str(tmp_path / cpp[:-4]),
+                               os.path.join(ROOT, "tests", "cpp", cpp), "-L" + os.path.join(ROOT, "sdk_b200"), "-lb200pir",
+                               "-Wl,-rpath," + os.path.join(ROOT, "sdk_b200")])
+
+
 def test_no_cpu_fallback_without_gpu():
     import sdk_b200.spiral as S
     import sdk_b200._lib as L
