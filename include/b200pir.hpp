@@ -29,6 +29,8 @@ struct Params {
   ~Params() { b200pir_ctx_destroy(ctx); }
   Params(const Params&) = delete;
   Params& operator=(const Params&) = delete;
+  // workspace for `queries` concurrent queries allocated now instead of on first use
+  void reserve(size_t queries) { check(b200pir_ctx_reserve(ctx, queries, (size_t)1 << p.nu_2)); }
   size_t dim0() const { return (size_t)1 << p.nu_1; }
   size_t num_per() const { return (size_t)1 << p.nu_2; }
   size_t slices() const { return p.instances * p.n * p.n; }
@@ -55,6 +57,10 @@ struct PublicParameters {
     check(b200pir_pp_create(params.ctx, v_packing.data(), v_expansion_left ? v_expansion_left->data() : nullptr,
                             v_expansion_right ? v_expansion_right->data() : nullptr,
                             v_conversion ? v_conversion->data() : nullptr, &h));
+  }
+  // PublicParameters::deserialize (client.rs:212-259): seed || rows 1.. of every matrix
+  PublicParameters(const Params& params, const uint8_t* data, size_t len) {
+    check(b200pir_pp_create_from_bytes(params.ctx, data, len, &h));
   }
   ~PublicParameters() { b200pir_pp_destroy(h); }
   PublicParameters(const PublicParameters&) = delete;
@@ -121,6 +127,30 @@ inline std::vector<uint8_t> process_query(const Params& params, const PublicPara
                               query.v_buf.empty() ? nullptr : query.v_buf.data(),
                               query.v_ct.empty() ? nullptr : query.v_ct.data(), out.data(), &n));
   out.resize(n);
+  return out;
+}
+// Query::deserialize + process_query on `count` serialized queries back to back (bin/server.rs:99-141); both query modes
+inline std::vector<uint8_t> process_query_bytes(const Params& params, const PublicParameters& public_params, const uint8_t* queries,
+                                                size_t len, size_t count, const Database& db) {
+  std::vector<uint8_t> out(count * params.response_bytes);
+  size_t each = 0;
+  check(b200pir_process_query_bytes(params.ctx, db.h, public_params.h, queries, len, count, out.data(), &each));
+  return out;
+}
+// concurrent queries of different clients in one database pass: public_params[i] belongs to the sender of queries[i]
+inline std::vector<std::vector<uint8_t>> process_queries(const Params& params, const std::vector<const PublicParameters*>& public_params,
+                                                         const std::vector<const Query*>& queries, const Database& db) {
+  if (public_params.size() != queries.size()) throw std::runtime_error("b200pir: one PublicParameters per query");
+  std::vector<std::vector<uint8_t>> out(queries.size(), std::vector<uint8_t>(params.response_bytes));
+  std::vector<b200pir_pp*> pps;
+  std::vector<const uint64_t*> cts;
+  std::vector<uint8_t*> outs;
+  for (size_t i = 0; i < queries.size(); i++) {
+    pps.push_back(public_params[i]->h);
+    cts.push_back(queries[i]->ct.data());
+    outs.push_back(out[i].data());
+  }
+  check(b200pir_process_queries(params.ctx, db.h, pps.data(), cts.data(), queries.size(), outs.data()));
   return out;
 }
 }  // namespace server
