@@ -158,6 +158,29 @@ def test_workspace_reserved_up_front(s8two):
     assert np.array_equal(S.process_query(G, g, q, gdb), ref)
 
 
+def test_single_serialized_query_takes_the_coalesced_path():
+    """One serialized query per call (what the /private-read handler sends) goes through the combiner like b200pir_process_query
+    does: same bytes as the deserialized query through process_query, and the combiner's counters move."""
+    from test_gpu_parity import setup_case
+    S, P, _, _, db, G, gdb, _ = setup_case("T")
+    cl = O.Client(P, 31337)
+    pp = cl.generate_keys()
+    gpp = S.PublicParameters.deserialize(G, cl.pp_bytes())
+    try:
+        for idx in (0, 9, P.dim0 * P.num_per - 1):
+            q = cl.generate_query(idx)
+            qb = cl.query_bytes()
+            b0, q0 = S.coalesce_stats(G)
+            got = S.process_query_bytes(G, gpp, qb, gdb)
+            b1, q1 = S.coalesce_stats(G)
+            assert (b1 - b0, q1 - q0) == (1, 1)
+            assert got.shape == (1, G.response_bytes)
+            assert np.array_equal(got[0], P.process_query(pp, q, db)), idx
+            assert np.array_equal(got[0], S.process_query(G, gpp, S.Query(ct=q["ct"]), gdb)), idx
+    finally:
+        gpp.close()
+
+
 def test_native_threads_share_database_passes(tmp_path):
     """The same measurement from native threads (tests/cpp/concurrent_callers.cpp): 32 std::threads, 8 requests each, every
     request a serialized query through b200pir_process_query_bytes — what lib/server's workers would call.  No interpreter
@@ -196,26 +219,3 @@ def test_native_threads_share_database_passes(tmp_path):
     assert queries == n * per_worker, queries
     assert passes <= n * per_worker // 4, ("database passes", passes, "queries", queries)
     assert serial_s / conc_s >= 3.0, ("serial s", serial_s, "concurrent s", conc_s, "passes", passes)
-
-
-def test_single_serialized_query_takes_the_coalesced_path():
-    """One serialized query per call (what the /private-read handler sends) goes through the combiner like b200pir_process_query
-    does: same bytes as the deserialized query through process_query, and the combiner's counters move."""
-    from test_gpu_parity import setup_case
-    S, P, _, _, db, G, gdb, _ = setup_case("T")
-    cl = O.Client(P, 31337)
-    pp = cl.generate_keys()
-    gpp = S.PublicParameters.deserialize(G, cl.pp_bytes())
-    try:
-        for idx in (0, 9, P.dim0 * P.num_per - 1):
-            q = cl.generate_query(idx)
-            qb = cl.query_bytes()
-            b0, q0 = S.coalesce_stats(G)
-            got = S.process_query_bytes(G, gpp, qb, gdb)
-            b1, q1 = S.coalesce_stats(G)
-            assert (b1 - b0, q1 - q0) == (1, 1)
-            assert got.shape == (1, G.response_bytes)
-            assert np.array_equal(got[0], P.process_query(pp, q, db)), idx
-            assert np.array_equal(got[0], S.process_query(G, gpp, S.Query(ct=q["ct"]), gdb)), idx
-    finally:
-        gpp.close()
