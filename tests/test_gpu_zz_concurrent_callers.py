@@ -35,74 +35,6 @@ def s8two():
     G.close()
 
 
-def test_concurrent_callers_share_database_passes(s8two):
-    """32 host threads, each serving 8 requests back to back through b200pir_process_query on ONE context, the two clients
-    alternating: every response identical to the serial call's and decoding to the planted item, far fewer database passes
-    than queries, and at least 3x the serial queries/s (one 8 GiB pass serves 16 callers; a lone caller is never made to
-    wait).  The timed loops call the C entry point directly (ctypes releases the GIL for the call), the way the reference's
-    Rust workers would; the comparison of the bytes happens afterwards."""
-    from sdk_b200._lib import LIB
-    S, P, G, gdb, clients = s8two
-    n, per_worker = 32, 8
-    who = [clients[k % 2] for k in range(n)]
-    idxs = [(7919 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
-    cts = [np.ascontiguousarray(cl.generate_query(i)["ct"], dtype=np.uint64) for (cl, _), i in zip(who, idxs)]
-    serial = [S.process_query(G, g, S.Query(ct=ct), gdb).copy() for (_, g), ct in zip(who, cts)]   # also warms the workspace up
-    for k, ((cl, _), i) in enumerate(zip(who, idxs)):
-        assert np.array_equal(cl.decode_response(serial[k]), P.db_plain_item(SEED, i)), k
-    rb = G.response_bytes
-    outs = np.zeros((n, per_worker, rb), dtype=np.uint8)
-    rcs = np.zeros((n, per_worker), dtype=np.int64)
-
-    def call(k, j):
-        return LIB.b200pir_process_query(G._h, gdb._h, who[k][1]._h, cts[k].ctypes.data, None, None, outs[k, j].ctypes.data, None)
-
-    def serial_round():
-        t0 = time.perf_counter()
-        for j in range(per_worker):
-            for k in range(n):
-                rcs[k, j] = call(k, j)
-        return time.perf_counter() - t0
-
-    def concurrent_round():
-        start = threading.Barrier(n + 1)
-
-        def worker(k):
-            start.wait()
-            for j in range(per_worker):
-                rcs[k, j] = call(k, j)
-
-        threads = [threading.Thread(target=worker, args=(k,)) for k in range(n)]
-        for t in threads:
-            t.start()
-        start.wait()
-        t0 = time.perf_counter()
-        for t in threads:
-            t.join()
-        return time.perf_counter() - t0
-
-    def check_outputs(what):
-        assert not rcs.any(), (what, rcs)
-        for k in range(n):
-            for j in range(per_worker):
-                assert np.array_equal(outs[k, j], serial[k]), (what, k, j)
-        outs[:] = 0
-
-    t_serial = serial_round()
-    check_outputs("serial")
-    best, passes = None, None
-    for _ in range(3):                                        # best of three: host scheduling noise only ever slows a round
-        b0, q0 = S.coalesce_stats(G)
-        t = concurrent_round()
-        b1, q1 = S.coalesce_stats(G)
-        check_outputs("concurrent")
-        assert q1 - q0 == n * per_worker, (q1 - q0)
-        assert b1 - b0 <= n * per_worker // 4, ("database passes", b1 - b0, "queries", q1 - q0)
-        if best is None or t < best:
-            best, passes = t, b1 - b0
-    assert t_serial / best >= 3.0, ("serial s", t_serial, "concurrent s", best, "passes", passes)
-
-
 def test_coalescing_can_be_switched_off(s8two):
     """Option "coalesce" = 0: strictly serial calls (one pass per query), same bytes."""
     S, P, G, gdb, clients = s8two
@@ -219,3 +151,71 @@ def test_native_threads_share_database_passes(tmp_path):
     assert queries == n * per_worker, queries
     assert passes <= n * per_worker // 4, ("database passes", passes, "queries", queries)
     assert serial_s / conc_s >= 3.0, ("serial s", serial_s, "concurrent s", conc_s, "passes", passes)
+
+
+def test_concurrent_callers_share_database_passes(s8two):
+    """32 host threads, each serving 8 requests back to back through b200pir_process_query on ONE context, the two clients
+    alternating: every response identical to the serial call's and decoding to the planted item, far fewer database passes
+    than queries, and at least 3x the serial queries/s (one 8 GiB pass serves 16 callers; a lone caller is never made to
+    wait).  The timed loops call the C entry point directly (ctypes releases the GIL for the call), the way the reference's
+    Rust workers would; the comparison of the bytes happens afterwards."""
+    from sdk_b200._lib import LIB
+    S, P, G, gdb, clients = s8two
+    n, per_worker = 32, 8
+    who = [clients[k % 2] for k in range(n)]
+    idxs = [(7919 * k + 11) % (P.dim0 * P.num_per) for k in range(n)]
+    cts = [np.ascontiguousarray(cl.generate_query(i)["ct"], dtype=np.uint64) for (cl, _), i in zip(who, idxs)]
+    serial = [S.process_query(G, g, S.Query(ct=ct), gdb).copy() for (_, g), ct in zip(who, cts)]   # also warms the workspace up
+    for k, ((cl, _), i) in enumerate(zip(who, idxs)):
+        assert np.array_equal(cl.decode_response(serial[k]), P.db_plain_item(SEED, i)), k
+    rb = G.response_bytes
+    outs = np.zeros((n, per_worker, rb), dtype=np.uint8)
+    rcs = np.zeros((n, per_worker), dtype=np.int64)
+
+    def call(k, j):
+        return LIB.b200pir_process_query(G._h, gdb._h, who[k][1]._h, cts[k].ctypes.data, None, None, outs[k, j].ctypes.data, None)
+
+    def serial_round():
+        t0 = time.perf_counter()
+        for j in range(per_worker):
+            for k in range(n):
+                rcs[k, j] = call(k, j)
+        return time.perf_counter() - t0
+
+    def concurrent_round():
+        start = threading.Barrier(n + 1)
+
+        def worker(k):
+            start.wait()
+            for j in range(per_worker):
+                rcs[k, j] = call(k, j)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(n)]
+        for t in threads:
+            t.start()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in threads:
+            t.join()
+        return time.perf_counter() - t0
+
+    def check_outputs(what):
+        assert not rcs.any(), (what, rcs)
+        for k in range(n):
+            for j in range(per_worker):
+                assert np.array_equal(outs[k, j], serial[k]), (what, k, j)
+        outs[:] = 0
+
+    t_serial = serial_round()
+    check_outputs("serial")
+    best, passes = None, None
+    for _ in range(3):                                        # best of three: host scheduling noise only ever slows a round
+        b0, q0 = S.coalesce_stats(G)
+        t = concurrent_round()
+        b1, q1 = S.coalesce_stats(G)
+        check_outputs("concurrent")
+        assert q1 - q0 == n * per_worker, (q1 - q0)
+        assert b1 - b0 <= n * per_worker // 4, ("database passes", b1 - b0, "queries", q1 - q0)
+        if best is None or t < best:
+            best, passes = t, b1 - b0
+    assert t_serial / best >= 3.0, ("serial s", t_serial, "concurrent s", best, "passes", passes)
