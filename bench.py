@@ -608,6 +608,8 @@ def main():
     # the peers: they last read that set in step k - NBUF; barrier(k - 1) (a 4-byte all-reduce each rank issues after its
     # pushes of step k - 1) has completed before the push starts, hence every rank has issued its pushes of step k - 1, and
     # those are stream-ordered after that rank's first dimension of step k - 1 - (pipelined ? 1 : 0) >= k - NBUF.
+    # (tests/test_exchange_protocol_sim.py replays this schedule with random timings: no hazard with three sets; two would also
+    # do, but only thanks to the survivors' all-gather, which this argument does not rely on.)
     TL = []                                         # --timeline: (label, step, CUDA event) in stream order
     tl_on = [False]
 
