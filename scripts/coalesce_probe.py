@@ -2,13 +2,13 @@
 then 32 threads x 4 requests through b200pir_process_query."""
 import os, sys, threading, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np
-import oracle_lib as O
 import sdk_b200.spiral as S
 
-P = O.Params.named("S8")
-G = S.Params(**P.kw)
+S8 = dict(n=2, nu_1=9, nu_2=8, p=256, q2_bits=22, t_gsw=8, t_conv=4, t_exp_left=8, t_exp_right=8, instances=1, db_item_size=8192,
+          version=0)
+G = S.Params(**S8)
 gdb = S.Database(G); gdb.fill_synthetic(0xB1755)
 rng = np.random.default_rng(1)
 def rnd(n):
